@@ -1,0 +1,203 @@
+/* libngpde -- C ABI of the B200-native message-passing hot path of NeuralGraphPDE.jl.
+ *
+ * The reference has no FFI of its own: its hot path is the Julia call chain
+ *     layer(x, ps, st)  ->  GraphNeuralNetworks.propagate  ->  NNlib.gather / Lux.Dense / NNlib.scatter
+ * (/root/reference/src/layers.jl:98-112, 200-239, 312-332, 390-422, 509-547).  This header is the boundary a
+ * Julia `ccall` shim or the Python/ctypes mirror (neuralgraphpde.jl_b200/) binds instead of
+ * that chain.  Plain pointers and sizes only; every tensor is caller-owned DEVICE memory, float32, laid out
+ * as Julia stores it: a feature matrix `(D, items)` column-major == C `[items][D]` row-major; a Lux Dense
+ * weight `(out, in)` column-major == C `[in][out]`; parameters of one MLP are the flat ComponentArray
+ * segment `weight_1, bias_1, weight_2, bias_2, ...`.
+ *
+ * Every function returns 0 on success or a negative NGPDE_ERR_* code; `ngpde_last_error()` returns a
+ * thread-local message.  Calls are asynchronous on the caller-supplied `cudaStream_t` (passed as void*)
+ * except graph construction, which synchronises that stream once.  No C++ exceptions cross the boundary.
+ */
+#ifndef NGPDE_H
+#define NGPDE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGPDE_VERSION 100
+
+/* status codes */
+#define NGPDE_OK 0
+#define NGPDE_ERR_INVALID (-1) /* bad argument (mirrors the reference's @assert failures, layers.jl:204-207) */
+#define NGPDE_ERR_CUDA (-2)    /* a CUDA runtime call failed */
+#define NGPDE_ERR_WORKSPACE (-3) /* workspace too small */
+#define NGPDE_ERR_UNSUPPORTED (-4)
+
+/* activation functions of a Lux Dense layer (NNlib names) */
+enum {
+  NGPDE_ACT_IDENTITY = 0,
+  NGPDE_ACT_RELU = 1,
+  NGPDE_ACT_TANH = 2,
+  NGPDE_ACT_SIGMOID = 3,
+  NGPDE_ACT_SWISH = 4,
+  NGPDE_ACT_GELU = 5, /* NNlib 0.8 gelu: tanh approximation */
+  NGPDE_ACT_SOFTPLUS = 6,
+  NGPDE_ACT_ELU = 7,
+  NGPDE_ACT_LEAKYRELU = 8 /* slope 0.01 */
+};
+
+/* aggregation operators of propagate(..., aggr) -- NNlib.scatter semantics: sequential in stored edge
+ * order per destination; identity 0 / 0 / -Inf / +Inf for isolated nodes; mean = sum / float(count). */
+enum { NGPDE_AGGR_SUM = 0, NGPDE_AGGR_MEAN = 1, NGPDE_AGGR_MAX = 2, NGPDE_AGGR_MIN = 3 };
+
+/* layer families (/root/reference/src/layers.jl) */
+enum {
+  NGPDE_EXPLICIT_EDGE_CONV = 0, /* :84-112  */
+  NGPDE_VMH_CONV = 1,           /* :295-332 */
+  NGPDE_MPPDE_CONV = 2,         /* :377-422 */
+  NGPDE_GNO_CONV = 3            /* :485-547 */
+};
+
+/* index arrays handed to ngpde_graph_create */
+enum { NGPDE_IDX_I32 = 0, NGPDE_IDX_I64 = 1 };
+
+/* integer arrays a graph handle exposes (ngpde_graph_array) -- part of the bit-exact index contract */
+enum {
+  NGPDE_GA_ROWPTR = 0,   /* int32 [N+1]  dst-sorted CSR row pointers                                  */
+  NGPDE_GA_SRC = 1,      /* int32 [E]    source of the k-th edge in CSR order                          */
+  NGPDE_GA_DST = 2,      /* int32 [E]    destination of the k-th edge in CSR order                     */
+  NGPDE_GA_PERM = 3,     /* int32 [E]    original COO position of the k-th CSR edge (stable sort)      */
+  NGPDE_GA_TPTR = 4,     /* int32 [N+1]  src-sorted transpose pointers                                 */
+  NGPDE_GA_TPOS = 5,     /* int32 [E]    CSR position of the k-th edge in src-sorted order (stable)    */
+  NGPDE_GA_UNITS32 = 6,  /* int32 [U+1]  work-unit node boundaries for 32-edge tiles                   */
+  NGPDE_GA_UNITS64 = 7,  /*              ... 64-edge tiles                                             */
+  NGPDE_GA_UNITS128 = 8, /*              ... 128-edge tiles                                            */
+  NGPDE_GA_GCN_COLPTR = 9,  /* int32 [N+1]  merged (dst, ascending src) adjacency, see ngpde_gcn_*     */
+  NGPDE_GA_GCN_ROWVAL = 10, /* int32 [nnz]                                                             */
+  NGPDE_GA_GCN_TPTR = 11,   /* int32 [N+1]  its transpose (src, ascending dst)                         */
+  NGPDE_GA_GCN_TPOS = 12    /* int32 [nnz]  merged-entry index of the k-th transposed entry            */
+};
+
+#define NGPDE_MAX_LAYERS 8
+
+/* A Lux `Chain` of `Dense` layers (or one bare `Dense`): layer l maps dims[l] -> dims[l+1]. */
+typedef struct {
+  int32_t n_layers;
+  int32_t dims[NGPDE_MAX_LAYERS + 1];
+  int32_t act[NGPDE_MAX_LAYERS];
+  int32_t has_bias[NGPDE_MAX_LAYERS];
+} ngpde_mlp;
+
+/* One message-passing layer call.  Which fields are read depends on `family`:
+ *
+ *  EXPLICIT_EDGE_CONV  m_k = phi([h_t; h_s; pos_s - pos_t]);           y = aggr_t(m)            (layers.jl:98-112)
+ *  VMH_CONV            m_k = phi([h_t; h_s - h_t; pos_s - pos_t]);     y = node([x; aggr_t(m)]) (layers.jl:312-332)
+ *      h = [x (dx cols, differentiable); snode[:, 0:dhs]],  pos = snode[:, dhs:dhs+dpos]
+ *  MPPDE_CONV          m_k = phi([x_t; x_s; S_t - S_s; e_k; theta_g(k)]); y = node([x; aggr(m); theta_g(i)])
+ *      S = snode (ds = dhs + dpos cols), theta indexed by (original edge position) / (E / G)      (layers.jl:390-422)
+ *  GNO_CONV            W_k = reshape(phi([S_t; S_s; e_k]), out, in);   m_k = W_k x_s;
+ *                      y = act(W_lin x + aggr_t(m) + b)   -- `node` is the 1-layer `linear` Dense (layers.jl:509-547)
+ */
+typedef struct {
+  int32_t family;
+  int32_t aggr;
+  int32_t dx;     /* width of the differentiable node state x                                  */
+  int32_t dhs;    /* static columns of snode that ride with h (EdgeConv / VMH), else part of S */
+  int32_t dpos;   /* position columns of snode (EdgeConv / VMH), else part of S                */
+  int32_t de;     /* width of edata                                                            */
+  int32_t dtheta; /* width of theta                                                            */
+  int32_t gno_in, gno_out;
+  ngpde_mlp phi;  /* edge MLP                                                                  */
+  ngpde_mlp node; /* gamma / psi / linear; n_layers == 0 for EXPLICIT_EDGE_CONV                */
+} ngpde_conv_desc;
+
+typedef struct {
+  const float* x;          /* [N][dx]                                   */
+  const float* snode;      /* [N][dhs + dpos] static node data, or NULL */
+  const float* edata;      /* [E][de] in ORIGINAL edge order, or NULL   */
+  const float* theta;      /* [G][dtheta], or NULL                      */
+  const float* phi_params; /* flat parameters of phi                    */
+  const float* node_params;/* flat parameters of gamma / psi / linear   */
+  float* mbar;             /* [N][dm] aggregated messages (written by forward, read by backward) */
+  float* y;                /* [N][dy] layer output (for EXPLICIT_EDGE_CONV this is mbar itself)  */
+  /* backward only */
+  const float* dy;         /* [N][dy] cotangent of y                    */
+  float* dx;               /* [N][dx] cotangent of x (overwritten)      */
+  float* dphi_params;      /* flat, overwritten                         */
+  float* dnode_params;     /* flat, overwritten                         */
+} ngpde_conv_io;
+
+typedef struct ngpde_graph* ngpde_graph_t;
+
+/* ---- library ---- */
+int ngpde_version(void);
+const char* ngpde_last_error(void);
+
+/* ---- graph handle: replaces GNNGraph's per-call gather/scatter index use and GCNConv's per-call
+ * add_self_loops / degree / adjacency_matrix (layers.jl:210-225).  Builds, on the device: the stable
+ * dst-sorted CSR, the edge permutation, in-degrees, the src-sorted transpose and the work-unit lists.
+ * `src`/`dst` are E indices (host or device memory, int32 or int64, `index_base` 0 or 1) in the stored
+ * COO order.  `num_graphs` equal-sized graphs are assumed laid out contiguously (layers.jl:410,418). ---- */
+int ngpde_graph_create(ngpde_graph_t* out, int64_t num_nodes, int64_t num_edges, const void* src, const void* dst,
+                       int32_t index_dtype, int32_t index_base, int32_t indices_on_device, int64_t num_graphs,
+                       void* stream);
+int ngpde_graph_destroy(ngpde_graph_t g);
+int ngpde_graph_array(ngpde_graph_t g, int32_t which, int32_t with_self_loops, const void** device_ptr, int64_t* len);
+/* copy one of those arrays into caller-owned device memory holding at least `capacity` int32 */
+int ngpde_graph_array_copy(ngpde_graph_t g, int32_t which, int32_t with_self_loops, int32_t* dst_device,
+                           int64_t capacity, void* stream);
+int64_t ngpde_graph_num_nodes(ngpde_graph_t g);
+int64_t ngpde_graph_num_edges(ngpde_graph_t g);
+
+/* ---- bare propagate(copy_xj | e_mul_xj, g, aggr; xj = x [, e = w]) on the scatter path: ordered,
+ * atomic-free aggregation (call sites layers.jl:228-232, 656).  w may be NULL; it is [E] in ORIGINAL order. ---- */
+int ngpde_aggregate(ngpde_graph_t g, int32_t aggr, const float* x, int32_t d, const float* w, float* out, void* stream);
+
+/* ---- MLP message-passing layers ---- */
+size_t ngpde_conv_workspace_bytes(ngpde_graph_t g, const ngpde_conv_desc* desc, int32_t backward);
+int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_conv_io* io, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_conv_io* io, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* per-family names (each checks desc->family and forwards to the two calls above) */
+int ngpde_explicit_edge_conv_forward(ngpde_graph_t, const ngpde_conv_desc*, const ngpde_conv_io*, void*, size_t, void*);
+int ngpde_explicit_edge_conv_backward(ngpde_graph_t, const ngpde_conv_desc*, const ngpde_conv_io*, void*, size_t, void*);
+int ngpde_vmh_conv_forward(ngpde_graph_t, const ngpde_conv_desc*, const ngpde_conv_io*, void*, size_t, void*);
+int ngpde_vmh_conv_backward(ngpde_graph_t, const ngpde_conv_desc*, const ngpde_conv_io*, void*, size_t, void*);
+int ngpde_mppde_conv_forward(ngpde_graph_t, const ngpde_conv_desc*, const ngpde_conv_io*, void*, size_t, void*);
+int ngpde_mppde_conv_backward(ngpde_graph_t, const ngpde_conv_desc*, const ngpde_conv_io*, void*, size_t, void*);
+int ngpde_gno_conv_forward(ngpde_graph_t, const ngpde_conv_desc*, const ngpde_conv_io*, void*, size_t, void*);
+int ngpde_gno_conv_backward(ngpde_graph_t, const ngpde_conv_desc*, const ngpde_conv_io*, void*, size_t, void*);
+
+/* ---- GCNConv (layers.jl:200-239), CPU sparse-matmul semantics of GNN.jl: merged duplicate edges,
+ * ascending-source accumulation order, multiply and add rounded separately.
+ *   y = act(W (c .* A^T (c .* x)) + b),   c = 1/sqrt(in-degree),   W applied first when out < in.
+ * edge_weight: NULL or [E] (original order; self-loop weights of 1 are appended internally, layers.jl:215).
+ * graph_weight: NULL or the graph's own stored weights [E], used when use_edge_weight != 0 (w_mul_xj).
+ * agg_buf: [N][min(in,out)] scratch kept for the backward; lin_buf: [N][min(in,out)] scratch. ---- */
+typedef struct {
+  int32_t in_chs, out_chs;
+  int32_t act;
+  int32_t has_bias;
+  int32_t add_self_loops;
+  int32_t use_edge_weight;
+} ngpde_gcn_desc;
+
+size_t ngpde_gcn_workspace_bytes(ngpde_graph_t g, const ngpde_gcn_desc* desc, int32_t backward);
+int ngpde_gcn_conv_forward(ngpde_graph_t g, const ngpde_gcn_desc* desc, const float* x, const float* weight,
+                           const float* bias, const float* edge_weight, const float* graph_weight, float* y,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int ngpde_gcn_conv_backward(ngpde_graph_t g, const ngpde_gcn_desc* desc, const float* x, const float* weight,
+                            const float* bias, const float* edge_weight, const float* graph_weight, const float* y,
+                            const float* dy, float* dx, float* dweight, float* dbias, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ---- fixed-step ODE glue (the immediate caller of the path):
+ * out = u + sum_i coef[i] * k[i]  over n floats, nk <= 8 stage arrays.  ---- */
+int ngpde_axpy_stages(float* out, const float* u, const float* const* k, const float* coef, int32_t nk, int64_t n,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGPDE_H */

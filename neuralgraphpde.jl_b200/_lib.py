@@ -1,0 +1,120 @@
+"""ctypes binding of libngpde.so (the C ABI in include/ngpde.h).
+
+The product path has no fallback: if the shared library is missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libngpde.so")
+
+MAX_LAYERS = 8
+
+# enums of include/ngpde.h
+ACT = {"identity": 0, "relu": 1, "tanh": 2, "sigmoid": 3, "swish": 4, "gelu": 5, "softplus": 6, "elu": 7,
+       "leakyrelu": 8}
+AGGR = {"+": 0, "sum": 0, "mean": 1, "max": 2, "min": 3}
+FAMILY = {"explicit_edge_conv": 0, "vmh_conv": 1, "mppde_conv": 2, "gno_conv": 3}
+IDX_I32, IDX_I64 = 0, 1
+GA = {"rowptr": 0, "src": 1, "dst": 2, "perm": 3, "tptr": 4, "tpos": 5, "units32": 6, "units64": 7, "units128": 8,
+      "gcn_colptr": 9, "gcn_rowval": 10, "gcn_tptr": 11, "gcn_tpos": 12}
+
+EXPORTS = [
+    "ngpde_version", "ngpde_last_error", "ngpde_graph_create", "ngpde_graph_destroy", "ngpde_graph_array", "ngpde_graph_array_copy",
+    "ngpde_graph_num_nodes", "ngpde_graph_num_edges", "ngpde_aggregate", "ngpde_conv_workspace_bytes",
+    "ngpde_conv_forward", "ngpde_conv_backward", "ngpde_explicit_edge_conv_forward",
+    "ngpde_explicit_edge_conv_backward", "ngpde_vmh_conv_forward", "ngpde_vmh_conv_backward",
+    "ngpde_mppde_conv_forward", "ngpde_mppde_conv_backward", "ngpde_gno_conv_forward", "ngpde_gno_conv_backward",
+    "ngpde_gcn_workspace_bytes", "ngpde_gcn_conv_forward", "ngpde_gcn_conv_backward", "ngpde_axpy_stages",
+]
+
+
+class Mlp(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)), ("act", C.c_int32 * MAX_LAYERS),
+                ("has_bias", C.c_int32 * MAX_LAYERS)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("family", C.c_int32), ("aggr", C.c_int32), ("dx", C.c_int32), ("dhs", C.c_int32),
+                ("dpos", C.c_int32), ("de", C.c_int32), ("dtheta", C.c_int32), ("gno_in", C.c_int32),
+                ("gno_out", C.c_int32), ("phi", Mlp), ("node", Mlp)]
+
+
+class ConvIO(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("snode", C.c_void_p), ("edata", C.c_void_p), ("theta", C.c_void_p),
+                ("phi_params", C.c_void_p), ("node_params", C.c_void_p), ("mbar", C.c_void_p), ("y", C.c_void_p),
+                ("dy", C.c_void_p), ("dx", C.c_void_p), ("dphi_params", C.c_void_p), ("dnode_params", C.c_void_p)]
+
+
+class GcnDesc(C.Structure):
+    _fields_ = [("in_chs", C.c_int32), ("out_chs", C.c_int32), ("act", C.c_int32), ("has_bias", C.c_int32),
+                ("add_self_loops", C.c_int32), ("use_edge_weight", C.c_int32)]
+
+
+class NgpdeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libngpde.so; raise loudly when it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NgpdeError(f"{LIB_PATH} is missing: run `python neuralgraphpde.jl_b200/build.py` "
+                         "(or __graft_entry__.build()). There is no CPU fallback for the message-passing path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    lib.ngpde_version.restype = C.c_int
+    lib.ngpde_last_error.restype = C.c_char_p
+    lib.ngpde_graph_create.argtypes = [C.POINTER(vp), i64, i64, vp, vp, i32, i32, i32, i64, vp]
+    lib.ngpde_graph_destroy.argtypes = [vp]
+    lib.ngpde_graph_array.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(i64)]
+    lib.ngpde_graph_array_copy.argtypes = [vp, i32, i32, vp, i64, vp]
+    lib.ngpde_graph_num_nodes.argtypes = [vp]
+    lib.ngpde_graph_num_nodes.restype = i64
+    lib.ngpde_graph_num_edges.argtypes = [vp]
+    lib.ngpde_graph_num_edges.restype = i64
+    lib.ngpde_aggregate.argtypes = [vp, i32, vp, i32, vp, vp, vp]
+    lib.ngpde_conv_workspace_bytes.argtypes = [vp, C.POINTER(ConvDesc), i32]
+    lib.ngpde_conv_workspace_bytes.restype = sz
+    conv_sig = [vp, C.POINTER(ConvDesc), C.POINTER(ConvIO), vp, sz, vp]
+    for name in ("conv", "explicit_edge_conv", "vmh_conv", "mppde_conv", "gno_conv"):
+        getattr(lib, f"ngpde_{name}_forward").argtypes = conv_sig
+        getattr(lib, f"ngpde_{name}_backward").argtypes = conv_sig
+    lib.ngpde_gcn_workspace_bytes.argtypes = [vp, C.POINTER(GcnDesc), i32]
+    lib.ngpde_gcn_workspace_bytes.restype = sz
+    lib.ngpde_gcn_conv_forward.argtypes = [vp, C.POINTER(GcnDesc), vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.ngpde_gcn_conv_backward.argtypes = [vp, C.POINTER(GcnDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.ngpde_axpy_stages.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_float), i32, i64, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().ngpde_last_error().decode("utf-8", "replace")
+        raise NgpdeError(f"libngpde error {rc}: {msg}")
+
+
+def make_mlp(spec) -> Mlp:
+    """spec: list of (in, out, activation-name, has_bias)."""
+    m = Mlp()
+    if len(spec) > MAX_LAYERS:
+        raise NgpdeError(f"at most {MAX_LAYERS} Dense layers per MLP are supported, got {len(spec)}")
+    m.n_layers = len(spec)
+    for i, (din, dout, act, hb) in enumerate(spec):
+        if i > 0 and spec[i - 1][1] != din:
+            raise NgpdeError(f"DimensionMismatch: layer {i + 1} expects {din} inputs, previous layer emits {spec[i - 1][1]}")
+        m.dims[i] = din
+        m.dims[i + 1] = dout
+        if act not in ACT:
+            raise NgpdeError(f"unsupported activation {act!r}; supported: {sorted(ACT)}")
+        m.act[i] = ACT[act]
+        m.has_bias[i] = 1 if hb else 0
+    return m

@@ -1,0 +1,638 @@
+// Host side of the fused message-passing layers: recipe construction per layer family, shared-memory planning,
+// workspace layout, launches, and the extern "C" entry points declared in include/ngpde.h.
+#include <algorithm>
+#include <cstring>
+
+#include "ngpde_conv_kernels.cuh"
+
+namespace ngpde {
+namespace {
+
+// host copy of the sign table coef_dst (the device versions live in the kernels header)
+int coef_dst_host(int kind) { return kind == SEG_DST || kind == SEG_SMD || kind == SEG_DMS; }
+
+constexpr int kSmemTwoCtas = 113 * 1024;  // <= this: two CTAs per SM
+constexpr int kSmemMax = 227 * 1024;
+
+int make_mlp(const ngpde_mlp& m, MlpDev* out, const char* what) {
+  NGPDE_REQUIRE(m.n_layers >= 0 && m.n_layers <= NGPDE_MAX_LAYERS, "%s: n_layers=%d out of range", what, m.n_layers);
+  out->L = m.n_layers;
+  int off = 0;
+  for (int l = 0; l <= m.n_layers; ++l) {
+    NGPDE_REQUIRE(m.n_layers == 0 || m.dims[l] > 0, "%s: dims[%d]=%d must be positive", what, l, m.dims[l]);
+    out->dims[l] = m.dims[l];
+  }
+  for (int l = 0; l < m.n_layers; ++l) {
+    NGPDE_REQUIRE(m.act[l] >= NGPDE_ACT_IDENTITY && m.act[l] <= NGPDE_ACT_LEAKYRELU, "%s: unknown activation %d", what,
+                  m.act[l]);
+    out->act[l] = m.act[l];
+    out->w_off[l] = off;
+    off += m.dims[l] * m.dims[l + 1];
+    if (m.has_bias[l]) {
+      out->b_off[l] = off;
+      off += m.dims[l + 1];
+    } else {
+      out->b_off[l] = -1;
+    }
+  }
+  out->n_params = off;
+  return NGPDE_OK;
+}
+
+struct Plan {
+  Seg esegs[8];
+  int n_esegs = 0;
+  Seg nsegs[8];
+  int n_nsegs = 0;
+  MlpDev phi{}, node{};
+  int contract = 0;
+  int dm = 0;  // width of the aggregated message
+  int dy = 0;  // width of the layer output
+  int ds = 0;
+  bool has_node = false;
+  bool node_addend = false;
+  bool edge_need_dz0 = false;
+  bool edge_dst_side = false;
+};
+
+void push_seg(Seg* segs, int* n, int* row, int kind, int arr, int col, int width) {
+  if (width <= 0) return;
+  segs[*n] = Seg{kind, arr, col, width, *row};
+  *row += width;
+  ++*n;
+}
+
+int make_plan(const ngpde_graph* g, const ngpde_conv_desc& d, Plan* p) {
+  NGPDE_REQUIRE(g != nullptr, "null graph handle");
+  NGPDE_REQUIRE(d.dx > 0, "dx must be positive");
+  NGPDE_REQUIRE(d.dhs >= 0 && d.dpos >= 0 && d.de >= 0 && d.dtheta >= 0, "negative feature width");
+  NGPDE_REQUIRE(d.aggr >= NGPDE_AGGR_SUM && d.aggr <= NGPDE_AGGR_MIN, "unknown aggregation %d", d.aggr);
+  if (int rc = make_mlp(d.phi, &p->phi, "phi")) return rc;
+  if (int rc = make_mlp(d.node, &p->node, "node")) return rc;
+  NGPDE_REQUIRE(p->phi.L >= 1, "phi needs at least one Dense layer");
+  p->ds = d.dhs + d.dpos;
+  int row = 0, nrow = 0;
+  switch (d.family) {
+    case NGPDE_EXPLICIT_EDGE_CONV:  // layers.jl:104-106: vcat(hi..., hj..., posj - posi)
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_DST, ARR_X, 0, d.dx);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_DST, ARR_S, 0, d.dhs);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_SRC, ARR_X, 0, d.dx);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_SRC, ARR_S, 0, d.dhs);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_SMD, ARR_S, d.dhs, d.dpos);
+      p->dm = p->phi.dims[p->phi.L];
+      p->dy = p->dm;
+      p->has_node = false;
+      NGPDE_REQUIRE(p->node.L == 0, "ExplicitEdgeConv has no node update");
+      break;
+    case NGPDE_VMH_CONV:  // layers.jl:314-316: vcat(hi..., (hj .- hi)..., posj .- posi); :328: gamma(vcat(x..., m))
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_DST, ARR_X, 0, d.dx);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_DST, ARR_S, 0, d.dhs);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_SMD, ARR_X, 0, d.dx);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_SMD, ARR_S, 0, d.dhs);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_SMD, ARR_S, d.dhs, d.dpos);
+      p->dm = p->phi.dims[p->phi.L];
+      push_seg(p->nsegs, &p->n_nsegs, &nrow, SEG_DST, ARR_X, 0, d.dx);
+      push_seg(p->nsegs, &p->n_nsegs, &nrow, SEG_DST, ARR_M, 0, p->dm);
+      p->has_node = true;
+      break;
+    case NGPDE_MPPDE_CONV:  // layers.jl:409-410: vcat(hi, hj, di .- dj, e, theta); :418: psi(vcat(x, m, theta))
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_DST, ARR_X, 0, d.dx);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_SRC, ARR_X, 0, d.dx);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_DMS, ARR_S, 0, p->ds);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_EDGE, ARR_E, 0, d.de);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_GRAPH, ARR_T, 0, d.dtheta);
+      p->dm = p->phi.dims[p->phi.L];
+      push_seg(p->nsegs, &p->n_nsegs, &nrow, SEG_DST, ARR_X, 0, d.dx);
+      push_seg(p->nsegs, &p->n_nsegs, &nrow, SEG_DST, ARR_M, 0, p->dm);
+      push_seg(p->nsegs, &p->n_nsegs, &nrow, SEG_GRAPH, ARR_T, 0, d.dtheta);
+      p->has_node = true;
+      if (d.dtheta > 0) {
+        NGPDE_REQUIRE(g->G > 0 && g->E % g->G == 0 && g->N % g->G == 0,
+                      "MPPDEConv assumes equal-sized graphs (E=%lld, N=%lld, G=%lld)", (long long)g->E,
+                      (long long)g->N, (long long)g->G);
+      }
+      break;
+    case NGPDE_GNO_CONV:  // layers.jl:516-530, 536-547
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_DST, ARR_S, 0, p->ds);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_SRC, ARR_S, 0, p->ds);
+      push_seg(p->esegs, &p->n_esegs, &row, SEG_EDGE, ARR_E, 0, d.de);
+      NGPDE_REQUIRE(d.gno_in == d.dx && d.gno_out > 0, "GNOConv: in_chs=%d must equal dx=%d", d.gno_in, d.dx);
+      NGPDE_REQUIRE(p->phi.dims[p->phi.L] == d.gno_in * d.gno_out, "GNOConv: phi must output in*out=%d values, got %d",
+                    d.gno_in * d.gno_out, p->phi.dims[p->phi.L]);
+      p->contract = 1;
+      p->dm = d.gno_out;
+      push_seg(p->nsegs, &p->n_nsegs, &nrow, SEG_DST, ARR_X, 0, d.dx);
+      NGPDE_REQUIRE(p->node.L == 1 && p->node.dims[1] == d.gno_out, "GNOConv: node must be the 1-layer linear map");
+      p->has_node = true;
+      p->node_addend = true;
+      break;
+    default:
+      set_error("unknown layer family %d", d.family);
+      return NGPDE_ERR_INVALID;
+  }
+  NGPDE_REQUIRE(row == p->phi.dims[0], "phi expects %d input rows but the layer assembles %d (DimensionMismatch)",
+                p->phi.dims[0], row);
+  if (p->has_node) {
+    NGPDE_REQUIRE(nrow == p->node.dims[0], "node update expects %d input rows but the layer assembles %d",
+                  p->node.dims[0], nrow);
+    p->dy = p->node.dims[p->node.L];
+  }
+  for (int i = 0; i < p->n_esegs; ++i) {
+    if (p->esegs[i].arr == ARR_X) {
+      p->edge_need_dz0 = true;
+      if (coef_dst_host(p->esegs[i].kind)) p->edge_dst_side = true;
+    }
+  }
+  return NGPDE_OK;
+}
+
+struct FwdSmem {
+  int offA, offB, offW, offH, floats;
+};
+
+FwdSmem fwd_smem(const MlpDev& m, int contract, int gin, int gout, int te) {
+  const int ld = te + 4;
+  const int npass = (te == 32) ? 128 : 64;
+  const int Lp = contract ? m.L - 1 : m.L;
+  int rows[2] = {0, 0};
+  for (int l = 0; l <= Lp; ++l) rows[l & 1] = std::max(rows[l & 1], m.dims[l]);
+  if (contract) rows[(Lp + 1) & 1] = std::max(rows[(Lp + 1) & 1], gout);
+  FwdSmem s;
+  s.offA = 0;
+  s.offB = rows[0] * ld;
+  s.offH = s.offB + rows[1] * ld;
+  s.offW = s.offH + (contract ? gin * ld : 0);
+  s.floats = 3 * te + s.offW + 2 * KC * npass;
+  return s;
+}
+
+struct BwdSmem {
+  int zoff[NGPDE_MAX_LAYERS + 1];
+  int offG0, offG1, offW, offH, offDM, offP, offDH, offRed, floats;
+  int store_last;
+};
+
+BwdSmem bwd_smem(const MlpDev& m, int contract, int gin, int gout, int aggr, bool node, bool need_dz0, int te) {
+  const int ld = te + 4;
+  const int npass = (te == 32) ? 128 : 64;
+  const int nth = (te == 32) ? 16 : 8;
+  const int Lp = contract ? m.L - 1 : m.L;
+  BwdSmem s{};
+  const int last_act = m.act[m.L - 1];
+  s.store_last = 0;
+  if (!contract) {
+    if (last_act != NGPDE_ACT_IDENTITY && act_grad_from_y(last_act)) s.store_last = 1;
+    if (!node && (aggr == NGPDE_AGGR_MAX || aggr == NGPDE_AGGR_MIN)) s.store_last = 1;
+  }
+  int off = 0;
+  const int nstore = (s.store_last || contract) ? Lp : Lp - 1;
+  for (int l = 0; l <= Lp; ++l) {
+    s.zoff[l] = off;
+    if (l <= nstore) off += m.dims[l] * ld;
+  }
+  // G ping-pong: G0 holds dZ_Lp, dZ_{Lp-2}, ...; G1 holds dZ_{Lp-1}, ...
+  int rows[2] = {0, 0};
+  for (int l = Lp; l >= 0; --l) {
+    if (l == 0 && !need_dz0 && Lp > 0) break;
+    rows[(Lp - l) & 1] = std::max(rows[(Lp - l) & 1], m.dims[l]);
+  }
+  rows[0] = std::max(rows[0], m.dims[Lp]);
+  s.offG0 = off;
+  off += rows[0] * ld;
+  s.offG1 = off;
+  off += rows[1] * ld;
+  if (contract) {
+    s.offH = off;  off += gin * ld;
+    s.offDH = off; off += gin * ld;
+    s.offDM = off; off += gout * ld;
+    s.offP = off;  off += npass * ld;
+    s.offRed = off; off += nth * te;
+  }
+  s.offW = off;
+  off += 2 * KC * npass;
+  s.floats = 3 * te + off;
+  return s;
+}
+
+template <class F>
+int pick_tile(F bytes_for, int* te_out, int* bytes_out) {
+  for (int pass = 0; pass < 2; ++pass) {
+    const int limit = pass == 0 ? kSmemTwoCtas : kSmemMax;
+    for (int t = 2; t >= 0; --t) {
+      const int b = bytes_for(kTileSizes[t]);
+      if (b <= limit) {
+        *te_out = kTileSizes[t];
+        *bytes_out = b;
+        return NGPDE_OK;
+      }
+    }
+  }
+  set_error("layer too wide for the shared-memory tile (needs %d bytes at the smallest tile)", bytes_for(32));
+  return NGPDE_ERR_UNSUPPORTED;
+}
+
+template <class K>
+int launch_cfg(K kernel, int smem_bytes, int n_units, int num_sms, int* grid) {
+  NGPDE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  int occ = 0;
+  NGPDE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NT, smem_bytes));
+  if (occ < 1) {
+    set_error("kernel cannot be resident with %d bytes of shared memory", smem_bytes);
+    return NGPDE_ERR_UNSUPPORTED;
+  }
+  *grid = std::max(1, std::min(n_units, occ * num_sms));
+  return NGPDE_OK;
+}
+
+template <bool NODE>
+int launch_fwd(int te, const FwdArgs& a, int smem_bytes, int num_sms, cudaStream_t st) {
+  int grid = 0;
+  if (a.tg.n_units <= 0) return NGPDE_OK;
+#define NGPDE_LAUNCH_FWD(TE)                                                          \
+  {                                                                                   \
+    if (int rc = launch_cfg(mp_fwd_kernel<TE, NODE>, smem_bytes, a.tg.n_units, num_sms, &grid)) return rc; \
+    mp_fwd_kernel<TE, NODE><<<grid, NT, smem_bytes, st>>>(a);                         \
+  }
+  if (te == 128) NGPDE_LAUNCH_FWD(128) else if (te == 64) NGPDE_LAUNCH_FWD(64) else NGPDE_LAUNCH_FWD(32)
+#undef NGPDE_LAUNCH_FWD
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
+template <bool NODE>
+int bwd_grid(int te, int smem_bytes, int n_units, int num_sms, int* grid) {
+  if (te == 128) return launch_cfg(mp_bwd_kernel<128, NODE>, smem_bytes, n_units, num_sms, grid);
+  if (te == 64) return launch_cfg(mp_bwd_kernel<64, NODE>, smem_bytes, n_units, num_sms, grid);
+  return launch_cfg(mp_bwd_kernel<32, NODE>, smem_bytes, n_units, num_sms, grid);
+}
+
+template <bool NODE>
+int launch_bwd(int te, const BwdArgs& a, int smem_bytes, int grid, cudaStream_t st) {
+  if (a.tg.n_units <= 0) return NGPDE_OK;
+  if (te == 128) mp_bwd_kernel<128, NODE><<<grid, NT, smem_bytes, st>>>(a);
+  else if (te == 64) mp_bwd_kernel<64, NODE><<<grid, NT, smem_bytes, st>>>(a);
+  else mp_bwd_kernel<32, NODE><<<grid, NT, smem_bytes, st>>>(a);
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
+int tile_index(int te) { return te == 32 ? 0 : (te == 64 ? 1 : 2); }
+
+void fill_arrays(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, const ngpde_conv_io& io,
+                 const float** arr, int* ld) {
+  arr[ARR_X] = io.x;      ld[ARR_X] = d.dx;
+  arr[ARR_S] = io.snode;  ld[ARR_S] = p.ds;
+  arr[ARR_E] = io.edata;  ld[ARR_E] = d.de;
+  arr[ARR_T] = io.theta;  ld[ARR_T] = d.dtheta;
+  arr[ARR_M] = io.mbar;   ld[ARR_M] = p.dm;
+  (void)g;
+}
+
+int check_io(const ngpde_conv_desc& d, const Plan& p, const ngpde_conv_io& io, bool backward) {
+  NGPDE_REQUIRE(io.x != nullptr, "x is NULL");
+  NGPDE_REQUIRE(p.ds == 0 || io.snode != nullptr, "snode is NULL but dhs+dpos=%d", p.ds);
+  NGPDE_REQUIRE(d.de == 0 || io.edata != nullptr, "edata is NULL but de=%d", d.de);
+  NGPDE_REQUIRE(d.dtheta == 0 || d.family != NGPDE_MPPDE_CONV || io.theta != nullptr, "theta is NULL but dtheta=%d",
+                d.dtheta);
+  NGPDE_REQUIRE(io.phi_params != nullptr, "phi_params is NULL");
+  NGPDE_REQUIRE(!p.has_node || io.node_params != nullptr, "node_params is NULL");
+  NGPDE_REQUIRE(io.mbar != nullptr, "mbar is NULL");
+  NGPDE_REQUIRE(!p.has_node || io.y != nullptr, "y is NULL");
+  if (backward) {
+    NGPDE_REQUIRE(io.dy != nullptr && io.dx != nullptr && io.dphi_params != nullptr, "backward outputs are NULL");
+    NGPDE_REQUIRE(!p.has_node || io.dnode_params != nullptr, "dnode_params is NULL");
+  }
+  return NGPDE_OK;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct BwdLayout {
+  int te_e, smem_e, grid_e;
+  int te_n, smem_n, grid_n;
+  BwdSmem se, sn;
+  size_t off_wt_phi, off_wt_node, off_dmbar, off_dxdirect, off_dxdst, off_desrc, off_part_phi, off_part_node, total;
+};
+
+int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, BwdLayout* L) {
+  if (int rc = pick_tile(
+          [&](int te) {
+            return 4 * bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, te).floats;
+          },
+          &L->te_e, &L->smem_e))
+    return rc;
+  L->se = bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, L->te_e);
+  if (int rc = bwd_grid<false>(L->te_e, L->smem_e, std::max(1, g->n_units[tile_index(L->te_e)]), g->num_sms, &L->grid_e))
+    return rc;
+  L->te_n = 0; L->smem_n = 0; L->grid_n = 0;
+  if (p.has_node) {
+    if (int rc = pick_tile([&](int te) { return 4 * bwd_smem(p.node, 0, 0, 0, d.aggr, true, true, te).floats; },
+                           &L->te_n, &L->smem_n))
+      return rc;
+    L->sn = bwd_smem(p.node, 0, 0, 0, d.aggr, true, true, L->te_n);
+    const int nu = (int)((g->N + L->te_n - 1) / L->te_n);
+    if (int rc = bwd_grid<true>(L->te_n, L->smem_n, std::max(1, nu), g->num_sms, &L->grid_n)) return rc;
+  }
+  size_t off = 0;
+  L->off_wt_phi = off;    off = align256(off + sizeof(float) * p.phi.n_params);
+  L->off_wt_node = off;   off = align256(off + sizeof(float) * p.node.n_params);
+  L->off_dmbar = off;     off = align256(off + (p.has_node ? sizeof(float) * g->N * p.dm : 0));
+  L->off_dxdirect = off;  off = align256(off + (p.has_node ? sizeof(float) * g->N * d.dx : 0));
+  L->off_dxdst = off;     off = align256(off + (p.edge_dst_side ? sizeof(float) * g->N * d.dx : 0));
+  L->off_desrc = off;     off = align256(off + sizeof(float) * g->E * d.dx);
+  L->off_part_phi = off;  off = align256(off + sizeof(float) * (size_t)L->grid_e * p.phi.n_params);
+  L->off_part_node = off; off = align256(off + sizeof(float) * (size_t)L->grid_n * p.node.n_params);
+  L->total = off;
+  return NGPDE_OK;
+}
+
+
+}  // namespace
+
+// ---- a bare Chain of Dense layers over the node axis (used by GCNConv's W*x) ----
+int make_mlp_dev(const ngpde_mlp& m, MlpDev* out, const char* what) { return make_mlp(m, out, what); }
+
+int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, float* y,
+                     cudaStream_t st) {
+  int te = 0, smem = 0;
+  if (int rc = pick_tile([&](int t) { return 4 * fwd_smem(mlp, 0, 0, 0, t).floats; }, &te, &smem)) return rc;
+  FwdSmem fs = fwd_smem(mlp, 0, 0, 0, te);
+  FwdArgs n{};
+  n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + te - 1) / te), (int)g->N, 1};
+  n.arr[ARR_X] = x;
+  n.ld[ARR_X] = mlp.dims[0];
+  n.n_segs = 1;
+  n.segs[0] = Seg{SEG_DST, ARR_X, 0, mlp.dims[0], 0};
+  n.mlp = mlp;
+  n.params = params;
+  n.dout = mlp.dims[mlp.L];
+  n.out = y;
+  n.offA = fs.offA; n.offB = fs.offB; n.offW = fs.offW; n.offH = fs.offH;
+  return launch_fwd<true>(te, n, smem, g->num_sms, st);
+}
+
+namespace {
+struct NodeBwdLayout {
+  int te, smem, grid;
+  BwdSmem s;
+  size_t off_wt, off_part, total;
+};
+int node_bwd_layout(const ngpde_graph* g, const MlpDev& mlp, NodeBwdLayout* L) {
+  if (int rc = pick_tile([&](int te) { return 4 * bwd_smem(mlp, 0, 0, 0, 0, true, true, te).floats; }, &L->te, &L->smem))
+    return rc;
+  L->s = bwd_smem(mlp, 0, 0, 0, 0, true, true, L->te);
+  const int nu = (int)((g->N + L->te - 1) / L->te);
+  if (int rc = bwd_grid<true>(L->te, L->smem, std::max(1, nu), g->num_sms, &L->grid)) return rc;
+  size_t off = 0;
+  L->off_wt = off;   off = align256(off + sizeof(float) * mlp.n_params);
+  L->off_part = off; off = align256(off + sizeof(float) * (size_t)L->grid * mlp.n_params);
+  L->total = off;
+  return NGPDE_OK;
+}
+}  // namespace
+
+size_t node_mlp_backward_ws(const ngpde_graph* g, const MlpDev& mlp) {
+  NodeBwdLayout L;
+  if (node_bwd_layout(g, mlp, &L)) return 0;
+  return L.total;
+}
+
+// dy -> dx (may be nullptr... it is always produced here), dparams
+int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, const float* dy,
+                      float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  NodeBwdLayout L;
+  if (int rc = node_bwd_layout(g, mlp, &L)) return rc;
+  if (ws_bytes < L.total) {
+    set_error("node MLP workspace too small: %zu < %zu", ws_bytes, L.total);
+    return NGPDE_ERR_WORKSPACE;
+  }
+  char* ws = static_cast<char*>(workspace);
+  float* wt = reinterpret_cast<float*>(ws + L.off_wt);
+  float* part = reinterpret_cast<float*>(ws + L.off_part);
+  NGPDE_CUDA_TRY(cudaMemsetAsync(part, 0, L.total - L.off_part, st));
+  transpose_weights_kernel<<<64, 256, 0, st>>>(params, wt, mlp);
+  BwdArgs n{};
+  n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + L.te - 1) / L.te), (int)g->N, 1};
+  n.arr[ARR_X] = x;
+  n.ld[ARR_X] = mlp.dims[0];
+  n.n_segs = 1;
+  n.segs[0] = Seg{SEG_DST, ARR_X, 0, mlp.dims[0], 0};
+  n.mlp = mlp;
+  n.params = params;
+  n.wt = wt;
+  n.dout = mlp.dims[mlp.L];
+  n.gout_ptr = dy;
+  n.dparams_partial = part;
+  n.dx_direct = dx;
+  n.dx = mlp.dims[0];
+  n.need_dz0 = 1;
+  n.store_last = L.s.store_last;
+  std::memcpy(n.zoff, L.s.zoff, sizeof(n.zoff));
+  n.offG0 = L.s.offG0; n.offG1 = L.s.offG1; n.offW = L.s.offW;
+  if (int rc = launch_bwd<true>(L.te, n, L.smem, L.grid, st)) return rc;
+  reduce_partials_kernel<<<(mlp.n_params + 255) / 256, 256, 0, st>>>(part, L.grid, mlp.n_params, dparams);
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
+}  // namespace ngpde
+
+using namespace ngpde;
+
+extern "C" size_t ngpde_conv_workspace_bytes(ngpde_graph_t g, const ngpde_conv_desc* desc, int32_t backward) {
+  if (!g || !desc) return 0;
+  if (!backward) return 256;
+  Plan p;
+  if (make_plan(g, *desc, &p)) return 0;
+  BwdLayout L;
+  if (bwd_layout(g, *desc, p, &L)) return 0;
+  return L.total + 256;
+}
+
+extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_conv_io* io,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  NGPDE_REQUIRE(g && desc && io, "null argument");
+  Plan p;
+  if (int rc = make_plan(g, *desc, &p)) return rc;
+  if (int rc = check_io(*desc, p, *io, false)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g->N == 0) return NGPDE_OK;
+
+  // ---- edge phase ----
+  int te = 0, smem = 0;
+  if (int rc = pick_tile(
+          [&](int t) { return 4 * fwd_smem(p.phi, p.contract, desc->gno_in, desc->gno_out, t).floats; }, &te, &smem))
+    return rc;
+  FwdSmem fs = fwd_smem(p.phi, p.contract, desc->gno_in, desc->gno_out, te);
+  FwdArgs a{};
+  const int ti = tile_index(te);
+  a.tg = TileGraph{g->rowptr, g->src, g->dst, g->perm, g->units[ti], g->n_units[ti], (int)g->N,
+                   (int)std::max<int64_t>(1, g->E / std::max<int64_t>(1, g->G))};
+  fill_arrays(g, *desc, p, *io, a.arr, a.ld);
+  a.n_segs = p.n_esegs;
+  std::memcpy(a.segs, p.esegs, sizeof(p.esegs));
+  a.mlp = p.phi;
+  a.params = io->phi_params;
+  a.contract = p.contract;
+  a.gin = desc->gno_in;
+  a.gout = desc->gno_out;
+  a.aggr = desc->aggr;
+  a.dout = p.dm;
+  a.out = io->mbar;
+  a.addend = nullptr;
+  a.offA = fs.offA; a.offB = fs.offB; a.offW = fs.offW; a.offH = fs.offH;
+  if (int rc = launch_fwd<false>(te, a, smem, g->num_sms, st)) return rc;
+
+  // ---- node phase ----
+  if (p.has_node) {
+    if (int rc = pick_tile([&](int t) { return 4 * fwd_smem(p.node, 0, 0, 0, t).floats; }, &te, &smem)) return rc;
+    fs = fwd_smem(p.node, 0, 0, 0, te);
+    FwdArgs n{};
+    n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + te - 1) / te), (int)g->N,
+                     (int)std::max<int64_t>(1, g->N / std::max<int64_t>(1, g->G))};
+    fill_arrays(g, *desc, p, *io, n.arr, n.ld);
+    n.n_segs = p.n_nsegs;
+    std::memcpy(n.segs, p.nsegs, sizeof(p.nsegs));
+    n.mlp = p.node;
+    n.params = io->node_params;
+    n.aggr = desc->aggr;
+    n.dout = p.dy;
+    n.out = io->y;
+    n.addend = p.node_addend ? io->mbar : nullptr;
+    n.offA = fs.offA; n.offB = fs.offB; n.offW = fs.offW; n.offH = fs.offH;
+    if (int rc = launch_fwd<true>(te, n, smem, g->num_sms, st)) return rc;
+  }
+  return NGPDE_OK;
+}
+
+extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_conv_io* io,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  NGPDE_REQUIRE(g && desc && io, "null argument");
+  Plan p;
+  if (int rc = make_plan(g, *desc, &p)) return rc;
+  if (int rc = check_io(*desc, p, *io, true)) return rc;
+  if (p.contract && (desc->aggr == NGPDE_AGGR_MAX || desc->aggr == NGPDE_AGGR_MIN)) {
+    set_error("GNOConv backward supports aggr = + and mean only");
+    return NGPDE_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BwdLayout L;
+  if (int rc = bwd_layout(g, *desc, p, &L)) return rc;
+  if (workspace_bytes < L.total || workspace == nullptr) {
+    set_error("workspace too small: %zu bytes given, %zu needed", workspace_bytes, L.total);
+    return NGPDE_ERR_WORKSPACE;
+  }
+  if (g->N == 0) return NGPDE_OK;
+  char* ws = static_cast<char*>(workspace);
+  NGPDE_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
+  float* wt_phi = reinterpret_cast<float*>(ws + L.off_wt_phi);
+  float* wt_node = reinterpret_cast<float*>(ws + L.off_wt_node);
+  float* dmbar = p.has_node ? reinterpret_cast<float*>(ws + L.off_dmbar) : nullptr;
+  float* dxdirect = p.has_node ? reinterpret_cast<float*>(ws + L.off_dxdirect) : nullptr;
+  float* dxdst = p.edge_dst_side ? reinterpret_cast<float*>(ws + L.off_dxdst) : nullptr;
+  float* desrc = reinterpret_cast<float*>(ws + L.off_desrc);
+  float* part_phi = reinterpret_cast<float*>(ws + L.off_part_phi);
+  float* part_node = reinterpret_cast<float*>(ws + L.off_part_node);
+
+  NGPDE_CUDA_TRY(cudaMemsetAsync(part_phi, 0, L.total - L.off_part_phi, st));
+  transpose_weights_kernel<<<64, 256, 0, st>>>(io->phi_params, wt_phi, p.phi);
+  if (p.has_node) transpose_weights_kernel<<<64, 256, 0, st>>>(io->node_params, wt_node, p.node);
+
+  // ---- node phase: dy -> (dx_direct, dmbar, dnode_params) ----
+  if (p.has_node) {
+    BwdArgs n{};
+    const int te = L.te_n;
+    n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + te - 1) / te), (int)g->N,
+                     (int)std::max<int64_t>(1, g->N / std::max<int64_t>(1, g->G))};
+    fill_arrays(g, *desc, p, *io, n.arr, n.ld);
+    n.n_segs = p.n_nsegs;
+    std::memcpy(n.segs, p.nsegs, sizeof(p.nsegs));
+    n.mlp = p.node;
+    n.params = io->node_params;
+    n.wt = wt_node;
+    n.aggr = desc->aggr;
+    n.dout = p.dy;
+    n.gout_ptr = io->dy;
+    n.fwd_out = io->y;
+    n.addend = p.node_addend ? io->mbar : nullptr;
+    n.dparams_partial = part_node;
+    n.dx_direct = dxdirect;
+    n.dmbar = dmbar;
+    n.dx = desc->dx;
+    n.need_dz0 = 1;
+    n.store_last = L.sn.store_last;
+    std::memcpy(n.zoff, L.sn.zoff, sizeof(n.zoff));
+    n.offG0 = L.sn.offG0; n.offG1 = L.sn.offG1; n.offW = L.sn.offW;
+    if (int rc = launch_bwd<true>(te, n, L.smem_n, L.grid_n, st)) return rc;
+    const int P = p.node.n_params;
+    reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_node, L.grid_n, P, io->dnode_params);
+  }
+
+  // ---- edge phase: dmbar -> (dxdst, desrc, dphi_params) ----
+  {
+    BwdArgs a{};
+    const int te = L.te_e;
+    const int ti = tile_index(te);
+    a.tg = TileGraph{g->rowptr, g->src, g->dst, g->perm, g->units[ti], g->n_units[ti], (int)g->N,
+                     (int)std::max<int64_t>(1, g->E / std::max<int64_t>(1, g->G))};
+    fill_arrays(g, *desc, p, *io, a.arr, a.ld);
+    a.n_segs = p.n_esegs;
+    std::memcpy(a.segs, p.esegs, sizeof(p.esegs));
+    a.mlp = p.phi;
+    a.params = io->phi_params;
+    a.wt = wt_phi;
+    a.contract = p.contract;
+    a.gin = desc->gno_in;
+    a.gout = desc->gno_out;
+    a.aggr = desc->aggr;
+    a.dout = p.dm;
+    a.gout_ptr = p.has_node ? dmbar : io->dy;
+    a.fwd_out = io->mbar;
+    a.dparams_partial = part_phi;
+    a.dxdst = dxdst;
+    a.desrc = desrc;
+    a.dx = desc->dx;
+    a.need_dz0 = p.edge_need_dz0 ? 1 : 0;
+    a.store_last = L.se.store_last;
+    a.has_dst_side = p.edge_dst_side ? 1 : 0;
+    std::memcpy(a.zoff, L.se.zoff, sizeof(a.zoff));
+    a.offG0 = L.se.offG0; a.offG1 = L.se.offG1; a.offW = L.se.offW; a.offH = L.se.offH;
+    a.offDM = L.se.offDM; a.offP = L.se.offP; a.offDH = L.se.offDH; a.offRed = L.se.offRed;
+    if (g->E > 0) {
+      if (int rc = launch_bwd<false>(te, a, L.smem_e, L.grid_e, st)) return rc;
+    } else if (dxdst) {
+      NGPDE_CUDA_TRY(cudaMemsetAsync(dxdst, 0, sizeof(float) * g->N * desc->dx, st));
+    }
+    const int P = p.phi.n_params;
+    reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_phi, L.grid_e, P, io->dphi_params);
+  }
+
+  // ---- dx = dx_direct + dxdst + transpose-gather(desrc) ----
+  {
+    const size_t total = (size_t)g->N * desc->dx;
+    const bool has_src = (p.edge_need_dz0 || p.contract) && g->E > 0;
+    dx_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dxdirect, dxdst, has_src ? desrc : nullptr,
+                                                                        g->tptr, g->tpos, (int)g->N, desc->dx, io->dx);
+  }
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
+#define NGPDE_FAMILY_WRAPPER(name, fam)                                                                         \
+  extern "C" int ngpde_##name##_forward(ngpde_graph_t g, const ngpde_conv_desc* d, const ngpde_conv_io* io,     \
+                                        void* ws, size_t wsb, void* st) {                                       \
+    NGPDE_REQUIRE(d && d->family == fam, "descriptor family does not match " #name);                            \
+    return ngpde_conv_forward(g, d, io, ws, wsb, st);                                                           \
+  }                                                                                                             \
+  extern "C" int ngpde_##name##_backward(ngpde_graph_t g, const ngpde_conv_desc* d, const ngpde_conv_io* io,    \
+                                         void* ws, size_t wsb, void* st) {                                      \
+    NGPDE_REQUIRE(d && d->family == fam, "descriptor family does not match " #name);                            \
+    return ngpde_conv_backward(g, d, io, ws, wsb, st);                                                          \
+  }
+
+NGPDE_FAMILY_WRAPPER(explicit_edge_conv, NGPDE_EXPLICIT_EDGE_CONV)
+NGPDE_FAMILY_WRAPPER(vmh_conv, NGPDE_VMH_CONV)
+NGPDE_FAMILY_WRAPPER(mppde_conv, NGPDE_MPPDE_CONV)
+NGPDE_FAMILY_WRAPPER(gno_conv, NGPDE_GNO_CONV)

@@ -1,0 +1,90 @@
+// Kernel argument blocks of the fused message-passing kernels.
+#pragma once
+#include "ngpde_tile.cuh"
+
+namespace ngpde {
+
+// How one block of rows of the MLP input Z0 is assembled per column (edge or node):
+enum { SEG_DST = 0, SEG_SRC = 1, SEG_SMD = 2 /* a[src]-a[dst] */, SEG_DMS = 3 /* a[dst]-a[src] */, SEG_EDGE = 4, SEG_GRAPH = 5 };
+// which array a segment reads
+enum { ARR_X = 0, ARR_S = 1, ARR_E = 2, ARR_T = 3, ARR_M = 4, ARR_COUNT = 5 };
+
+struct Seg {
+  int kind, arr, col, width, row;
+};
+
+struct MlpDev {
+  int L;
+  int dims[NGPDE_MAX_LAYERS + 1];
+  int act[NGPDE_MAX_LAYERS];
+  int w_off[NGPDE_MAX_LAYERS];   // float offset of weight [in][out] in the flat parameter segment
+  int b_off[NGPDE_MAX_LAYERS];   // float offset of bias [out], or -1
+  int n_params;
+};
+
+// Topology seen by one kernel.  In the node phase a "unit" is TE consecutive nodes and src = dst = perm = node id.
+struct TileGraph {
+  const int* rowptr;
+  const int* src;
+  const int* dst;
+  const int* perm;
+  const int* unit_ptr;
+  int n_units;
+  int N;
+  int gdiv;  // items per graph: E/G (edge phase, indexed by ORIGINAL edge position) or N/G (node phase)
+};
+
+struct FwdArgs {
+  TileGraph tg;
+  const float* arr[ARR_COUNT];
+  int ld[ARR_COUNT];
+  int n_segs;
+  Seg segs[8];
+  MlpDev mlp;
+  const float* params;
+  int contract;  // GNO: last layer is contracted with x[src] instead of materialised
+  int gin, gout;
+  int aggr;
+  int dout;             // rows of the result tile
+  float* out;           // edge phase: mbar [N][dout]; node phase: y [N][dout]
+  const float* addend;  // node phase (GNO): [N][dout] added before the last activation
+  int offA, offB, offW, offH;  // shared-memory float offsets
+};
+
+struct BwdArgs {
+  TileGraph tg;
+  const float* arr[ARR_COUNT];
+  int ld[ARR_COUNT];
+  int n_segs;
+  Seg segs[8];
+  MlpDev mlp;
+  const float* params;
+  const float* wt;  // transposed weights: layer l at wt + w_off[l], laid out [out][in]
+  int contract, gin, gout;
+  int aggr;
+  int dout;
+  const float* gout_ptr;  // edge phase: dmbar [N][dout]; node phase: dy [N][dout]
+  const float* fwd_out;   // edge phase: mbar (max/min mask)
+  const float* addend;    // node phase (GNO)
+  float* dparams_partial; // [gridDim.x][n_params], zero-initialised
+  float* dx_direct;       // node phase: [N][dx]
+  float* dmbar;           // node phase: [N][dm]
+  float* dxdst;           // edge phase: [N][dx], destination-side input gradient
+  float* desrc;           // edge phase: [E][dx], per-edge source-side input gradient (CSR order)
+  int dx;
+  int need_dz0;
+  int store_last;         // Z_L has to be recomputed (activation on the last layer, or max/min)
+  int has_dst_side;
+  int zoff[NGPDE_MAX_LAYERS + 1];
+  int offG0, offG1, offW, offH, offDM, offP, offDZ, offDH, offRed;
+};
+
+// bare Dense chains over the node axis (ngpde_conv.cu), used by GCNConv
+int make_mlp_dev(const ngpde_mlp& m, MlpDev* out, const char* what);
+int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, float* y,
+                     cudaStream_t st);
+size_t node_mlp_backward_ws(const ngpde_graph* g, const MlpDev& mlp);
+int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, const float* dy,
+                      float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace ngpde

@@ -1,0 +1,70 @@
+"""Shared helpers for the parity tests: product (ngpde) <-> oracle conversions and error measures."""
+import numpy as np
+import torch
+
+import ngpde
+import ngpde_oracle as orc
+
+
+def relerr(a: torch.Tensor, b: torch.Tensor) -> float:
+    """Max-norm relative error  max|a-b| / max|b|  (the tolerance measure of every float parity test)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.numel() == 0:
+        return 0.0
+    den = max(b.abs().max().item(), 1e-30)
+    return (a - b).abs().max().item() / den
+
+
+def tree_to_cpu(ps, dtype=torch.float32):
+    """ngpde NT / ComponentArray tree -> nested dict of CPU tensors (Julia shapes) for the oracle."""
+    if isinstance(ps, ngpde.ComponentArray):
+        ps = ps.to_tree()
+    out = {}
+    for k, v in ps.items():
+        out[k] = v.detach().cpu().to(dtype).contiguous().clone() if isinstance(v, torch.Tensor) else tree_to_cpu(v, dtype)
+    return out
+
+
+def tree_requires_grad(tree):
+    for v in tree.values():
+        if isinstance(v, torch.Tensor):
+            v.requires_grad_(True)
+        else:
+            tree_requires_grad(v)
+    return tree
+
+
+def tree_leaves(tree):
+    for v in tree.values():
+        if isinstance(v, torch.Tensor):
+            yield v
+        else:
+            yield from tree_leaves(v)
+
+
+def flat_grad(tree) -> torch.Tensor:
+    """Gradients of a Julia-shaped parameter tree flattened in ComponentArray order (column-major leaves)."""
+    parts = []
+    for v in tree_leaves(tree):
+        g = v.grad if v.grad is not None else torch.zeros_like(v)
+        parts.append(g.T.reshape(-1) if g.dim() == 2 else g.reshape(-1))
+    return torch.cat(parts)
+
+
+def to_ograph(g: ngpde.GNNGraph, dtype=torch.float32) -> orc.OGraph:
+    cv = lambda d: {k: v.detach().cpu().to(dtype) for k, v in d.items()}
+    return orc.OGraph(g.s.cpu().numpy().astype(np.int64), g.t.cpu().numpy().astype(np.int64), g.num_nodes, g.num_graphs,
+                      cv(g.ndata), cv(g.edata), cv(g.gdata), None if g.w is None else g.w.detach().cpu().to(dtype))
+
+
+def jl_rand(rng: np.random.Generator, d: int, n: int, device="cpu", lo=-1.0, hi=1.0) -> torch.Tensor:
+    """(d, n) Julia-shaped float32 tensor stored column-major, U(lo, hi)."""
+    a = rng.uniform(lo, hi, size=(n, d)).astype(np.float32)
+    return torch.from_numpy(a).to(device).T
+
+
+def random_graph(rng, n, e, device="cpu", **kw):
+    s = torch.from_numpy(rng.integers(0, n, e))
+    t = torch.from_numpy(rng.integers(0, n, e))
+    return ngpde.GNNGraph(s.to(device), t.to(device), num_nodes=n, **kw)
