@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the message-passing hot path (BASELINE.json metric: edge-messages/s and ODE-RHS-evals/s, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one right-hand-side evaluation, forward plus its vector-Jacobian product w.r.t. (x, ps), of the workload's
+layer over its synthetic graph -- by default C3: VMHConv on the 256x256 grid-8 graph (65,536 nodes, 521,220 edges,
+hidden 64), the configuration BASELINE.json's target is quoted on.  With N > 1 ranks every rank owns one such graph
+(batched-ensemble sharding, SURVEY.md 8e: no data-path collective; the flat parameter gradient is all-reduced over NCCL
+every step, as a data-parallel training step does), so scaling is weak.
+
+One JSON line on stdout (rank 0).  `value` = edge messages (fwd+bwd) per second over all ranks with inputs resident in
+HBM; `e2e` = the same through the public layer API with pinned HOST buffers copied in and results copied out every
+step; `roofline` = the dominant kernel (edge-phase backward) timed with CUDA events inside the library;
+`cpu_baseline` = the oracle's unfused restatement of the reference algorithm on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+METRIC = "edge_messages_per_sec_fwd_bwd"
+UNIT = "edge-messages/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    _NAMES = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+              0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+              0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self._NAMES.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:  # noqa: BLE001
+            return local_rank
+    return local_rank
+
+
+def cpu_reference_step_fn(workload_name: str, sample_kw: dict):
+    """The oracle's (unfused, torch-CPU float32) forward + backward on a bounded sample of the workload."""
+    import ngpde
+    from ngpde import workloads
+    from common import oracle_forward, to_ograph, tree_requires_grad, tree_to_cpu
+    w = workloads.WORKLOADS[workload_name]("cpu", **sample_kw)
+    og = to_ograph(w.graph)
+    pc = tree_requires_grad(tree_to_cpu(w.ps))
+    x = w.x.detach().clone().contiguous().requires_grad_(True)
+    gen = torch.Generator().manual_seed(0)
+    y0 = oracle_forward(w.layer, x, pc, og)
+    dy = torch.randn(y0.shape, generator=gen)
+
+    def step():
+        x.grad = None
+        y = oracle_forward(w.layer, x, pc, og)
+        y.backward(dy)
+        return y
+
+    return step, w
+
+
+CPU_SAMPLE = {"c1": {}, "c2": {}, "c3": {"side": 128}, "c4": {"n_nodes": 15625}, "c5": {"n_graphs": 8}}
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample_kw = CPU_SAMPLE[args.workload]
+    step, w = cpu_reference_step_fn(args.workload, sample_kw)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = w.n_edges * args.steps / dt
+    sample = f"{w.name}: {w.n_nodes} nodes / {w.n_edges} edges per step (kwargs {sample_kw})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_label(args.workload), "sample": sample,
+                   "note": "CPU restatement (torch) of the reference's unfused gather->Dense->scatter algorithm; the Julia "
+                           "package itself cannot run in this image"},
+        "rhs_evals_per_sec": args.steps / dt,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_label(name: str) -> str:
+    return {
+        "c1": "C1 ExplicitEdgeConv Neural-ODE RHS, 32x32 grid-4 graph (1,024 nodes / 3,968 edges), hidden 16",
+        "c2": "C2 MPPDEConv, 64 x 256-node path graphs batched (16,384 nodes / 32,640 edges), hidden 128",
+        "c3": "C3 VMHConv RHS, 256x256 grid-8 graph (65,536 nodes / 521,220 edges), phi 6-64-64-64-64, gamma 66-64-64-64-2",
+        "c4": "C4 GNOConv 64=>64, random-geometric graph 1M nodes / ~16M edges, phi 6-64-64-4096",
+        "c5": "C5 GCNConv+GCNConv+VMHConv RHS on 512 x (64x64 grid-8) graphs",
+    }[name]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--cuda-graph", action="store_true", help="replay fwd+bwd from a captured CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (reported under config)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import ngpde
+    from ngpde import _lib, engine, ops, workloads
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the message-passing path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = workloads.WORKLOADS[args.workload](dev)
+    K, W = args.steps, args.warmup
+    gen = torch.Generator().manual_seed(1234)
+    runner = engine.RhsRunner(w.layer, w.x, w.ps, w.st)
+    runner.dy.copy_(torch.randn(tuple(runner.dy.shape), generator=gen).to(dev))
+    if args.cuda_graph:
+        runner.capture()
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    grads = [t for t in (runner.dphi, runner.dnode) if t is not None]
+
+    def one_step():
+        runner.step()
+        if world > 1:
+            for t in grads:  # data-parallel: sum the flat parameter gradients over ranks (NCCL over NVLink)
+                dist.all_reduce(t)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        evs = []
+        sync_all()
+        for _ in range(k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+            if flush is not None:
+                flush.zero_()
+        sync_all()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(W):
+        one_step()
+        if flush is not None:
+            flush.zero_()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    l0 = ops.LAUNCHES["count"]
+    total_ms = timed(one_step, K)
+    launches = ops.LAUNCHES["count"] - l0
+    clocks = sampler.stop()
+
+    edges_total = w.n_edges * K * world
+    value = edges_total / (total_ms * 1e-3)
+
+    # ---- dominant kernel, timed by the library's own CUDA events on the launching stream ----
+    _lib.profile_enable(True)
+    timed(one_step, K)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    peaks = measured_peaks()
+    dom = max(prof, key=lambda k: prof[k][0])
+    dom_ms = prof[dom][0] / max(prof[dom][1], 1)
+    phase_e = dom.endswith("edge")
+    # algorithmic flops of that launch: forward F; backward 2F (dgrad + wgrad); recompute not counted
+    f_edge = w.notes.get("flops_edge_fwd")
+    f_node = w.notes.get("flops_node_fwd")
+    f_phase = (f_edge if phase_e else f_node) if f_edge is not None else w.flops_fwd
+    alg_flops = f_phase * (1.0 if dom.startswith("fwd") else 2.0)
+    ach_tflops = alg_flops / (dom_ms * 1e-3) / 1e12
+    step_kernel_ms = sum(v[0] for v in prof.values()) / K
+    roofline = {
+        "kernel": {"fwd_edge": "mp_fwd_kernel<edge>", "fwd_node": "mp_fwd_kernel<node>", "bwd_node": "mp_bwd_kernel<node>",
+                   "bwd_edge": "mp_bwd_kernel<edge>"}[dom],
+        "bound": "tensor", "achieved": ach_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": ach_tflops / peaks["bf16_tflops"], "traffic": None,
+        "peak_source": peaks["source"] + " bf16 cuBLAS burst (MEASURED_PEAKS.json)",
+        "pipe": "fp32 FFMA (fp32-accurate; tolerance 1e-5 excludes plain TF32/BF16)",
+        "pipe_peak_tflops": 74.4, "pipe_frac": ach_tflops / 74.4,
+        "avg_launch_ms": dom_ms, "algorithmic_flops_per_launch": alg_flops,
+        "share_of_step_kernel_time": (prof[dom][0] / K) / step_kernel_ms if step_kernel_ms else None,
+        "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items()},
+        "hbm": {"algorithmic_bytes_per_step": w.bytes_fwdbwd,
+                "achieved_gbs": w.bytes_fwdbwd / (total_ms / K * 1e-3) / 1e9,
+                "frac_of_measured": w.bytes_fwdbwd / (total_ms / K * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+    }
+
+    # ---- end to end through the public layer API with host buffers ----
+    ca = ngpde.ComponentArray(w.ps)
+    ca.data.requires_grad_(True)
+    x_host = w.x.T.contiguous().cpu().pin_memory()          # [N, d] == Julia (d, N)
+    dy_host = runner.dy.cpu().pin_memory()
+    x_dev = torch.empty_like(x_host, device=dev)
+    dy_dev = torch.empty_like(dy_host, device=dev)
+    y_host = torch.empty(tuple(runner.y.shape), dtype=torch.float32).pin_memory()
+    dx_host = torch.empty_like(x_host).pin_memory()
+    dp_host = torch.empty(ca.data.numel(), dtype=torch.float32).pin_memory()
+    h2d = x_host.numel() * 4 + dy_host.numel() * 4
+    d2h = y_host.numel() * 4 + dx_host.numel() * 4 + dp_host.numel() * 4
+
+    def e2e_step():
+        x_dev.copy_(x_host, non_blocking=True)
+        dy_dev.copy_(dy_host, non_blocking=True)
+        xin = x_dev.T.requires_grad_(True)
+        ca.data.grad = None
+        y, _ = w.layer(xin, ca, w.st)
+        y.backward(dy_dev.T)
+        if world > 1:
+            dist.all_reduce(ca.data.grad)
+        y_host.copy_(y.detach().T, non_blocking=True)
+        dx_host.copy_(xin.grad.T, non_blocking=True)
+        dp_host.copy_(ca.data.grad, non_blocking=True)
+
+    for _ in range(W):
+        e2e_step()
+    e2e_ms = timed(e2e_step, K)
+    e2e_value = edges_total / (e2e_ms * 1e-3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_label(args.workload), "nodes_per_gpu": w.n_nodes, "edges_per_gpu": w.n_edges,
+                   "step": "one RHS evaluation: layer forward + VJP w.r.t. (x, ps)", "aggr": "mean",
+                   "l2": "warm (--no-flush)" if flush is None else "flushed between steps (256 MiB memset, untimed)",
+                   "parallelism": "1 graph per GPU, dW all-reduce over NCCL" if world > 1 else "single GPU",
+                   "cuda_graph": bool(args.cuda_graph)},
+        "rhs_evals_per_sec": K * world / (total_ms * 1e-3),
+        "algorithmic_tflops": 3.0 * w.flops_fwd * world / (total_ms / K * 1e-3) / 1e12,
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / K, "api": "layer(x, ps, st) + backward via the C ABI (torch.autograd bridge)"},
+        "roofline": roofline,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        sample_kw = CPU_SAMPLE[args.workload]
+        step, ws = cpu_reference_step_fn(args.workload, sample_kw)
+        step()
+        n, t0 = 0, time.perf_counter()
+        while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 50):
+            step()
+            n += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": ws.n_edges * n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{ws.name}: {ws.n_nodes} nodes / {ws.n_edges} edges, {n} fwd+bwd steps in {dt:.1f} s "
+                      "(oracle: torch-CPU restatement of the unfused reference algorithm; Julia is not installed)"}
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

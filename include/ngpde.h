@@ -193,9 +193,17 @@ int ngpde_gcn_conv_backward(ngpde_graph_t g, const ngpde_gcn_desc* desc, const f
                             size_t workspace_bytes, void* stream);
 
 /* ---- fixed-step ODE glue (the immediate caller of the path):
- * out = u + sum_i coef[i] * k[i]  over n floats, nk <= 8 stage arrays.  ---- */
+ * out = u + sum_i coef[i] * k[i]  over n floats, nk <= 8 stage arrays; u == NULL stands for zeros.  ---- */
 int ngpde_axpy_stages(float* out, const float* u, const float* const* k, const float* coef, int32_t nk, int64_t n,
                       void* stream);
+
+/* ---- optional kernel timing: while enabled, the four fused kernels of the conv layers (edge/node phase, forward/
+ * backward) are bracketed by CUDA events on the launching stream.  ngpde_profile_read synchronises those events, returns
+ * the summed milliseconds and launch counts per slot (arrays of NGPDE_PROF_SLOTS) and clears the record.  Not
+ * thread-safe; meant for benchmarks. ---- */
+enum { NGPDE_PROF_FWD_EDGE = 0, NGPDE_PROF_FWD_NODE = 1, NGPDE_PROF_BWD_NODE = 2, NGPDE_PROF_BWD_EDGE = 3, NGPDE_PROF_SLOTS = 4 };
+int ngpde_profile_enable(int32_t on);
+int ngpde_profile_read(double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,7 @@ EXPORTS = [
     "ngpde_explicit_edge_conv_backward", "ngpde_vmh_conv_forward", "ngpde_vmh_conv_backward",
     "ngpde_mppde_conv_forward", "ngpde_mppde_conv_backward", "ngpde_gno_conv_forward", "ngpde_gno_conv_backward",
     "ngpde_gcn_workspace_bytes", "ngpde_gcn_conv_forward", "ngpde_gcn_conv_backward", "ngpde_axpy_stages",
+    "ngpde_profile_enable", "ngpde_profile_read",
 ]
 
 
@@ -92,8 +93,25 @@ def load() -> C.CDLL:
     lib.ngpde_gcn_conv_forward.argtypes = [vp, C.POINTER(GcnDesc), vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.ngpde_gcn_conv_backward.argtypes = [vp, C.POINTER(GcnDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.ngpde_axpy_stages.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_float), i32, i64, vp]
+    lib.ngpde_profile_enable.argtypes = [i32]
+    lib.ngpde_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]
     _lib = lib
     return lib
+
+
+PROF_SLOTS = ("fwd_edge", "fwd_node", "bwd_node", "bwd_edge")
+
+
+def profile_enable(on: bool) -> None:
+    check(load().ngpde_profile_enable(1 if on else 0))
+
+
+def profile_read() -> dict:
+    """{slot: (total_ms, launches)} of the fused kernels since the last read (synchronises their events)."""
+    ms = (C.c_double * 4)()
+    n = (C.c_int64 * 4)()
+    check(load().ngpde_profile_read(ms, n))
+    return {k: (ms[i], int(n[i])) for i, k in enumerate(PROF_SLOTS)}
 
 
 def check(rc: int) -> None:

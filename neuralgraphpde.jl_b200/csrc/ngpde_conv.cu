@@ -2,11 +2,37 @@
 // workspace layout, launches, and the extern "C" entry points declared in include/ngpde.h.
 #include <algorithm>
 #include <cstring>
+#include <utility>
+#include <vector>
 
 #include "ngpde_conv_kernels.cuh"
 
 namespace ngpde {
 namespace {
+
+// ---- optional per-kernel timing (ngpde_profile_*): CUDA events recorded on the launching stream around the four
+// fused kernels, so a benchmark can attribute time to the dominant kernel without a profiler attached ----
+struct ProfSlot {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+};
+bool g_prof_on = false;
+ProfSlot g_prof[NGPDE_PROF_SLOTS];
+
+struct ProfScope {
+  cudaStream_t st;
+  cudaEvent_t e1 = nullptr;
+  bool on;
+  ProfScope(int slot, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (!on) return;
+    cudaEvent_t e0;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { on = false; return; }
+    cudaEventRecord(e0, st);
+    g_prof[slot].ev.emplace_back(e0, e1);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(e1, st);
+  }
+};
 
 // host copy of the sign table coef_dst (the device versions live in the kernels header)
 int coef_dst_host(int kind) { return kind == SEG_DST || kind == SEG_SMD || kind == SEG_DMS; }
@@ -456,9 +482,9 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
   NGPDE_REQUIRE(g && desc && io, "null argument");
   Plan p;
   if (int rc = make_plan(g, *desc, &p)) return rc;
+  if (g->N == 0) return NGPDE_OK;
   if (int rc = check_io(*desc, p, *io, false)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (g->N == 0) return NGPDE_OK;
 
   // ---- edge phase ----
   int te = 0, smem = 0;
@@ -483,7 +509,10 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
   a.out = io->mbar;
   a.addend = nullptr;
   a.offA = fs.offA; a.offB = fs.offB; a.offW = fs.offW; a.offH = fs.offH;
-  if (int rc = launch_fwd<false>(te, a, smem, g->num_sms, st)) return rc;
+  {
+    ProfScope prof(NGPDE_PROF_FWD_EDGE, st);
+    if (int rc = launch_fwd<false>(te, a, smem, g->num_sms, st)) return rc;
+  }
 
   // ---- node phase ----
   if (p.has_node) {
@@ -502,6 +531,7 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
     n.out = io->y;
     n.addend = p.node_addend ? io->mbar : nullptr;
     n.offA = fs.offA; n.offB = fs.offB; n.offW = fs.offW; n.offH = fs.offH;
+    ProfScope prof(NGPDE_PROF_FWD_NODE, st);
     if (int rc = launch_fwd<true>(te, n, smem, g->num_sms, st)) return rc;
   }
   return NGPDE_OK;
@@ -512,6 +542,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   NGPDE_REQUIRE(g && desc && io, "null argument");
   Plan p;
   if (int rc = make_plan(g, *desc, &p)) return rc;
+  if (g->N == 0) return NGPDE_OK;
   if (int rc = check_io(*desc, p, *io, true)) return rc;
   if (p.contract && (desc->aggr == NGPDE_AGGR_MAX || desc->aggr == NGPDE_AGGR_MIN)) {
     set_error("GNOConv backward supports aggr = + and mean only");
@@ -565,7 +596,10 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     n.store_last = L.sn.store_last;
     std::memcpy(n.zoff, L.sn.zoff, sizeof(n.zoff));
     n.offG0 = L.sn.offG0; n.offG1 = L.sn.offG1; n.offW = L.sn.offW;
-    if (int rc = launch_bwd<true>(te, n, L.smem_n, L.grid_n, st)) return rc;
+    {
+      ProfScope prof(NGPDE_PROF_BWD_NODE, st);
+      if (int rc = launch_bwd<true>(te, n, L.smem_n, L.grid_n, st)) return rc;
+    }
     const int P = p.node.n_params;
     reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_node, L.grid_n, P, io->dnode_params);
   }
@@ -601,6 +635,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     a.offG0 = L.se.offG0; a.offG1 = L.se.offG1; a.offW = L.se.offW; a.offH = L.se.offH;
     a.offDM = L.se.offDM; a.offP = L.se.offP; a.offDH = L.se.offDH; a.offRed = L.se.offRed;
     if (g->E > 0) {
+      ProfScope prof(NGPDE_PROF_BWD_EDGE, st);
       if (int rc = launch_bwd<false>(te, a, L.smem_e, L.grid_e, st)) return rc;
     } else if (dxdst) {
       NGPDE_CUDA_TRY(cudaMemsetAsync(dxdst, 0, sizeof(float) * g->N * desc->dx, st));
@@ -617,6 +652,30 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
                                                                         g->tptr, g->tpos, (int)g->N, desc->dx, io->dx);
   }
   NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
+extern "C" int ngpde_profile_enable(int32_t on) {
+  g_prof_on = on != 0;
+  return NGPDE_OK;
+}
+
+extern "C" int ngpde_profile_read(double* total_ms, int64_t* launches) {
+  NGPDE_REQUIRE(total_ms && launches, "null argument");
+  for (int s = 0; s < NGPDE_PROF_SLOTS; ++s) {
+    double ms = 0.0;
+    for (auto& pr : g_prof[s].ev) {
+      NGPDE_CUDA_TRY(cudaEventSynchronize(pr.second));
+      float t = 0.f;
+      NGPDE_CUDA_TRY(cudaEventElapsedTime(&t, pr.first, pr.second));
+      ms += t;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    total_ms[s] = ms;
+    launches[s] = (int64_t)g_prof[s].ev.size();
+    g_prof[s].ev.clear();
+  }
   return NGPDE_OK;
 }
 

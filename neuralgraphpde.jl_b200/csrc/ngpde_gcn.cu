@@ -158,7 +158,7 @@ __global__ void axpy_stages_kernel(float* __restrict__ out, const float* __restr
   const float* ks[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
   const float cs[8] = {c0, c1, c2, c3, c4, c5, c6, c7};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float v = u[i];
+    float v = u ? u[i] : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (j < nk) v = fmaf(cs[j], ks[j][i], v);
@@ -350,7 +350,7 @@ extern "C" int ngpde_aggregate(ngpde_graph_t g, int32_t aggr, const float* x, in
 
 extern "C" int ngpde_axpy_stages(float* out, const float* u, const float* const* k, const float* coef, int32_t nk,
                                  int64_t n, void* stream) {
-  NGPDE_REQUIRE(out && u && nk >= 0 && nk <= 8 && n >= 0, "bad argument");
+  NGPDE_REQUIRE(out && nk >= 0 && nk <= 8 && n >= 0, "bad argument");
   NGPDE_REQUIRE(nk == 0 || (k && coef), "null stage arrays");
   if (n == 0) return NGPDE_OK;
   const float* ks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

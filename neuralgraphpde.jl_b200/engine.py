@@ -1,0 +1,91 @@
+"""Preallocated right-hand-side runner: one message-passing layer bound to a graph, its buffers and workspace, calling
+the C ABI directly (no autograd bookkeeping, no allocator traffic) -- what an ODE integration loop or a benchmark calls
+thousands of times.  `forward()` evaluates y = layer(x); `backward()` the VJP w.r.t. (x, ps) for the cotangent in
+`self.dy`.  Optionally the forward+backward pair is captured once into a CUDA graph and replayed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib, ops
+from .lux import ComponentArray
+
+Tensor = torch.Tensor
+
+
+class RhsRunner:
+    def __init__(self, layer, x: Tensor, ps, st, use_cuda_graph: bool = False):
+        if not hasattr(layer, "prepare"):
+            raise TypeError("RhsRunner binds one of ExplicitEdgeConv / VMHConv / MPPDEConv / GNOConv")
+        self.lib = _lib.load()
+        (x_rm, phi, node, self.handle, self.desc, self.snode, self.edata, self.theta, dm, dy) = layer.prepare(x, ps, st)
+        dev = x_rm.device
+        self.dev = dev
+        self.x = x_rm.detach().clone()
+        self.phi = phi.detach().contiguous()
+        self.node = None if node is None else node.detach().contiguous()
+        self.has_node = self.desc.node.n_layers > 0
+        N = self.x.shape[0]
+        self.mbar = torch.empty((N, dm), dtype=torch.float32, device=dev)
+        self.y = torch.empty((N, dy), dtype=torch.float32, device=dev) if self.has_node else self.mbar
+        self.dy = torch.zeros_like(self.y)
+        self.dx = torch.empty_like(self.x)
+        self.dphi = torch.empty_like(self.phi)
+        self.dnode = None if self.node is None else torch.empty_like(self.node)
+        with torch.cuda.device(dev):
+            nbytes = self.lib.ngpde_conv_workspace_bytes(self.handle, C.byref(self.desc), 1)
+            if nbytes == 0:
+                _lib.check(-1)
+        self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        p = ops._ptr
+        self.io = _lib.ConvIO(x=p(self.x), snode=p(self.snode), edata=p(self.edata), theta=p(self.theta),
+                              phi_params=p(self.phi), node_params=p(self.node), mbar=p(self.mbar), y=p(self.y),
+                              dy=p(self.dy), dx=p(self.dx), dphi_params=p(self.dphi), dnode_params=p(self.dnode))
+        fam = ops._FAMILY_FN[self.desc.family]
+        self._fwd = getattr(self.lib, f"ngpde_{fam}_forward")
+        self._bwd = getattr(self.lib, f"ngpde_{fam}_backward")
+        self.launches_fwd = 2 if self.has_node else 1
+        self.launches_bwd = 8 if self.has_node else 5
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        if use_cuda_graph:
+            self.capture()
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def forward(self) -> Tensor:
+        _lib.check(self._fwd(self.handle, C.byref(self.desc), C.byref(self.io), None, 0, self._stream()))
+        ops.LAUNCHES["count"] += self.launches_fwd
+        return self.y
+
+    def backward(self):
+        _lib.check(self._bwd(self.handle, C.byref(self.desc), C.byref(self.io), self.ws.data_ptr(), self.ws.numel(),
+                             self._stream()))
+        ops.LAUNCHES["count"] += self.launches_bwd
+        return self.dx, self.dphi, self.dnode
+
+    def capture(self):
+        """Capture forward+backward into one CUDA graph (launch-latency-bound configs such as C1)."""
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self.forward()
+            self.backward()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.forward()
+            self.backward()
+
+    def step(self):
+        """One RHS evaluation, forward + VJP."""
+        if self.graph is not None:
+            self.graph.replay()
+            ops.LAUNCHES["count"] += self.launches_fwd + self.launches_bwd
+        else:
+            self.forward()
+            self.backward()

@@ -119,7 +119,8 @@ class ExplicitEdgeConv(AbstractGNNContainerLayer):
         self.initialgraph = wrapgraph(initialgraph)
         self.aggr = _aggr_name(aggr)
 
-    def __call__(self, x, ps, st: NT):
+    def prepare(self, x, ps, st: NT):
+        """Everything one C-ABI call needs: (x [N,dx], phi params, node params, handle, desc, snode, edata, theta, dm, dy)."""
         g: GNNGraph = st.graph
         xs = _named(x)
         if "x" not in g.ndata:
@@ -132,9 +133,10 @@ class ExplicitEdgeConv(AbstractGNNContainerLayer):
         dhs = snode.shape[1] - g.ndata["x"].shape[0]
         phi = mlp_spec(self.ϕ)
         desc = _conv_desc("explicit_edge_conv", self.aggr, x_rm.shape[1], dhs, g.ndata["x"].shape[0], 0, 0, phi, None)
-        y = ops.ConvFunction.apply(x_rm, flat_params(ps, _nparams(phi)), None, g.handle(dev), desc, snode, None, None,
-                                   phi[-1][1], phi[-1][1])
-        return from_rowmajor(y), st
+        return (x_rm, flat_params(ps, _nparams(phi)), None, g.handle(dev), desc, snode, None, None, phi[-1][1], phi[-1][1])
+
+    def __call__(self, x, ps, st: NT):
+        return from_rowmajor(ops.ConvFunction.apply(*self.prepare(x, ps, st))), st
 
 
 class VMHConv(AbstractGNNContainerLayer):
@@ -147,7 +149,7 @@ class VMHConv(AbstractGNNContainerLayer):
         self.initialgraph = wrapgraph(initialgraph)
         self.aggr = _aggr_name(aggr)
 
-    def __call__(self, x, ps, st: NT):
+    def prepare(self, x, ps, st: NT):
         g: GNNGraph = st.graph
         xs = _named(x)
         if "x" not in g.ndata:
@@ -160,9 +162,11 @@ class VMHConv(AbstractGNNContainerLayer):
         dpos = g.ndata["x"].shape[0]
         phi, gamma = mlp_spec(self.ϕ), mlp_spec(self.γ)
         desc = _conv_desc("vmh_conv", self.aggr, x_rm.shape[1], snode.shape[1] - dpos, dpos, 0, 0, phi, gamma)
-        y = ops.ConvFunction.apply(x_rm, flat_params(ps.ϕ, _nparams(phi)), flat_params(ps.γ, _nparams(gamma)),
-                                   g.handle(dev), desc, snode, None, None, phi[-1][1], gamma[-1][1])
-        return from_rowmajor(y), st
+        return (x_rm, flat_params(ps.ϕ, _nparams(phi)), flat_params(ps.γ, _nparams(gamma)), g.handle(dev), desc, snode,
+                None, None, phi[-1][1], gamma[-1][1])
+
+    def __call__(self, x, ps, st: NT):
+        return from_rowmajor(ops.ConvFunction.apply(*self.prepare(x, ps, st))), st
 
 
 class MPPDEConv(AbstractGNNContainerLayer):
@@ -175,7 +179,7 @@ class MPPDEConv(AbstractGNNContainerLayer):
         self.initialgraph = wrapgraph(initialgraph)
         self.aggr = _aggr_name(aggr)
 
-    def __call__(self, x: Tensor, ps, st: NT):
+    def prepare(self, x: Tensor, ps, st: NT):
         g: GNNGraph = st.graph
         dev = x.device
         x_rm = rowmajor(x)
@@ -189,9 +193,11 @@ class MPPDEConv(AbstractGNNContainerLayer):
         phi, psi = mlp_spec(self.ϕ), mlp_spec(self.ψ)
         desc = _conv_desc("mppde_conv", self.aggr, x_rm.shape[1], 0 if snode is None else snode.shape[1], 0,
                           0 if edata is None else edata.shape[1], 0 if theta is None else theta.shape[1], phi, psi)
-        y = ops.ConvFunction.apply(x_rm, flat_params(ps.ϕ, _nparams(phi)), flat_params(ps.ψ, _nparams(psi)),
-                                   g.handle(dev), desc, snode, edata, theta, phi[-1][1], psi[-1][1])
-        return from_rowmajor(y), st
+        return (x_rm, flat_params(ps.ϕ, _nparams(phi)), flat_params(ps.ψ, _nparams(psi)), g.handle(dev), desc, snode,
+                edata, theta, phi[-1][1], psi[-1][1])
+
+    def __call__(self, x: Tensor, ps, st: NT):
+        return from_rowmajor(ops.ConvFunction.apply(*self.prepare(x, ps, st))), st
 
 
 class GNOConv(AbstractGNNContainerLayer):
@@ -214,7 +220,7 @@ class GNOConv(AbstractGNNContainerLayer):
                             init_bias=init_bias)
         self.ϕ = ϕ
 
-    def __call__(self, x: Tensor, ps, st: NT):
+    def prepare(self, x: Tensor, ps, st: NT):
         g: GNNGraph = st.graph
         dev = x.device
         x_rm = rowmajor(x)
@@ -224,9 +230,11 @@ class GNOConv(AbstractGNNContainerLayer):
         phi, lin = mlp_spec(self.ϕ), self.linear.spec()
         desc = _conv_desc("gno_conv", self.aggr, x_rm.shape[1], 0 if snode is None else snode.shape[1], 0,
                           0 if edata is None else edata.shape[1], 0, phi, lin, self.in_chs, self.out_chs)
-        y = ops.ConvFunction.apply(x_rm, flat_params(ps.ϕ, _nparams(phi)), flat_params(ps.linear, _nparams(lin)),
-                                   g.handle(dev), desc, snode, edata, None, self.out_chs, self.out_chs)
-        return from_rowmajor(y), st
+        return (x_rm, flat_params(ps.ϕ, _nparams(phi)), flat_params(ps.linear, _nparams(lin)), g.handle(dev), desc, snode,
+                edata, None, self.out_chs, self.out_chs)
+
+    def __call__(self, x: Tensor, ps, st: NT):
+        return from_rowmajor(ops.ConvFunction.apply(*self.prepare(x, ps, st))), st
 
 
 class GCNConv(AbstractGNNLayer):

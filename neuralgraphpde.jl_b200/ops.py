@@ -170,3 +170,29 @@ def axpy_stages(out: Tensor, u: Tensor, ks, coefs) -> Tensor:
         _lib.check(lib.ngpde_axpy_stages(out.data_ptr(), u.data_ptr(), arr, cf, nk, u.numel(), _stream(u.device)))
     LAUNCHES["count"] += 1
     return out
+
+
+class AxpyStagesFunction(torch.autograd.Function):
+    """Differentiable `u + sum_i c_i k_i` (the Runge-Kutta stage combination) on the fused axpy kernel."""
+
+    @staticmethod
+    def forward(ctx, coefs, u: Tensor, *ks: Tensor):
+        u = u.contiguous()
+        ks = [k.contiguous() for k in ks]
+        ctx.coefs = tuple(float(c) for c in coefs)
+        return axpy_stages(torch.empty_like(u), u, ks, ctx.coefs)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        g = g.contiguous()
+        lib = _lib.load()
+        outs = []
+        for c in ctx.coefs:
+            o = torch.empty_like(g)
+            arr = (C.c_void_p * 1)(g.data_ptr())
+            cf = (C.c_float * 1)(c)
+            with torch.cuda.device(g.device):
+                _lib.check(lib.ngpde_axpy_stages(o.data_ptr(), None, arr, cf, 1, g.numel(), _stream(g.device)))
+            LAUNCHES["count"] += 1
+            outs.append(o)
+        return (None, g, *outs)

@@ -604,3 +604,35 @@ def radius_graph(n: int, mean_deg: float, rng: np.random.Generator):
     s, t = np.concatenate(s_l).astype(np.int64), np.concatenate(t_l).astype(np.int64)
     p = rng.permutation(len(s))
     return s[p], t[p], pos.T.copy()
+
+
+# --------------------------------------------------------------------------------------
+# Fixed-step Runge-Kutta restatement ([DEP] DifferentialEquations.jl `RK4()` / `Tsit5()` with adaptive=false;
+# call sites /root/reference/docs/src/tutorials/graph_node.md:59-66, VMH.md:87).  Plain torch-CPU axpys.
+# --------------------------------------------------------------------------------------
+
+RK4_TABLEAU = (((), (0.5,), (0.0, 0.5), (0.0, 0.0, 1.0)), (1 / 6, 1 / 3, 1 / 3, 1 / 6))
+TSIT5_TABLEAU = (
+    ((), (0.161,), (-0.008480655492356989, 0.335480655492357),
+     (2.8971530571054935, -6.359448489975075, 4.3622954328695815),
+     (5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525),
+     (5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383)),
+    (0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774),
+)
+
+
+def integrate_fixed(rhs: Callable[[Tensor], Tensor], u0: Tensor, t0: float, t1: float, dt: float,
+                    method: str = "rk4") -> Tensor:
+    A, b = RK4_TABLEAU if method == "rk4" else TSIT5_TABLEAU
+    u = u0
+    for _ in range(int(round((t1 - t0) / dt))):
+        ks: List[Tensor] = []
+        for row in A:
+            ui = u
+            for a, k in zip(row, ks):
+                if a != 0.0:
+                    ui = ui + (dt * a) * k
+            ks.append(rhs(ui))
+        for w, k in zip(b, ks):
+            u = u + (dt * w) * k
+    return u

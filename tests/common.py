@@ -6,6 +6,10 @@ import ngpde
 import ngpde_oracle as orc
 
 
+# the product's NT stores field names NFKC-normalised (U+03C6); the oracle spells them as the reference does (U+03D5)
+_ORACLE_KEY = {"\u03c6": "\u03d5"}
+
+
 def relerr(a: torch.Tensor, b: torch.Tensor) -> float:
     """Max-norm relative error  max|a-b| / max|b|  (the tolerance measure of every float parity test)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
@@ -22,6 +26,7 @@ def tree_to_cpu(ps, dtype=torch.float32):
         ps = ps.to_tree()
     out = {}
     for k, v in ps.items():
+        k = _ORACLE_KEY.get(k, k)
         out[k] = v.detach().cpu().to(dtype).contiguous().clone() if isinstance(v, torch.Tensor) else tree_to_cpu(v, dtype)
     return out
 
@@ -68,3 +73,52 @@ def random_graph(rng, n, e, device="cpu", **kw):
     s = torch.from_numpy(rng.integers(0, n, e))
     t = torch.from_numpy(rng.integers(0, n, e))
     return ngpde.GNNGraph(s.to(device), t.to(device), num_nodes=n, **kw)
+
+
+def oracle_forward(layer, x: torch.Tensor, ps: dict, og: orc.OGraph, edge_weight=None) -> torch.Tensor:
+    """Evaluate the oracle's restatement of `layer` (an ngpde layer object or a Chain of them) on CPU tensors.
+    `ps` is the tree produced by tree_to_cpu (oracle key spelling)."""
+    from ngpde.lux import mlp_spec
+    if isinstance(layer, ngpde.Chain):
+        for i, l in enumerate(layer.layers):
+            x = oracle_forward(l, x, ps[f"layer_{i + 1}"], og)
+        return x
+    if isinstance(layer, ngpde.ExplicitEdgeConv):
+        return orc.explicit_edge_conv(x, ps, og, mlp_spec(layer.ϕ), layer.aggr)
+    if isinstance(layer, ngpde.VMHConv):
+        return orc.vmh_conv(x, ps, og, mlp_spec(layer.ϕ), mlp_spec(layer.γ), layer.aggr)
+    if isinstance(layer, ngpde.MPPDEConv):
+        return orc.mppde_conv(x, ps, og, mlp_spec(layer.ϕ), mlp_spec(layer.ψ), layer.aggr)
+    if isinstance(layer, ngpde.GNOConv):
+        return orc.gno_conv(x, ps, og, layer.in_chs, layer.out_chs, mlp_spec(layer.ϕ), layer.linear.activation,
+                            layer.aggr, layer.bias)
+    if isinstance(layer, ngpde.GCNConv):
+        return orc.gcn_conv(x, ps, og, layer.in_chs, layer.out_chs, layer.activation, layer.add_self_loops,
+                            layer.use_edge_weight, edge_weight, layer.bias)
+    raise TypeError(type(layer))
+
+
+def product_fwd_bwd(layer, x, ps, st, dy=None, **kw):
+    """y, dx, flat dps of the CUDA path (ps: NT tree on the device; gradients in ComponentArray order)."""
+    x = x.detach().clone().requires_grad_(True)
+    ca = ngpde.ComponentArray(ps)
+    ca.data.requires_grad_(True)
+    y, _ = layer(x, ca, st, **kw)
+    if dy is None:
+        return y.detach(), None, None
+    y.backward(dy)
+    return y.detach(), x.grad.detach(), ca.data.grad.detach()
+
+
+def oracle_fwd_bwd(layer, x, ps, g, dy=None, dtype=torch.float32, **kw):
+    """Same through the oracle (torch autograd over the unfused restatement), on CPU in `dtype`."""
+    og = to_ograph(g, dtype)
+    xc = x.detach().cpu().to(dtype).clone().requires_grad_(dy is not None)
+    pc = tree_to_cpu(ps, dtype)
+    if dy is not None:
+        tree_requires_grad(pc)
+    y = oracle_forward(layer, xc, pc, og, **kw)
+    if dy is None:
+        return y.detach(), None, None
+    y.backward(dy.detach().cpu().to(y.dtype))
+    return y.detach(), xc.grad.detach(), flat_grad(pc)

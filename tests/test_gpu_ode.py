@@ -1,0 +1,41 @@
+"""Fixed-step Neural-ODE trajectory parity (north_star: <= 1e-4 on the trajectory at fixed step), forward and the
+discrete-adjoint gradient, for the C1 (Tsit5) and C3 (RK4) model shapes."""
+import numpy as np
+import pytest
+import torch
+
+import ngpde
+import ngpde_oracle as orc
+from common import flat_grad, oracle_forward, relerr, to_ograph, tree_requires_grad, tree_to_cpu
+from ngpde import ode, workloads
+
+pytestmark = pytest.mark.gpu
+TRAJ_TOL = 1e-4
+
+
+def _oracle_traj(w, method, dt, t1, dtype, with_grad):
+    og = to_ograph(w.graph, dtype)
+    pc = tree_to_cpu(w.ps, dtype)
+    if with_grad:
+        tree_requires_grad(pc)
+    u0 = w.x.detach().cpu().to(dtype)
+    uT = orc.integrate_fixed(lambda u: oracle_forward(w.layer, u, pc, og), u0, 0.0, t1, dt, method)
+    if not with_grad:
+        return uT.detach(), None
+    (uT ** 2).mean().backward()
+    return uT.detach(), flat_grad(pc)
+
+
+@pytest.mark.parametrize("name,method,kw,dt,t1", [("c1", "tsit5", {}, 0.05, 1.0), ("c3", "rk4", {"side": 20}, 0.05, 0.5)])
+def test_trajectory_and_adjoint(name, method, kw, dt, t1):
+    w = workloads.WORKLOADS[name]("cuda", **kw)
+    ca = ngpde.ComponentArray(w.ps)
+    ca.data.requires_grad_(True)
+    uT, _, evals = ode.solve_fixed(w.layer, w.x, ca, w.st, (0.0, t1), dt, method)
+    nsteps = int(round(t1 / dt))
+    assert evals == nsteps * (6 if method == "tsit5" else 4)
+    (uT ** 2).mean().backward()
+    u32, g32 = _oracle_traj(w, method, dt, t1, torch.float32, True)
+    u64, g64 = _oracle_traj(w, method, dt, t1, torch.float64, True)
+    errs = dict(u32=relerr(uT, u32), u64=relerr(uT, u64), g32=relerr(ca.data.grad, g32), g64=relerr(ca.data.grad, g64))
+    assert all(v <= TRAJ_TOL for v in errs.values()), errs
