@@ -131,6 +131,10 @@ typedef struct ngpde_graph* ngpde_graph_t;
 /* ---- library ---- */
 int ngpde_version(void);
 const char* ngpde_last_error(void);
+/* Process-wide switches (benchmarks and tests only).  NGPDE_OPT_TENSOR_CORES: 1 (default) runs MLPs whose layers are at
+ * most 64 wide on the tcgen05 tensor-core kernels (3xTF32, fp32-accurate); 0 forces the FP32-FFMA kernels everywhere. */
+enum { NGPDE_OPT_TENSOR_CORES = 0 };
+int ngpde_set_option(int32_t option, int32_t value);
 
 /* ---- graph handle: replaces GNNGraph's per-call gather/scatter index use and GCNConv's per-call
  * add_self_loops / degree / adjacency_matrix (layers.jl:210-225).  Builds, on the device: the stable
@@ -152,7 +156,9 @@ int64_t ngpde_graph_num_edges(ngpde_graph_t g);
  * atomic-free aggregation (call sites layers.jl:228-232, 656).  w may be NULL; it is [E] in ORIGINAL order. ---- */
 int ngpde_aggregate(ngpde_graph_t g, int32_t aggr, const float* x, int32_t d, const float* w, float* out, void* stream);
 
-/* ---- MLP message-passing layers ---- */
+/* ---- MLP message-passing layers.  Both calls need a caller-owned device workspace of at least
+ * ngpde_conv_workspace_bytes(g, desc, backward) bytes, 256-byte aligned (forward: prepared weight images of the
+ * tensor-core path; backward: transposed weights, per-edge source gradients, per-CTA parameter-gradient partials). ---- */
 size_t ngpde_conv_workspace_bytes(ngpde_graph_t g, const ngpde_conv_desc* desc, int32_t backward);
 int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_conv_io* io, void* workspace,
                        size_t workspace_bytes, void* stream);

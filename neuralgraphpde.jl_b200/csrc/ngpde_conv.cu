@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "ngpde_conv_kernels.cuh"
+#include "ngpde_tc.cuh"
 
 namespace ngpde {
 namespace {
@@ -33,6 +34,49 @@ struct ProfScope {
     if (on) cudaEventRecord(e1, st);
   }
 };
+
+// ---- tensor-core (tcgen05) path selection ----
+constexpr int kSmemMaxTc = 227 * 1024;
+bool g_use_tc = true;
+
+int pad16(int x) { return (x + 15) / 16 * 16; }
+
+// Lays out the prepared weight block of `m` and decides whether the tcgen05 kernels can run it.
+bool tc_make_layout(const MlpDev& m, bool contract, bool addend, int dout, bool node, TcLayout* lay, int* smem_bytes,
+                    int* off_groups, int* group_bytes) {
+  if (!g_use_tc || contract || addend || m.L < 1 || m.L > NGPDE_MAX_LAYERS) return false;
+  *lay = TcLayout{};
+  lay->L = m.L;
+  int off = 0, kmax = 0;
+  for (int l = 0; l < m.L; ++l) {
+    const int K = m.dims[l], N = m.dims[l + 1];
+    if (N > TC_MAXN || K > 192) return false;
+    lay->K[l] = K;
+    lay->N[l] = N;
+    lay->Kp[l] = pad16(K);
+    lay->Np[l] = pad16(N);
+    lay->img_floats[l] = ((lay->Np[l] + 31) / 32) * lay->Kp[l] * 32;
+    lay->img_off[l] = off;
+    off += 2 * lay->img_floats[l];  // Kp is a multiple of 16, so every image is a multiple of 2 KB
+    kmax = std::max(kmax, lay->Kp[l]);
+  }
+  lay->bias_off = off;
+  off += m.L * TC_MAXN;
+  lay->block_floats = (off + 3) & ~3;
+  lay->kmax = kmax;
+  lay->cols_group = TC_MAXN + 2 * kmax;
+  const int need = TC_GROUPS * lay->cols_group;
+  if (need > 512) return false;
+  int cols = 32;
+  while (cols < need) cols *= 2;
+  lay->tmem_cols = cols;
+  *off_groups = (4 * lay->block_floats + 127) & ~127;
+  *group_bytes = node ? 128 : ((TC_TILE * (dout + 1) * 4 + 127) & ~127);
+  const int total = 1024 + *off_groups + TC_GROUPS * *group_bytes;
+  // at least half of the SM's shared memory, so that two CTAs (and two 512-column TMEM allocations) never share an SM
+  *smem_bytes = std::max(total, 116 * 1024);
+  return total <= kSmemMaxTc;
+}
 
 // host copy of the sign table coef_dst (the device versions live in the kernels header)
 int coef_dst_host(int kind) { return kind == SEG_DST || kind == SEG_SMD || kind == SEG_DMS; }
@@ -465,11 +509,84 @@ int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* para
 
 using namespace ngpde;
 
+namespace {
+
+struct TcPhase {
+  bool on = false;
+  TcLayout lay{};
+  int smem = 0, off_groups = 0, group_bytes = 0;
+  size_t ws_off = 0;  // byte offset of the prepared weight block in the forward workspace
+};
+
+struct FwdPlan {
+  TcPhase edge, node;
+  size_t ws_bytes = 0;
+};
+
+FwdPlan fwd_plan(const Plan& p, int aggr) {
+  FwdPlan f;
+  size_t off = 0;
+  // max/min: the backward's tie mask compares recomputed messages with the forward's bit for bit, so both must run
+  // the same arithmetic -- those aggregations stay on the FFMA kernels until the backward has a tensor-core twin.
+  const bool aggr_ok = aggr == NGPDE_AGGR_SUM || aggr == NGPDE_AGGR_MEAN;
+  f.edge.on = aggr_ok && tc_make_layout(p.phi, p.contract, false, p.dm, false, &f.edge.lay, &f.edge.smem, &f.edge.off_groups,
+                             &f.edge.group_bytes);
+  if (f.edge.on) {
+    f.edge.ws_off = off;
+    off = align256(off + 4 * (size_t)f.edge.lay.block_floats);
+  }
+  if (p.has_node) {
+    f.node.on = tc_make_layout(p.node, 0, p.node_addend, p.dy, true, &f.node.lay, &f.node.smem, &f.node.off_groups,
+                               &f.node.group_bytes);
+    if (f.node.on) {
+      f.node.ws_off = off;
+      off = align256(off + 4 * (size_t)f.node.lay.block_floats);
+    }
+  }
+  f.ws_bytes = off;
+  return f;
+}
+
+template <bool NODE>
+int launch_fwd_tc(const ngpde_graph* g, const TcPhase& t, const MlpDev& mlp, const float* params, const FwdArgs& base,
+                  float* wblock, cudaStream_t st) {
+  if (base.tg.n_units <= 0) return NGPDE_OK;
+  tc_prep_weights_kernel<<<32, 256, 0, st>>>(params, mlp, t.lay, wblock);
+  TcFwdArgs a{};
+  a.tg = base.tg;
+  std::memcpy(a.arr, base.arr, sizeof(a.arr));
+  std::memcpy(a.ld, base.ld, sizeof(a.ld));
+  a.n_segs = base.n_segs;
+  std::memcpy(a.segs, base.segs, sizeof(a.segs));
+  a.lay = t.lay;
+  for (int l = 0; l < mlp.L; ++l) a.act[l] = mlp.act[l];
+  a.wblock = wblock;
+  a.aggr = base.aggr;
+  a.dout = base.dout;
+  a.out = base.out;
+  a.off_groups = t.off_groups;
+  a.group_bytes = t.group_bytes;
+  NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_fwd_tc_kernel<NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
+  const int grid = std::max(1, std::min((a.tg.n_units + TC_GROUPS - 1) / TC_GROUPS, g->num_sms));
+  mp_fwd_tc_kernel<NODE><<<grid, TC_THREADS, t.smem, st>>>(a);
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
+}  // namespace
+
+extern "C" int ngpde_set_option(int32_t option, int32_t value) {
+  switch (option) {
+    case NGPDE_OPT_TENSOR_CORES: g_use_tc = value != 0; return NGPDE_OK;
+    default: set_error("unknown option %d", option); return NGPDE_ERR_INVALID;
+  }
+}
+
 extern "C" size_t ngpde_conv_workspace_bytes(ngpde_graph_t g, const ngpde_conv_desc* desc, int32_t backward) {
   if (!g || !desc) return 0;
-  if (!backward) return 256;
   Plan p;
   if (make_plan(g, *desc, &p)) return 0;
+  if (!backward) return fwd_plan(p, desc->aggr).ws_bytes + 256;
   BwdLayout L;
   if (bwd_layout(g, *desc, p, &L)) return 0;
   return L.total + 256;
@@ -477,14 +594,19 @@ extern "C" size_t ngpde_conv_workspace_bytes(ngpde_graph_t g, const ngpde_conv_d
 
 extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_conv_io* io,
                                   void* workspace, size_t workspace_bytes, void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   NGPDE_REQUIRE(g && desc && io, "null argument");
   Plan p;
   if (int rc = make_plan(g, *desc, &p)) return rc;
   if (g->N == 0) return NGPDE_OK;
   if (int rc = check_io(*desc, p, *io, false)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const FwdPlan fp = fwd_plan(p, desc->aggr);
+  if (fp.ws_bytes > 0 && (workspace == nullptr || workspace_bytes < fp.ws_bytes)) {
+    set_error("forward workspace too small: %zu bytes given, %zu needed (ngpde_conv_workspace_bytes(g, desc, 0))",
+              workspace_bytes, fp.ws_bytes);
+    return NGPDE_ERR_WORKSPACE;
+  }
+  char* fws = static_cast<char*>(workspace);
 
   // ---- edge phase ----
   int te = 0, smem = 0;
@@ -511,7 +633,14 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
   a.offA = fs.offA; a.offB = fs.offB; a.offW = fs.offW; a.offH = fs.offH;
   {
     ProfScope prof(NGPDE_PROF_FWD_EDGE, st);
-    if (int rc = launch_fwd<false>(te, a, smem, g->num_sms, st)) return rc;
+    if (fp.edge.on) {
+      a.tg.unit_ptr = g->units[2];
+      a.tg.n_units = g->n_units[2];
+      if (int rc = launch_fwd_tc<false>(g, fp.edge, p.phi, io->phi_params, a, reinterpret_cast<float*>(fws + fp.edge.ws_off), st))
+        return rc;
+    } else {
+      if (int rc = launch_fwd<false>(te, a, smem, g->num_sms, st)) return rc;
+    }
   }
 
   // ---- node phase ----
@@ -532,7 +661,13 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
     n.addend = p.node_addend ? io->mbar : nullptr;
     n.offA = fs.offA; n.offB = fs.offB; n.offW = fs.offW; n.offH = fs.offH;
     ProfScope prof(NGPDE_PROF_FWD_NODE, st);
-    if (int rc = launch_fwd<true>(te, n, smem, g->num_sms, st)) return rc;
+    if (fp.node.on) {
+      n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
+      if (int rc = launch_fwd_tc<true>(g, fp.node, p.node, io->node_params, n, reinterpret_cast<float*>(fws + fp.node.ws_off), st))
+        return rc;
+    } else {
+      if (int rc = launch_fwd<true>(te, n, smem, g->num_sms, st)) return rc;
+    }
   }
   return NGPDE_OK;
 }

@@ -39,7 +39,11 @@ class RhsRunner:
             nbytes = self.lib.ngpde_conv_workspace_bytes(self.handle, C.byref(self.desc), 1)
             if nbytes == 0:
                 _lib.check(-1)
+            nbytes_f = self.lib.ngpde_conv_workspace_bytes(self.handle, C.byref(self.desc), 0)
+            if nbytes_f == 0:
+                _lib.check(-1)
         self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        self.ws_fwd = torch.empty(int(nbytes_f), dtype=torch.uint8, device=dev)
         p = ops._ptr
         self.io = _lib.ConvIO(x=p(self.x), snode=p(self.snode), edata=p(self.edata), theta=p(self.theta),
                               phi_params=p(self.phi), node_params=p(self.node), mbar=p(self.mbar), y=p(self.y),
@@ -57,7 +61,8 @@ class RhsRunner:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def forward(self) -> Tensor:
-        _lib.check(self._fwd(self.handle, C.byref(self.desc), C.byref(self.io), None, 0, self._stream()))
+        _lib.check(self._fwd(self.handle, C.byref(self.desc), C.byref(self.io), self.ws_fwd.data_ptr(), self.ws_fwd.numel(),
+                             self._stream()))
         ops.LAUNCHES["count"] += self.launches_fwd
         return self.y
 

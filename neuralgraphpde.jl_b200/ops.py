@@ -58,8 +58,12 @@ class ConvFunction(torch.autograd.Function):
         io = _lib.ConvIO(x=_ptr(x), snode=_ptr(snode), edata=_ptr(edata), theta=_ptr(theta),
                          phi_params=_ptr(phi_params), node_params=_ptr(node_params), mbar=_ptr(mbar), y=_ptr(y))
         with torch.cuda.device(dev):
+            nbytes = lib.ngpde_conv_workspace_bytes(handle, C.byref(desc), 0)
+            if nbytes == 0:
+                _lib.check(-1)
+            ws = _workspace(nbytes, dev)
             fn = getattr(lib, f"ngpde_{_FAMILY_FN[desc.family]}_forward")
-            _lib.check(fn(handle, C.byref(desc), C.byref(io), None, 0, _stream(dev)))
+            _lib.check(fn(handle, C.byref(desc), C.byref(io), ws.data_ptr(), ws.numel(), _stream(dev)))
         LAUNCHES["count"] += 2 if has_node else 1
         ctx.save_for_backward(x, phi_params, node_params if node_params is not None else x.new_empty(0), mbar)
         ctx.handle, ctx.desc = handle, desc

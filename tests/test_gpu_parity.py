@@ -115,14 +115,19 @@ def test_spectralconv_known_answer_on_cuda():
         assert torch.equal(got, orc.spectral_conv(f(xs), og, n))  # and bit-exact with the oracle's float32 run
 
 
-def test_fused_kernel_aggregation_order_bit_exact():
+@pytest.mark.parametrize("tensor_cores", [0, 1])
+def test_fused_kernel_aggregation_order_bit_exact(tensor_cores):
     # phi = a 0/1 selection matrix without bias: messages are exact copies of gathered inputs, so the fused kernel's
-    # output exposes its reduction order -- it must be the sequential stored-edge order, bit for bit.
+    # output exposes its reduction order -- it must be the sequential stored-edge order, bit for bit.  (On the
+    # tensor-core kernels a copy is exact for inputs of at most 21 significant bits -- the 3xTF32 split -- so that run
+    # uses inputs on a 2^-8 grid; it covers "+" and mean, the aggregations those kernels take.)
     rng = np.random.default_rng(11)
     n, e = 300, 5000
     s, t = rng.integers(0, n, e), rng.integers(0, n - 2, e)
     t[:400] = 9
-    pos = jl_rand(rng, 2, n)
+    q = (lambda v: torch.round(v * 256) / 256) if tensor_cores else (lambda v: v)
+    pos = q(jl_rand(rng, 2, n))
+    ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, tensor_cores)
     for aggr in ("+", "mean", "max", "min"):
         g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"x": pos}).to(DEV)
         layer = ExplicitEdgeConv(Dense(8, 3, bias=False), initialgraph=g, aggr=aggr)
@@ -132,10 +137,11 @@ def test_fused_kernel_aggregation_order_bit_exact():
         W[1, 6] = 1.0  # (pos_j - pos_i)[0]
         W[2, 1] = 1.0  # h_i[1]
         ps = NT(weight=W.T.contiguous().T.to(DEV))
-        x = jl_rand(rng, 3, n, DEV)
+        x = q(jl_rand(rng, 3, n, DEV))
         y, _ = layer(x, ps, st)
         ref, _, _ = oracle_fwd_bwd(layer, x, ps, g)
         assert torch.equal(y.cpu(), ref), aggr
+    ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, 1)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -408,3 +414,47 @@ def test_c4_large_graph_sampled_rows_against_oracle():
     yo, _, _ = oracle_fwd_bwd(w.layer, w.x.cpu()[:, idx], w.ps, sub)
     sel = torch.from_numpy(remap[rows])
     assert relerr(y.cpu()[:, torch.from_numpy(rows)], yo[:, sel]) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, 3xTF32) kernels vs FP32-FFMA kernels: both must meet the same bar
+# ------------------------------------------------------------------------------------------------------------
+
+@pytest.fixture
+def ffma_only():
+    ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, 0)
+    yield
+    ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, 1)
+
+
+def test_c3_ffma_kernels_also_meet_the_bar(ffma_only):
+    w = workloads.c3_vmh(DEV, side=40)
+    check_layer(w.layer, w.x, w.ps, w.st, w.graph)
+
+
+def test_tensor_core_and_ffma_paths_agree():
+    w = workloads.c3_vmh(DEV, side=48)
+    y_tc, _ = w.layer(w.x, w.ps, w.st)
+    ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, 0)
+    try:
+        y_ff, _ = w.layer(w.x, w.ps, w.st)
+    finally:
+        ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, 1)
+    assert not torch.equal(y_tc, y_ff)  # different kernels really ran
+    assert relerr(y_tc, y_ff) <= TOL
+
+
+@pytest.mark.parametrize("dims", [[6, 64, 64, 64, 64], [6, 16, 48, 5], [11, 33, 10], [150, 64, 7]])
+def test_tensor_core_path_odd_widths(dims):
+    rng = np.random.default_rng(31)
+    n = 700
+    s, t = rng.integers(0, n, 6000), rng.integers(0, n, 6000)
+    t[:300] = 11  # a row longer than one tile
+    dx = dims[0] // 2 - 1  # phi input = [x_i (dx); x_j - x_i (dx); pos (2)]
+    g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"x": jl_rand(rng, dims[0] - 2 * dx, n)}).to(DEV)
+    acts = ["tanh", "swish", "gelu", "sigmoid"]
+    phi = Chain(*[Dense(dims[i], dims[i + 1], acts[i % 4] if i < len(dims) - 2 else "identity") for i in range(len(dims) - 1)])
+    gam = Chain(Dense(dx + dims[-1], 40, "elu"), Dense(40, 3))
+    layer = VMHConv(phi, gam, initialgraph=g, aggr="mean")
+    ps, st = setup(rng, layer, DEV)
+    check_layer(layer, jl_rand(rng, dx, n, DEV), ps, st, g)
