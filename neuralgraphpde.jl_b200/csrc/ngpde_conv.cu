@@ -43,7 +43,7 @@ int pad16(int x) { return (x + 15) / 16 * 16; }
 
 // Lays out the prepared weight block of `m` and decides whether the tcgen05 kernels can run it.
 bool tc_make_layout(const MlpDev& m, bool contract, bool addend, int dout, bool node, TcLayout* lay, int* smem_bytes,
-                    int* off_groups, int* group_bytes) {
+                    int* off_cols, int* off_groups, int* group_bytes) {
   if (!g_use_tc || contract || addend || m.L < 1 || m.L > NGPDE_MAX_LAYERS) return false;
   *lay = TcLayout{};
   lay->L = m.L;
@@ -53,16 +53,15 @@ bool tc_make_layout(const MlpDev& m, bool contract, bool addend, int dout, bool 
     if (N > TC_MAXN || K > 192) return false;
     lay->K[l] = K;
     lay->N[l] = N;
-    lay->Kp[l] = pad16(K);
+    lay->Kd[l] = pad16(K);
+    lay->Kp[l] = lay->Kd[l] + 8;
     lay->Np[l] = pad16(N);
     lay->img_floats[l] = ((lay->Np[l] + 31) / 32) * lay->Kp[l] * 32;
     lay->img_off[l] = off;
-    off += 2 * lay->img_floats[l];  // Kp is a multiple of 16, so every image is a multiple of 2 KB
+    off += 2 * lay->img_floats[l];  // Kp is a multiple of 8, so every image is a multiple of 1 KB
     kmax = std::max(kmax, lay->Kp[l]);
   }
-  lay->bias_off = off;
-  off += m.L * TC_MAXN;
-  lay->block_floats = (off + 3) & ~3;
+  lay->block_floats = off;
   lay->kmax = kmax;
   lay->cols_group = TC_MAXN + 2 * kmax;
   const int need = TC_GROUPS * lay->cols_group;
@@ -70,7 +69,8 @@ bool tc_make_layout(const MlpDev& m, bool contract, bool addend, int dout, bool 
   int cols = 32;
   while (cols < need) cols *= 2;
   lay->tmem_cols = cols;
-  *off_groups = (4 * lay->block_floats + 127) & ~127;
+  *off_cols = 4 * lay->block_floats;
+  *off_groups = (*off_cols + (int)sizeof(TcCol) * lay->Kd[0] + 127) & ~127;
   *group_bytes = node ? 128 : ((TC_TILE * (dout + 1) * 4 + 127) & ~127);
   const int total = 1024 + *off_groups + TC_GROUPS * *group_bytes;
   // at least half of the SM's shared memory, so that two CTAs (and two 512-column TMEM allocations) never share an SM
@@ -514,7 +514,7 @@ namespace {
 struct TcPhase {
   bool on = false;
   TcLayout lay{};
-  int smem = 0, off_groups = 0, group_bytes = 0;
+  int smem = 0, off_cols = 0, off_groups = 0, group_bytes = 0;
   size_t ws_off = 0;  // byte offset of the prepared weight block in the forward workspace
 };
 
@@ -529,15 +529,15 @@ FwdPlan fwd_plan(const Plan& p, int aggr) {
   // max/min: the backward's tie mask compares recomputed messages with the forward's bit for bit, so both must run
   // the same arithmetic -- those aggregations stay on the FFMA kernels until the backward has a tensor-core twin.
   const bool aggr_ok = aggr == NGPDE_AGGR_SUM || aggr == NGPDE_AGGR_MEAN;
-  f.edge.on = aggr_ok && tc_make_layout(p.phi, p.contract, false, p.dm, false, &f.edge.lay, &f.edge.smem, &f.edge.off_groups,
-                             &f.edge.group_bytes);
+  f.edge.on = aggr_ok && tc_make_layout(p.phi, p.contract, false, p.dm, false, &f.edge.lay, &f.edge.smem, &f.edge.off_cols,
+                                        &f.edge.off_groups, &f.edge.group_bytes);
   if (f.edge.on) {
     f.edge.ws_off = off;
     off = align256(off + 4 * (size_t)f.edge.lay.block_floats);
   }
   if (p.has_node) {
-    f.node.on = tc_make_layout(p.node, 0, p.node_addend, p.dy, true, &f.node.lay, &f.node.smem, &f.node.off_groups,
-                               &f.node.group_bytes);
+    f.node.on = tc_make_layout(p.node, 0, p.node_addend, p.dy, true, &f.node.lay, &f.node.smem, &f.node.off_cols,
+                               &f.node.off_groups, &f.node.group_bytes);
     if (f.node.on) {
       f.node.ws_off = off;
       off = align256(off + 4 * (size_t)f.node.lay.block_floats);
@@ -564,6 +564,7 @@ int launch_fwd_tc(const ngpde_graph* g, const TcPhase& t, const MlpDev& mlp, con
   a.aggr = base.aggr;
   a.dout = base.dout;
   a.out = base.out;
+  a.off_cols = t.off_cols;
   a.off_groups = t.off_groups;
   a.group_bytes = t.group_bytes;
   NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_fwd_tc_kernel<NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));

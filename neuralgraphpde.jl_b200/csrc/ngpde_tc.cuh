@@ -16,22 +16,34 @@
 
 namespace ngpde {
 
-constexpr int TC_TILE = 128;   // rows per tile = MMA M
-constexpr int TC_GROUPS = 2;   // 128-thread groups per CTA
-constexpr int TC_MAXN = 64;    // widest layer output the path accepts
-constexpr int TC_THREADS = TC_TILE * TC_GROUPS;
+constexpr int TC_TILE = 128;    // rows per tile = MMA M
+constexpr int TC_GTHREADS = 256;  // threads per group: 8 warps = 4 TMEM lane quarters x 2 column halves
+constexpr int TC_GROUPS = 2;    // groups per CTA, each with its own tile in flight
+constexpr int TC_MAXN = 64;     // widest layer output the path accepts
+constexpr int TC_THREADS = TC_GTHREADS * TC_GROUPS;
 
+// Shapes of one MLP on the tensor-core path.  Layer l reads A columns [0, Kd) (data, zero padded), a "ones" block at
+// column Kd (1, 0, ..., 0) that multiplies the bias row of the weight image -- so the bias add costs no epilogue
+// instruction -- and writes Np = pad16(N) accumulator columns.
 struct TcLayout {
   int L;
   int K[NGPDE_MAX_LAYERS], N[NGPDE_MAX_LAYERS];    // logical layer shapes
-  int Kp[NGPDE_MAX_LAYERS], Np[NGPDE_MAX_LAYERS];  // padded to multiples of 16
+  int Kd[NGPDE_MAX_LAYERS];                        // pad16(K): data columns / rows
+  int Kp[NGPDE_MAX_LAYERS];                        // Kd + 8: rows of the weight image (K extent of the MMAs)
+  int Np[NGPDE_MAX_LAYERS];                        // pad16(N)
   int img_off[NGPDE_MAX_LAYERS];                   // float offset of the hi image; the lo image follows it
   int img_floats[NGPDE_MAX_LAYERS];                // floats of one image = ceil(Np/32) * Kp * 32
-  int bias_off;                                    // float offset of biases [L][TC_MAXN]
-  int block_floats;                                // images + biases
-  int kmax;                                        // widest padded input
+  int block_floats;                                // all images
+  int kmax;                                        // widest Kp
   int cols_group;                                  // TMEM columns per group: TC_MAXN (D) + 2*kmax (A hi, A lo)
   int tmem_cols;                                   // allocation: power of two >= 32
+};
+
+// how column `c` of the MLP input is produced from the gathered arrays
+struct TcCol {
+  const float* base;  // array + column offset
+  int ld;
+  int kind;           // SEG_*
 };
 
 struct TcFwdArgs {
@@ -46,33 +58,39 @@ struct TcFwdArgs {
   int aggr;
   int dout;
   float* out;           // edge phase: mbar [N][dout]; node phase: y [N][dout]
-  int off_groups;       // byte offset of the per-group regions in dynamic shared memory
+  int off_cols;         // byte offsets into dynamic shared memory: column table, per-group regions
+  int off_groups;
   int group_bytes;
 };
 
-// ---- prepared weight block: per layer hi image, lo image (SWIZZLE_128B_BASE32B, rows = k), then the biases ----
+// ---- prepared weight block: per layer hi image then lo image (SWIZZLE_128B_BASE32B, rows = k, bias at row Kd) ----
 __global__ void tc_prep_weights_kernel(const float* __restrict__ params, MlpDev mlp, TcLayout lay, float* __restrict__ out) {
   const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   for (int l = 0; l < lay.L; ++l) {
-    const int K = lay.K[l], N = lay.N[l], Kp = lay.Kp[l];
+    const int K = lay.K[l], N = lay.N[l], Kp = lay.Kp[l], Kd = lay.Kd[l];
     const int cols = lay.img_floats[l] / Kp;  // 32 * groups
     const float* W = params + mlp.w_off[l];
+    const float* b = mlp.b_off[l] >= 0 ? params + mlp.b_off[l] : nullptr;
     float* hi = out + lay.img_off[l];
     float* lo = hi + lay.img_floats[l];
     for (int i = t0; i < Kp * cols; i += stride) {
       const int k = i / cols, n = i - k * cols;
-      const float w = (k < K && n < N) ? W[(size_t)k * N + n] : 0.f;
+      float w = 0.f;
+      if (n < N) {
+        if (k < K) w = W[(size_t)k * N + n];
+        else if (k == Kd && b != nullptr) w = b[n];
+      }
       const float h = umma::tf32_hi(w);
       const uint32_t off = umma::sw128b32_offset(n >> 5, Kp, k, n & 31);
       hi[off] = h;
       lo[off] = umma::tf32_hi(w - h);
     }
-    for (int n = t0; n < TC_MAXN; n += stride)
-      out[lay.bias_off + l * TC_MAXN + n] = (mlp.b_off[l] >= 0 && n < N) ? params[mlp.b_off[l] + n] : 0.f;
   }
 }
 
-__device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(TC_TILE) : "memory"); }
+__device__ __forceinline__ void group_bar(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(TC_GTHREADS) : "memory");
+}
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
@@ -84,27 +102,83 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                : "memory");
 }
 
-// value of input column `col` of the MLP for the item whose (src, dst, original position) are (s, d, p)
+// column table of the gather: cols[c] for c < Kd[0] (padding columns get kind = -1)
 template <class Args>
-__device__ __forceinline__ float tc_gather_value(const Args& a, int col, int s, int d, int p) {
-  float v = 0.f;
-  for (int si = 0; si < a.n_segs; ++si) {
-    const Seg sg = a.segs[si];
-    const int f = col - sg.row;
-    if (f < 0 || f >= sg.width) continue;
-    const float* __restrict__ A = a.arr[sg.arr] + sg.col + f;
-    const size_t ld = (size_t)a.ld[sg.arr];
-    switch (sg.kind) {
-      case SEG_DST: v = A[d * ld]; break;
-      case SEG_SRC: v = A[s * ld]; break;
-      case SEG_SMD: v = A[s * ld] - A[d * ld]; break;
-      case SEG_DMS: v = A[d * ld] - A[s * ld]; break;
-      case SEG_EDGE: v = A[p * ld]; break;
-      default: v = A[(size_t)(p / a.tg.gdiv) * ld]; break;  // SEG_GRAPH
+__device__ __forceinline__ void tc_build_cols(const Args& a, TcCol* cols, int ncols, int tid, int nthreads) {
+  for (int c = tid; c < ncols; c += nthreads) {
+    TcCol t{nullptr, 0, -1};
+    for (int si = 0; si < a.n_segs; ++si) {
+      const Seg sg = a.segs[si];
+      const int f = c - sg.row;
+      if (f >= 0 && f < sg.width) {
+        t.base = a.arr[sg.arr] + sg.col + f;
+        t.ld = a.ld[sg.arr];
+        t.kind = sg.kind;
+      }
     }
-    break;
+    cols[c] = t;
   }
+}
+
+__device__ __forceinline__ float tc_gather_col(const TcCol t, int s, int d, int p, int pg) {
+  if (t.kind < 0) return 0.f;
+  const int i0 = (t.kind == SEG_SRC || t.kind == SEG_SMD) ? s : (t.kind == SEG_EDGE ? p : (t.kind == SEG_GRAPH ? pg : d));
+  float v = t.base[(size_t)i0 * t.ld];
+  if (t.kind == SEG_SMD) v -= t.base[(size_t)d * t.ld];
+  if (t.kind == SEG_DMS) v -= t.base[(size_t)s * t.ld];
   return v;
+}
+
+// tanh(x) = 1 - 2 / (2^(2x log2 e) + 1) on the SFU exponential and reciprocal: 5 instructions, absolute error <= 1.5e-7
+// over the whole range (saturates correctly to +-1), i.e. at the level of one float32 rounding of an O(1) activation.
+__device__ __forceinline__ float tc_tanh(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
+}
+
+// activation of a 16-value chunk with the dispatch hoisted out of the element loop (accurate float32 variants)
+__device__ __forceinline__ void tc_act16(int act, float (&f)[16]) {
+  switch (act) {
+    case NGPDE_ACT_IDENTITY: break;
+    case NGPDE_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      break;
+    case NGPDE_ACT_TANH:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = tc_tanh(f[j]);
+      break;
+    case NGPDE_ACT_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __fdividef(1.f, 1.f + expf(-f[j]));
+      break;
+    case NGPDE_ACT_SWISH:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __fdividef(f[j], 1.f + expf(-f[j]));
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = act_fwd(act, f[j]);
+      break;
+  }
+}
+
+__device__ __forceinline__ void tc_split16(const float (&f)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float h = umma::tf32_hi(f[j]);
+    hi[j] = __float_as_uint(h);
+    lo[j] = __float_as_uint(umma::tf32_hi(f[j] - h));
+  }
+}
+
+// the "ones" block (1, 0, ..., 0) that meets the bias row of the next weight image
+__device__ __forceinline__ void tc_store_ones(uint32_t tAhi, uint32_t tAlo, uint32_t col) {
+  const uint32_t one[8] = {0x3f800000u, 0, 0, 0, 0, 0, 0, 0}, zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  umma::tmem_st8(tAhi + col, one);
+  umma::tmem_st8(tAlo + col, zero);
 }
 
 // issue the 3xTF32 MMAs of one Dense layer: D[128 x Np] = A[128 x Kp] (TMEM hi/lo) x W (smem hi/lo images, MN-major)
@@ -126,17 +200,21 @@ __device__ __forceinline__ void tc_issue_layer(const TcLayout& lay, int l, uint3
 }
 
 template <bool NODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const TcFwdArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_constant__ TcFwdArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t bars[TC_GROUPS];
   __shared__ __align__(8) uint64_t wbar;
   __shared__ uint32_t tmem_slot;
   const TcLayout& lay = a.lay;
-  const int tid = threadIdx.x, grp = tid >> 7, gt = tid & 127;
+  const int tid = threadIdx.x, grp = tid / TC_GTHREADS, gt = tid % TC_GTHREADS;
+  const int row = gt & 127;  // tile row this thread serves: lane quarter (gt>>5)&3, lane gt&31
+  const int half = gt >> 7;  // which 16-column chunks of a layer's output it handles (chunk & 1 == half)
   float* wblk = reinterpret_cast<float*>(smem);
+  TcCol* cols = reinterpret_cast<TcCol*>(smem + a.off_cols);
   float* M = reinterpret_cast<float*>(smem + a.off_groups + grp * a.group_bytes);  // [128][dout + 1]
-  const int ldm = a.dout + 1;
+  const int dout = a.dout, ldm = dout + 1, aggr = a.aggr;
+  float* __restrict__ out = a.out;
 
   if (tid < 32) umma::tmem_alloc(&tmem_slot, lay.tmem_cols);
   if (tid == 0) {
@@ -144,6 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const TcFwdArg
     for (int g = 0; g < TC_GROUPS; ++g) umma::mbar_init(&bars[g], 1);
     umma::fence_mbar_init();
   }
+  tc_build_cols(a, cols, lay.Kd[0], tid, TC_THREADS);
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
@@ -156,12 +235,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const TcFwdArg
   umma::mbar_wait(&wbar, 0);
 
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_addr = (uint32_t)((gt >> 5) * 32) << 16;
+  const uint32_t lane_addr = (uint32_t)(((gt >> 5) & 3) * 32) << 16;
   const uint32_t tD = tmem + grp * lay.cols_group, tAhi = tD + TC_MAXN, tAlo = tAhi + lay.kmax;
   const uint32_t wblk_smem = umma::smem_u32(wblk);
-  const float* bias_all = wblk + lay.bias_off;
   uint32_t phase = 0;
-  const int L = lay.L;
+  const int L = lay.L, Kd0 = lay.Kd[0], gdiv = a.tg.gdiv;
+  const float ident = aggr == NGPDE_AGGR_MAX ? -INFINITY : (aggr == NGPDE_AGGR_MIN ? INFINITY : 0.f);
 
   for (int unit = blockIdx.x * TC_GROUPS + grp; unit < a.tg.n_units; unit += gridDim.x * TC_GROUPS) {
     int n0, n1, kbeg, kend;
@@ -175,31 +254,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const TcFwdArg
       n1 = a.tg.unit_ptr[unit + 1];
       kbeg = a.tg.rowptr[n0];
       kend = a.tg.rowptr[n1];
-      const float ident = a.aggr == NGPDE_AGGR_MAX ? -INFINITY : (a.aggr == NGPDE_AGGR_MIN ? INFINITY : 0.f);
-      for (int item = gt; item < (n1 - n0) * a.dout; item += TC_TILE) {
-        const int jj = item / a.dout;
-        if (a.tg.rowptr[n0 + jj] == a.tg.rowptr[n0 + jj + 1]) a.out[(size_t)n0 * a.dout + item] = ident;
+      for (int item = gt; item < (n1 - n0) * dout; item += TC_GTHREADS) {  // isolated destinations
+        const int jj = item / dout;
+        if (a.tg.rowptr[n0 + jj] == a.tg.rowptr[n0 + jj + 1]) out[(size_t)n0 * dout + item] = ident;
       }
     }
     for (int k0 = kbeg; k0 < kend; k0 += TC_TILE) {
       const int ne = min(TC_TILE, kend - k0);
-      const bool valid = gt < ne;
+      const bool valid = row < ne;
       int s = 0, d = 0, p = 0;
       if (valid) {
         if (NODE) {
-          s = d = p = k0 + gt;
+          s = d = p = k0 + row;
         } else {
-          s = a.tg.src[k0 + gt];
-          d = a.tg.dst[k0 + gt];
-          p = a.tg.perm[k0 + gt];
+          s = a.tg.src[k0 + row];
+          d = a.tg.dst[k0 + row];
+          p = a.tg.perm[k0 + row];
         }
       }
-      // ---- gather this row's MLP input straight into TMEM ----
-      for (int c0 = 0; c0 < lay.Kp[0]; c0 += 8) {
+      const int pg = p / gdiv;
+      // ---- gather this row's MLP input straight into TMEM (8-column chunks alternate between the two halves) ----
+      for (int c0 = 8 * half; c0 < Kd0; c0 += 16) {
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float v = (valid && c0 + j < lay.K[0]) ? tc_gather_value(a, c0 + j, s, d, p) : 0.f;
+          const float v = valid ? tc_gather_col(cols[c0 + j], s, d, p, pg) : 0.f;
           const float h = umma::tf32_hi(v);
           hi[j] = __float_as_uint(h);
           lo[j] = __float_as_uint(umma::tf32_hi(v - h));
@@ -207,61 +286,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const TcFwdArg
         umma::tmem_st8(tAhi + lane_addr + c0, hi);
         umma::tmem_st8(tAlo + lane_addr + c0, lo);
       }
+      if (half == 0) tc_store_ones(tAhi + lane_addr, tAlo + lane_addr, Kd0);
       umma::tmem_wait_st();
       umma::tc_fence_before();
       group_bar(grp);
 
       for (int l = 0; l < L; ++l) {
         if (gt < 32) {
-          // one elected lane issues; its warp-mates park on __syncwarp instead of spinning in try_wait next to it
+          // one elected lane issues the MMAs and waits for their completion; everybody else parks on barriers
+          // (a spinning try_wait loop in 255 threads would steal issue slots from the other group's epilogue)
           if (gt == 0) {
             umma::tc_fence_after();
             tc_issue_layer(lay, l, wblk_smem, tD, tAhi, tAlo);
             umma::mma_commit(&bars[grp]);
+            umma::mbar_wait(&bars[grp], phase);
           }
           __syncwarp();
         }
-        umma::mbar_wait(&bars[grp], phase);
         phase ^= 1;
+        group_bar(grp);
         umma::tc_fence_after();
-        const float* bias = bias_all + l * TC_MAXN;
-        const int act = a.act[l];
+        const int act = a.act[l], Np = lay.Np[l];
         const bool last = l == L - 1;
-        for (int c0 = 0; c0 < lay.Np[l]; c0 += 16) {
+        for (int c0 = 16 * half; c0 < Np; c0 += 32) {
           uint32_t v[16];
           umma::tmem_ld16(tD + lane_addr + c0, v);
           umma::tmem_wait_ld();
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bias[c0 + j];
-          if (act != NGPDE_ACT_IDENTITY) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = act_fwd(act, f[j]);
-          }
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          tc_act16(act, f);
           if (!last) {
             uint32_t lo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float h = umma::tf32_hi(f[j]);
-              v[j] = __float_as_uint(h);
-              lo[j] = __float_as_uint(umma::tf32_hi(f[j] - h));
-            }
+            tc_split16(f, v, lo);
             umma::tmem_st16(tAhi + lane_addr + c0, v);
             umma::tmem_st16(tAlo + lane_addr + c0, lo);
           } else if (NODE) {
             if (valid) {
-              float* o = a.out + (size_t)(k0 + gt) * a.dout + c0;
+              float* o = out + (size_t)(k0 + row) * dout + c0;
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (c0 + j < a.dout) o[j] = f[j];
+                if (c0 + j < dout) o[j] = f[j];
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (c0 + j < a.dout) M[gt * ldm + c0 + j] = f[j];
+              if (c0 + j < dout) M[row * ldm + c0 + j] = f[j];
           }
         }
         if (!last) {
+          if (half == 0) tc_store_ones(tAhi + lane_addr, tAlo + lane_addr, Np);  // Np[l] == Kd[l+1]
           umma::tmem_wait_st();
           umma::tc_fence_before();
           group_bar(grp);
@@ -270,26 +344,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const TcFwdArg
       if (!NODE) {
         // ---- ordered per-destination reduction of the tile's messages (ascending stored edge position) ----
         group_bar(grp);
-        const int dm = a.dout;
-        const int total = (n1 - n0) * dm;
-        for (int item = gt; item < total; item += TC_TILE) {
-          const int jj = item / dm, c = item - jj * dm;
+        const int total = (n1 - n0) * dout;
+        for (int item = gt; item < total; item += TC_GTHREADS) {
+          const int jj = item / dout, c = item - jj * dout;
           const int j = n0 + jj;
           const int r0 = a.tg.rowptr[j], r1 = a.tg.rowptr[j + 1];
           const int lo = max(r0, k0), hi = min(r1, k0 + ne);
           if (lo >= hi) continue;
-          float acc = (lo == r0) ? (a.aggr == NGPDE_AGGR_MAX ? -INFINITY : (a.aggr == NGPDE_AGGR_MIN ? INFINITY : 0.f))
-                                 : a.out[(size_t)j * dm + c];
-          const float* m = M + c - (size_t)k0 * ldm;
-          if (a.aggr == NGPDE_AGGR_MAX) {
-            for (int e = lo; e < hi; ++e) acc = fmaxf(acc, m[(size_t)e * ldm]);
-          } else if (a.aggr == NGPDE_AGGR_MIN) {
-            for (int e = lo; e < hi; ++e) acc = fminf(acc, m[(size_t)e * ldm]);
+          float acc = (lo == r0) ? ident : out[(size_t)j * dout + c];
+          const float* m = M + c + (lo - k0) * ldm;
+          const int cnt = hi - lo;
+          if (aggr == NGPDE_AGGR_MAX) {
+            for (int e = 0; e < cnt; ++e) acc = fmaxf(acc, m[e * ldm]);
+          } else if (aggr == NGPDE_AGGR_MIN) {
+            for (int e = 0; e < cnt; ++e) acc = fminf(acc, m[e * ldm]);
           } else {
-            for (int e = lo; e < hi; ++e) acc = __fadd_rn(acc, m[(size_t)e * ldm]);
-            if (a.aggr == NGPDE_AGGR_MEAN && hi == r1) acc = __fdiv_rn(acc, (float)(r1 - r0));
+            for (int e = 0; e < cnt; ++e) acc = __fadd_rn(acc, m[e * ldm]);
+            if (aggr == NGPDE_AGGR_MEAN && hi == r1) acc = __fdiv_rn(acc, (float)(r1 - r0));
           }
-          a.out[(size_t)j * dm + c] = acc;
+          out[(size_t)j * dout + c] = acc;
         }
         group_bar(grp);
       }
