@@ -2,6 +2,7 @@
 //   mode 0  D[128 x 64] = A(TMEM, lane = row, column = k) x W[K x 64]        B = MN-major SWIZZLE_128B image of W
 //   mode 1  D[128 x Kp] = G(TMEM)[128 x 64] x W^T                            B = the SAME image read K-major
 //   mode 2  D[128 x 64] = Aw^T x G,  Aw [nE x 128], G [nE x 64] in smem      both operands MN-major SWIZZLE_128B
+//   mode 3  dW[64 x 64] = Z^T x G,  Z [nE x 64], G [nE x 64] in smem         M = 64, full 3xTF32; prints the TMEM lane of each row
 // Each mode is checked against a double-precision CPU product; passes = 1 (plain TF32) or 3 (hi/lo split, ~fp32).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o umma_probe tools/umma_probe.cu && ./umma_probe <mode> [passes] [Kp]
 #include <cuda_runtime.h>
@@ -87,6 +88,26 @@ __global__ void __launch_bounds__(128) probe_kernel(Params p, const float* __res
       tmem_st8(lane_base + COL_ALO + c0, lo);
     }
     tmem_wait_st();
+  } else if (p.mode == 3) {
+    float* Alo = reinterpret_cast<float*>(smem + 160 * 1024);
+    for (int i = tid; i < p.nE * 64; i += 128) {
+      const int e = i / 64, m = i % 64;
+      const float a = A[e * 64 + m], g = B[e * 64 + m];
+      const float ah = tf32_hi(a), gh = tf32_hi(g);
+      const uint32_t off = img_offset(p.img, p.nE, 64, e, m);
+      Aw[off] = ah;
+      Alo[off] = tf32_hi(a - ah);
+      Bhi[off] = gh;
+      Blo[off] = tf32_hi(g - gh);
+    }
+    // sentinel in the accumulator columns so that untouched lanes are recognisable
+    for (int c0 = 0; c0 < 64; c0 += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(-777.f);
+      tmem_st8(lane_base + COL_D + c0, v);
+    }
+    tmem_wait_st();
   } else {
     // mode 2: Aw [nE][128] -> 4 groups, G [nE][64] -> 2 groups (hi only unless passes == 3)
     for (int i = tid; i < p.nE * 128; i += 128) {
@@ -130,6 +151,20 @@ __global__ void __launch_bounds__(128) probe_kernel(Params p, const float* __res
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t bdesc = desc_rows_are_n(p.img, bb, p.Kp, 64, ks);
           mma_tf32_ts(tmem + COL_D, tmem + acol + ks * 8, bdesc, idesc, !first);
+          first = 0;
+        }
+      }
+    } else if (p.mode == 3) {
+      const uint32_t idesc = make_idesc(64, 64, 1, 1);
+      const uint32_t ahi = smem_u32(Aw), alo = ahi + 32 * 1024;
+      int first = 1;
+      for (int pass = 0; pass < p.passes; ++pass) {
+        const uint32_t aa = (pass == 1) ? alo : ahi;
+        const uint32_t bb = (pass == 2) ? blo : bhi;
+        for (int ks = 0; ks < p.nE / 8; ++ks) {
+          const uint64_t adesc = desc_rows_are_k(p.img, aa, p.nE, 64, ks);
+          const uint64_t bdesc = desc_rows_are_k(p.img, bb, p.nE, 64, ks);
+          mma_tf32_ss(tmem + COL_D, adesc, bdesc, idesc, !first);
           first = 0;
         }
       }
@@ -185,6 +220,7 @@ int main(int argc, char** argv) {
   int ar, ac, br, bc, dr = 128, dc;
   if (p.mode == 0) { ar = 128; ac = p.K; br = p.K; bc = 64; dc = 64; }
   else if (p.mode == 1) { ar = 128; ac = 64; br = p.K; bc = 64; dc = p.Kp; }
+  else if (p.mode == 3) { ar = p.nE; ac = 64; br = p.nE; bc = 64; dc = 64; }
   else { ar = p.nE; ac = 128; br = p.nE; bc = 64; dc = 64; }
   std::vector<float> A(ar * ac), B(br * bc), D(dr * dc, -777.f);
   for (auto& v : A) v = rnd();
@@ -200,6 +236,38 @@ int main(int argc, char** argv) {
   cudaError_t err = cudaDeviceSynchronize();
   if (err != cudaSuccess) { printf("mode %d: CUDA error %s\n", p.mode, cudaGetErrorString(err)); return 1; }
   cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  if (p.mode == 3) {
+    // find, for every row k of dW = Z^T G, the TMEM lane that holds it
+    double maxref = 0, maxerr = 0;
+    int lane_of[64], bad = 0;
+    for (int k = 0; k < 64; ++k) {
+      double best = 1e30; int bl = -1;
+      std::vector<double> ref(64, 0.0);
+      for (int n = 0; n < 64; ++n) {
+        for (int e = 0; e < p.nE; ++e) {
+          const double a = p.passes == 1 ? tf32_trunc_host(A[e * 64 + k]) : A[e * 64 + k];
+          const double g = p.passes == 1 ? tf32_trunc_host(B[e * 64 + n]) : B[e * 64 + n];
+          ref[n] += a * g;
+        }
+        maxref = fmax(maxref, fabs(ref[n]));
+      }
+      for (int l = 0; l < 128; ++l) {
+        double err = 0;
+        for (int n = 0; n < 64; ++n) err = fmax(err, fabs(ref[n] - D[l * 64 + n]));
+        if (err < best) { best = err; bl = l; }
+      }
+      lane_of[k] = bl;
+      maxerr = fmax(maxerr, best);
+    }
+    int touched = 0;
+    for (int l = 0; l < 128; ++l) touched += D[l * 64] != -777.f;
+    printf("mode 3 img %d passes %d nE %d: max|err| %.3e max|ref| %.3e rel %.3e touched lanes %d; lane of row k:", p.img, p.passes,
+           p.nE, maxerr, maxref, maxerr / maxref, touched);
+    for (int k = 0; k < 64; ++k) printf(" %d", lane_of[k]);
+    printf("\n");
+    (void)bad;
+    return 0;
+  }
   double maxref = 0, maxerr = 0;
   for (int m = 0; m < dr; ++m)
     for (int n = 0; n < dc; ++n) {
