@@ -178,6 +178,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--partition", action="store_true",
+                    help="N>1: split ONE graph over the ranks by nodes with a per-step halo exchange (strong scaling) "
+                         "instead of one graph per rank (weak scaling)")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "put"], help="halo transfer: NCCL all-to-all or peer stores")
+    ap.add_argument("--nodes", type=int, default=0, help="override the node count of c4 (default 1,000,000)")
     ap.add_argument("--cuda-graph", action="store_true", help="replay fwd+bwd from a captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (reported under config)")
@@ -204,21 +209,31 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    w = workloads.WORKLOADS[args.workload](dev)
+    wkw = {"n_nodes": args.nodes} if (args.workload == "c4" and args.nodes) else {}
+    w = workloads.WORKLOADS[args.workload](dev, **wkw)
     K, W = args.steps, args.warmup
     gen = torch.Generator().manual_seed(1234)
-    runner = engine.RhsRunner(w.layer, w.x, w.ps, w.st)
-    runner.dy.copy_(torch.randn(tuple(runner.dy.shape), generator=gen).to(dev))
-    if args.cuda_graph:
-        runner.capture()
+    partitioned = args.partition and world > 1
     flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    grads = [t for t in (runner.dphi, runner.dnode) if t is not None]
+    if partitioned:
+        from ngpde import distributed as D
+        pl = D.PartitionedLayer(w.layer, w.graph, rank, world, dev, mode=args.halo)
+        prunner = engine.PartitionedRhsRunner(pl, pl.owned(w.x), w.ps, w.st)
+        runner = prunner.runner
+        prunner.dy_owned.copy_(torch.randn(tuple(prunner.dy_owned.shape), generator=gen).to(dev))
+        one_step = prunner.step
+    else:
+        runner = engine.RhsRunner(w.layer, w.x, w.ps, w.st)
+        runner.dy.copy_(torch.randn(tuple(runner.dy.shape), generator=gen).to(dev))
+        if args.cuda_graph:
+            runner.capture()
+        grads = [t for t in (runner.dphi, runner.dnode) if t is not None]
 
-    def one_step():
-        runner.step()
-        if world > 1:
-            for t in grads:  # data-parallel: sum the flat parameter gradients over ranks (NCCL over NVLink)
-                dist.all_reduce(t)
+        def one_step():
+            runner.step()
+            if world > 1:
+                for t in grads:  # data-parallel: sum the flat parameter gradients over ranks (NCCL over NVLink)
+                    dist.all_reduce(t)
 
     def sync_all():
         if world > 1:
@@ -255,7 +270,7 @@ def main():
     launches = ops.LAUNCHES["count"] - l0
     clocks = sampler.stop()
 
-    edges_total = w.n_edges * K * world
+    edges_total = w.n_edges * K * (1 if partitioned else world)
     value = edges_total / (total_ms * 1e-3)
 
     # ---- dominant kernel, timed by the library's own CUDA events on the launching stream ----
@@ -289,6 +304,24 @@ def main():
                 "achieved_gbs": w.bytes_fwdbwd / (total_ms / K * 1e-3) / 1e9,
                 "frac_of_measured": w.bytes_fwdbwd / (total_ms / K * 1e-3) / 1e9 / peaks["hbm_gbs"]},
     }
+
+    if partitioned:
+        p = pl.part
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_label(args.workload), "nodes_total": w.n_nodes, "edges_total": w.n_edges,
+                       "nodes_owned_rank0": p.n_owned, "halo_rows_rank0": p.n_halo, "edges_rank0": int(p.edge_ids.size),
+                       "step": "one RHS evaluation: halo exchange + layer forward + VJP + reverse halo + dW all-reduce",
+                       "parallelism": f"node-partitioned over {world} GPUs, halo via {args.halo}",
+                       "l2": "warm (--no-flush)" if flush is None else "flushed between steps (256 MiB memset, untimed)"},
+            "rhs_evals_per_sec": K / (total_ms * 1e-3), "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        }
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        dist.destroy_process_group()
+        return
 
     # ---- end to end through the public layer API with host buffers ----
     ca = ngpde.ComponentArray(w.ps)

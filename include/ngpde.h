@@ -203,6 +203,23 @@ int ngpde_gcn_conv_backward(ngpde_graph_t g, const ngpde_gcn_desc* desc, const f
 int ngpde_axpy_stages(float* out, const float* u, const float* const* k, const float* coef, int32_t nk, int64_t n,
                       void* stream);
 
+/* ---- multi-GPU: halo exchange of a node-partitioned graph.  The reference is single-device
+ * (no collective call site exists under /root/reference); a partitioned `propagate` (call sites layers.jl:111,326,416,534)
+ * needs, per layer call, the boundary rows of x packed for every peer and -- in the pullback -- the returned halo
+ * cotangents added into the owner's rows.  The transfer itself is NCCL (all-to-all over NVLink) in the host layer, or
+ * direct peer stores (ngpde_rows_put) when the destination buffers are peer-mapped.
+ *   rows_gather       out[i][:] = x[rows[i]][:]                                  i < n_rows
+ *   rows_put          row i goes to peer p = the slot with peer_ptr[p] <= i < peer_ptr[p+1], at
+ *                     peer_dst[p][(i - peer_ptr[p])][:]  (peer_ptr, peer_dst: DEVICE arrays; peer_dst[p] may point into
+ *                     another GPU's memory)
+ *   rows_segment_add  dst[seg_rows[u]][:] += sum over q in [seg_ptr[u], seg_ptr[u+1]) of src[seg_pos[q]][:], q ascending:
+ *                     deterministic, atomic-free; seg_rows must be distinct. ---- */
+int ngpde_rows_gather(const float* x, const int32_t* rows, int64_t n_rows, int32_t d, float* out, void* stream);
+int ngpde_rows_put(const float* x, const int32_t* rows, const int64_t* peer_ptr, float* const* peer_dst, int32_t n_peers,
+                   int64_t n_rows, int32_t d, void* stream);
+int ngpde_rows_segment_add(float* dst, const float* src, const int32_t* seg_rows, const int32_t* seg_ptr,
+                           const int32_t* seg_pos, int64_t n_segs, int32_t d, void* stream);
+
 /* ---- optional kernel timing: while enabled, the four fused kernels of the conv layers (edge/node phase, forward/
  * backward) are bracketed by CUDA events on the launching stream.  ngpde_profile_read synchronises those events, returns
  * the summed milliseconds and launch counts per slot (arrays of NGPDE_PROF_SLOTS) and clears the record.  Not

@@ -28,7 +28,8 @@ EXPORTS = [
     "ngpde_explicit_edge_conv_backward", "ngpde_vmh_conv_forward", "ngpde_vmh_conv_backward",
     "ngpde_mppde_conv_forward", "ngpde_mppde_conv_backward", "ngpde_gno_conv_forward", "ngpde_gno_conv_backward",
     "ngpde_gcn_workspace_bytes", "ngpde_gcn_conv_forward", "ngpde_gcn_conv_backward", "ngpde_axpy_stages",
-    "ngpde_profile_enable", "ngpde_profile_read", "ngpde_set_option",
+    "ngpde_profile_enable", "ngpde_profile_read", "ngpde_set_option", "ngpde_rows_gather", "ngpde_rows_put",
+    "ngpde_rows_segment_add",
 ]
 
 
@@ -93,6 +94,9 @@ def load() -> C.CDLL:
     lib.ngpde_gcn_conv_forward.argtypes = [vp, C.POINTER(GcnDesc), vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.ngpde_gcn_conv_backward.argtypes = [vp, C.POINTER(GcnDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.ngpde_axpy_stages.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_float), i32, i64, vp]
+    lib.ngpde_rows_gather.argtypes = [vp, vp, i64, i32, vp, vp]
+    lib.ngpde_rows_put.argtypes = [vp, vp, vp, vp, i32, i64, i32, vp]
+    lib.ngpde_rows_segment_add.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
     lib.ngpde_set_option.argtypes = [i32, i32]
     lib.ngpde_profile_enable.argtypes = [i32]
     lib.ngpde_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]

@@ -94,3 +94,35 @@ class RhsRunner:
         else:
             self.forward()
             self.backward()
+
+
+class PartitionedRhsRunner:
+    """RhsRunner over this rank's share of a node-partitioned graph (distributed.PartitionedLayer): every step exchanges
+    the boundary rows of x, runs the local forward + VJP, sends the halo cotangents home and all-reduces the flat
+    parameter gradients -- the per-RHS sequence of SURVEY.md section 8e."""
+
+    def __init__(self, pl, x_owned: Tensor, ps, st):
+        from .distributed import allreduce_gradients
+        from .graph import from_rowmajor, rowmajor
+        self.pl, self._allreduce = pl, allreduce_gradients
+        p = pl.part
+        self.n_owned = p.n_owned
+        self.x_owned = rowmajor(x_owned).detach().clone()
+        x_local = pl.exchange.forward(self.x_owned)
+        self.runner = RhsRunner(pl.layer, from_rowmajor(x_local), ps, pl.local_state(st))
+        self.dy_owned = torch.zeros((p.n_owned, self.runner.dy.shape[1]), dtype=torch.float32, device=self.x_owned.device)
+        self.dx_owned: Optional[Tensor] = None
+
+    @property
+    def y_owned(self) -> Tensor:
+        return self.runner.y[:self.n_owned]
+
+    def step(self):
+        r = self.runner
+        r.x.copy_(self.pl.exchange.forward(self.x_owned))
+        r.forward()
+        r.dy[self.n_owned:].zero_()
+        r.dy[:self.n_owned].copy_(self.dy_owned)
+        r.backward()
+        self.dx_owned = self.pl.exchange.backward(r.dx)
+        self._allreduce([r.dphi, r.dnode], self.pl.exchange.group)
