@@ -7,6 +7,7 @@
 
 #include "ngpde_conv_kernels.cuh"
 #include "ngpde_tc.cuh"
+#include "ngpde_tc_bwd.cuh"
 
 namespace ngpde {
 namespace {
@@ -41,10 +42,9 @@ bool g_use_tc = true;
 
 int pad16(int x) { return (x + 15) / 16 * 16; }
 
-// Lays out the prepared weight block of `m` and decides whether the tcgen05 kernels can run it.
-bool tc_make_layout(const MlpDev& m, bool contract, bool addend, int dout, bool node, TcLayout* lay, int* smem_bytes,
-                    int* off_cols, int* off_groups, int* group_bytes) {
-  if (!g_use_tc || contract || addend || m.L < 1 || m.L > NGPDE_MAX_LAYERS) return false;
+// Shapes and prepared-weight-block offsets of `m` on the tensor-core path; false when a layer is too wide for it.
+bool tc_fill_layout(const MlpDev& m, TcLayout* lay) {
+  if (m.L < 1 || m.L > NGPDE_MAX_LAYERS) return false;
   *lay = TcLayout{};
   lay->L = m.L;
   int off = 0, kmax = 0;
@@ -64,6 +64,80 @@ bool tc_make_layout(const MlpDev& m, bool contract, bool addend, int dout, bool 
   lay->block_floats = off;
   lay->kmax = kmax;
   lay->cols_group = TC_MAXN + 2 * kmax;
+  return true;
+}
+
+// Backward on tensor cores: TMEM column map, shared-memory map and eligibility (see ngpde_tc_bwd.cuh).
+struct TcBwdPhase {
+  bool on = false;
+  TcLayout lay{};
+  int smem = 0;
+  int c_zs[NGPDE_MAX_LAYERS] = {0};
+  int c_a = 0, a_width = 0, c_d = 0, c_dw = 0, c_d0 = 0, c_dw0 = 0, tmem_cols = 0;
+  int off_cols = 0, off_stage = 0, off_dz = 0, nzh = 0, nzl = 0;
+  size_t ws_off = 0;
+  int grid = 0;
+};
+
+bool tc_bwd_make(const MlpDev& m, bool contract, bool addend, bool node, int aggr, bool need_dz0, TcBwdPhase* t) {
+  *t = TcBwdPhase{};
+  if (!g_use_tc || contract || addend || m.L > TCB_MAXL) return false;
+  if (!node && !(aggr == NGPDE_AGGR_SUM || aggr == NGPDE_AGGR_MEAN)) return false;
+  if (!tc_fill_layout(m, &t->lay)) return false;
+  const TcLayout& lay = t->lay;
+  const int L = lay.L;
+  if (m.act[L - 1] != NGPDE_ACT_IDENTITY) return false;  // Z_L is not recomputed
+  for (int l = 0; l < L; ++l) {
+    if (!act_grad_from_y(m.act[l])) return false;         // swish / gelu need the pre-activation
+    if (lay.Kp[l] > 88) return false;                     // register accumulators cover 64 + 24 columns of dW^T
+  }
+  // TMEM columns
+  int zs = 0, wdw = 0, kdmax = 0;
+  for (int l = 1; l < L; ++l) {
+    t->c_zs[l] = zs;
+    zs += lay.Kd[l];
+    wdw = std::max(wdw, lay.Kp[l]);
+  }
+  for (int l = 0; l < L; ++l) kdmax = std::max(kdmax, lay.Kd[l]);
+  // one A image holds a layer input (Kp columns, forward recompute) or a layer-output cotangent (Np columns, backward)
+  t->a_width = lay.kmax;
+  for (int l = 0; l < L; ++l) t->a_width = std::max(t->a_width, lay.Np[l]);
+  t->c_a = zs;
+  t->c_d = zs + 2 * t->a_width;
+  t->c_dw = t->c_d + 64;
+  if (zs >= lay.Kd[0] + lay.Kp[0]) {  // layer 0's outputs may overwrite the (dead by then) activation copies
+    t->c_d0 = 0;
+    t->c_dw0 = lay.Kd[0];
+  } else {
+    if (lay.Kd[0] > 64) return false;
+    t->c_d0 = t->c_d;
+    t->c_dw0 = t->c_dw;
+    wdw = std::max(wdw, lay.Kp[0]);
+  }
+  const int total = t->c_dw + wdw;
+  if (total > 512) return false;
+  int cols = 32;
+  while (cols < total) cols *= 2;
+  t->tmem_cols = cols;
+  // shared memory
+  t->nzh = (kdmax + 8 + 31) / 32;
+  t->nzl = (kdmax + 31) / 32;
+  t->off_cols = 4 * lay.block_floats;
+  t->off_stage = (t->off_cols + (int)(sizeof(TcCol) + sizeof(TcDst)) * lay.Kd[0] + 1023) & ~1023;
+  t->off_dz = t->off_stage + (t->nzh + t->nzl + 4) * TCB_HALF * 128;
+  const int dz_bytes = (!node && need_dz0) ? TC_TILE * (lay.Kd[0] + 1) * 4 : 0;
+  const int totalb = 1024 + t->off_dz + dz_bytes;
+  if (totalb > kSmemMaxTc) return false;
+  t->smem = std::max(totalb, 116 * 1024);  // one CTA per SM: its TMEM allocation must not wait for a neighbour's
+  t->on = true;
+  return true;
+}
+
+// Lays out the prepared weight block of `m` and decides whether the tcgen05 forward kernels can run it.
+bool tc_make_layout(const MlpDev& m, bool contract, bool addend, int dout, bool node, TcLayout* lay, int* smem_bytes,
+                    int* off_cols, int* off_groups, int* group_bytes) {
+  if (!g_use_tc || contract || addend || m.L < 1 || m.L > NGPDE_MAX_LAYERS) return false;
+  if (!tc_fill_layout(m, lay)) return false;
   const int need = TC_GROUPS * lay->cols_group;
   if (need > 512) return false;
   int cols = 32;
@@ -381,29 +455,44 @@ struct BwdLayout {
   int te_e, smem_e, grid_e;
   int te_n, smem_n, grid_n;
   BwdSmem se, sn;
+  TcBwdPhase tce, tcn;  // tensor-core variants of the two phases (when eligible)
   size_t off_wt_phi, off_wt_node, off_dmbar, off_dxdirect, off_dxdst, off_desrc, off_part_phi, off_part_node, total;
 };
 
 int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, BwdLayout* L) {
-  if (int rc = pick_tile(
-          [&](int te) {
-            return 4 * bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, te).floats;
-          },
-          &L->te_e, &L->smem_e))
-    return rc;
-  L->se = bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, L->te_e);
-  if (int rc = bwd_grid<false>(L->te_e, L->smem_e, std::max(1, g->n_units[tile_index(L->te_e)]), g->num_sms, &L->grid_e))
-    return rc;
-  L->te_n = 0; L->smem_n = 0; L->grid_n = 0;
-  if (p.has_node) {
-    if (int rc = pick_tile([&](int te) { return 4 * bwd_smem(p.node, 0, 0, 0, d.aggr, true, true, te).floats; },
-                           &L->te_n, &L->smem_n))
+  L->te_e = 0; L->smem_e = 0; L->grid_e = 0;
+  if (tc_bwd_make(p.phi, p.contract, false, false, d.aggr, p.edge_need_dz0, &L->tce)) {
+    L->tce.grid = std::max(1, std::min(g->n_units[2], g->num_sms));
+    L->grid_e = L->tce.grid;
+  } else {
+    if (int rc = pick_tile(
+            [&](int te) {
+              return 4 * bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, te).floats;
+            },
+            &L->te_e, &L->smem_e))
       return rc;
-    L->sn = bwd_smem(p.node, 0, 0, 0, d.aggr, true, true, L->te_n);
-    const int nu = (int)((g->N + L->te_n - 1) / L->te_n);
-    if (int rc = bwd_grid<true>(L->te_n, L->smem_n, std::max(1, nu), g->num_sms, &L->grid_n)) return rc;
+    L->se = bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, L->te_e);
+    if (int rc = bwd_grid<false>(L->te_e, L->smem_e, std::max(1, g->n_units[tile_index(L->te_e)]), g->num_sms, &L->grid_e))
+      return rc;
+  }
+  L->te_n = 0; L->smem_n = 0; L->grid_n = 0;
+  L->tcn = TcBwdPhase{};
+  if (p.has_node) {
+    if (tc_bwd_make(p.node, 0, p.node_addend, true, d.aggr, true, &L->tcn)) {
+      L->tcn.grid = std::max(1, std::min((int)((g->N + TC_TILE - 1) / TC_TILE), g->num_sms));
+      L->grid_n = L->tcn.grid;
+    } else {
+      if (int rc = pick_tile([&](int te) { return 4 * bwd_smem(p.node, 0, 0, 0, d.aggr, true, true, te).floats; },
+                             &L->te_n, &L->smem_n))
+        return rc;
+      L->sn = bwd_smem(p.node, 0, 0, 0, d.aggr, true, true, L->te_n);
+      const int nu = (int)((g->N + L->te_n - 1) / L->te_n);
+      if (int rc = bwd_grid<true>(L->te_n, L->smem_n, std::max(1, nu), g->num_sms, &L->grid_n)) return rc;
+    }
   }
   size_t off = 0;
+  if (L->tce.on) { L->tce.ws_off = off; off = align256(off + 4 * (size_t)L->tce.lay.block_floats); }
+  if (L->tcn.on) { L->tcn.ws_off = off; off = align256(off + 4 * (size_t)L->tcn.lay.block_floats); }
   L->off_wt_phi = off;    off = align256(off + sizeof(float) * p.phi.n_params);
   L->off_wt_node = off;   off = align256(off + sizeof(float) * p.node.n_params);
   L->off_dmbar = off;     off = align256(off + (p.has_node ? sizeof(float) * g->N * p.dm : 0));
@@ -574,6 +663,44 @@ int launch_fwd_tc(const ngpde_graph* g, const TcPhase& t, const MlpDev& mlp, con
   return NGPDE_OK;
 }
 
+template <bool NODE>
+int launch_bwd_tc(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base, float* wblock, cudaStream_t st) {
+  if (base.tg.n_units <= 0) return NGPDE_OK;
+  tc_prep_weights_kernel<<<32, 256, 0, st>>>(base.params, mlp, t.lay, wblock);
+  TcBwdArgs a{};
+  a.tg = base.tg;
+  std::memcpy(a.arr, base.arr, sizeof(a.arr));
+  std::memcpy(a.ld, base.ld, sizeof(a.ld));
+  a.n_segs = base.n_segs;
+  std::memcpy(a.segs, base.segs, sizeof(a.segs));
+  a.lay = t.lay;
+  for (int l = 0; l < mlp.L; ++l) {
+    a.act[l] = mlp.act[l];
+    a.w_off[l] = mlp.w_off[l];
+    a.b_off[l] = mlp.b_off[l];
+  }
+  a.n_params = mlp.n_params;
+  a.wblock = wblock;
+  a.aggr = base.aggr;
+  a.dout = base.dout;
+  a.gout_ptr = base.gout_ptr;
+  a.dparams_partial = base.dparams_partial;
+  a.dx_direct = base.dx_direct;
+  a.dmbar = base.dmbar;
+  a.dxdst = base.dxdst;
+  a.desrc = base.desrc;
+  a.dx = base.dx;
+  a.need_dz0 = base.need_dz0;
+  a.has_dst_side = base.has_dst_side;
+  std::memcpy(a.c_zs, t.c_zs, sizeof(a.c_zs));
+  a.c_a = t.c_a; a.a_width = t.a_width; a.c_d = t.c_d; a.c_dw = t.c_dw; a.c_d0 = t.c_d0; a.c_dw0 = t.c_dw0; a.tmem_cols = t.tmem_cols;
+  a.off_cols = t.off_cols; a.off_stage = t.off_stage; a.off_dz = t.off_dz; a.nzh = t.nzh; a.nzl = t.nzl;
+  NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_bwd_tc_kernel<NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
+  mp_bwd_tc_kernel<NODE><<<t.grid, TCB_THREADS, t.smem, st>>>(a);
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
 }  // namespace
 
 extern "C" int ngpde_set_option(int32_t option, int32_t value) {
@@ -710,7 +837,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   // ---- node phase: dy -> (dx_direct, dmbar, dnode_params) ----
   if (p.has_node) {
     BwdArgs n{};
-    const int te = L.te_n;
+    const int te = L.tcn.on ? TC_TILE : L.te_n;
     n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + te - 1) / te), (int)g->N,
                      (int)std::max<int64_t>(1, g->N / std::max<int64_t>(1, g->G))};
     fill_arrays(g, *desc, p, *io, n.arr, n.ld);
@@ -734,7 +861,12 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     n.offG0 = L.sn.offG0; n.offG1 = L.sn.offG1; n.offW = L.sn.offW;
     {
       ProfScope prof(NGPDE_PROF_BWD_NODE, st);
-      if (int rc = launch_bwd<true>(te, n, L.smem_n, L.grid_n, st)) return rc;
+      if (L.tcn.on) {
+        n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
+        if (int rc = launch_bwd_tc<true>(L.tcn, p.node, n, reinterpret_cast<float*>(ws + L.tcn.ws_off), st)) return rc;
+      } else {
+        if (int rc = launch_bwd<true>(te, n, L.smem_n, L.grid_n, st)) return rc;
+      }
     }
     const int P = p.node.n_params;
     reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_node, L.grid_n, P, io->dnode_params);
@@ -743,7 +875,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   // ---- edge phase: dmbar -> (dxdst, desrc, dphi_params) ----
   {
     BwdArgs a{};
-    const int te = L.te_e;
+    const int te = L.tce.on ? TC_TILE : L.te_e;
     const int ti = tile_index(te);
     a.tg = TileGraph{g->rowptr, g->src, g->dst, g->perm, g->units[ti], g->n_units[ti], (int)g->N,
                      (int)std::max<int64_t>(1, g->E / std::max<int64_t>(1, g->G))};
@@ -772,7 +904,13 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     a.offDM = L.se.offDM; a.offP = L.se.offP; a.offDH = L.se.offDH; a.offRed = L.se.offRed;
     if (g->E > 0) {
       ProfScope prof(NGPDE_PROF_BWD_EDGE, st);
-      if (int rc = launch_bwd<false>(te, a, L.smem_e, L.grid_e, st)) return rc;
+      if (L.tce.on) {
+        a.tg.unit_ptr = g->units[2];
+        a.tg.n_units = g->n_units[2];
+        if (int rc = launch_bwd_tc<false>(L.tce, p.phi, a, reinterpret_cast<float*>(ws + L.tce.ws_off), st)) return rc;
+      } else {
+        if (int rc = launch_bwd<false>(te, a, L.smem_e, L.grid_e, st)) return rc;
+      }
     } else if (dxdst) {
       NGPDE_CUDA_TRY(cudaMemsetAsync(dxdst, 0, sizeof(float) * g->N * desc->dx, st));
     }

@@ -3,7 +3,7 @@
 // One thread owns one edge (edge phase) or one node (node phase): a group of 128 threads owns a tile of 128 rows, which
 // is the M dimension of every MMA.  Activations never leave the SM and never touch shared memory:
 //     gather -> registers -> TMEM (A operand, lane = row, column = feature, split hi/lo for 3xTF32)
-//     tcgen05.mma  D[128 x N](TMEM) = A(TMEM) x W(smem image)           3 passes: hi*hi + lo*hi + hi*lo, FP32 accumulate
+//     tcgen05.mma  D[128 x N](TMEM) = A(TMEM) x W(smem image)           3 passes: lo*hi + hi*lo + hi*hi, FP32 accumulate
 //     tcgen05.ld D -> registers: + bias, activation (accurate tanhf/expf), split -> tcgen05.st -> next layer's A
 // The last layer's rows go through a padded shared-memory tile only to be reduced per destination node in stored edge
 // order (same atomic-free sequential reduction as the FFMA engine), or straight to global memory in the node phase.
@@ -189,14 +189,15 @@ __device__ __forceinline__ void tc_issue_layer(const TcLayout& lay, int l, uint3
   const uint32_t lbo = 128u * lay.Kp[l];
   const uint64_t dhi = umma::make_sdesc(hi, lbo, 512, 1), dlo = umma::make_sdesc(lo, lbo, 512, 1);
   const int nks = lay.Kp[l] / 8;
-  // one K-step = 8 rows of the image = 1024 bytes = 64 units of the descriptor's 16-byte address field
-  umma::mma_tf32_ts(tD, tAhi, dhi, idesc, 0);
+  // one K-step = 8 rows of the image = 1024 bytes = 64 units of the descriptor's 16-byte address field.
+  // Cross terms first, hi*hi last (see ngpde_umma.cuh).
+  umma::mma_tf32_ts(tD, tAlo, dhi, idesc, 0);
 #pragma unroll 4
-  for (int ks = 1; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAhi + ks * 8, dhi + (uint64_t)(ks * 64), idesc, 1);
-#pragma unroll 4
-  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAlo + ks * 8, dhi + (uint64_t)(ks * 64), idesc, 1);
+  for (int ks = 1; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAlo + ks * 8, dhi + (uint64_t)(ks * 64), idesc, 1);
 #pragma unroll 4
   for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAhi + ks * 8, dlo + (uint64_t)(ks * 64), idesc, 1);
+#pragma unroll 4
+  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAhi + ks * 8, dhi + (uint64_t)(ks * 64), idesc, 1);
 }
 
 template <bool NODE>

@@ -1,0 +1,511 @@
+// Tensor-core (tcgen05 + TMEM) backward of the fused message-passing kernels for MLPs whose layers are at most 64 wide
+// (the twin of ngpde_tc.cuh).  One CTA of 512 threads owns one tile of 128 rows (edges or nodes); thread (row, q) serves
+// the 16-column chunk q of its row, so a layer's 64 columns are handled by four warps at once.
+//
+// Per tile, with everything on chip:
+//   1. recompute the forward activations Z_1 .. Z_{L-1} (3xTF32 MMAs as in the forward); they stay in TMEM as FP32;
+//   2. G_L = cotangent of the tile's MLP output (gathered from dmbar[dst] / deg for the edge phase, dy[row] for nodes);
+//   3. for l = L-1 .. 0:
+//        input gradient   dZ_l = G_{l+1} W_l^T     M = 128 rows, A = G (TMEM, hi/lo), B = the FORWARD weight image read
+//                                                  K-major (same shared-memory bytes serve both directions);
+//        weight gradient  dW_l^T = G_{l+1}^T Z_l   M = 64 (output features), K = 64 rows per half tile, both operands
+//                                                  staged in shared memory as MN-major SWIZZLE_128B_BASE32B images; a
+//                                                  "ones" column appended to Z_l makes the same MMA produce db_l;
+//        G_l = dZ_l .* act'(Z_l)                   in registers, from TMEM.
+//      Each tile's dW^T block is read out of TMEM and added to per-thread FP32 register accumulators (so the running sum
+//      is rounded once per tile in FP32, not inside the tensor core), written as this CTA's partial at kernel end and
+//      reduced over CTAs in fixed order by reduce_partials_kernel: deterministic, no atomics.
+//   4. dZ_0 goes back to the arrays it was gathered from: node phase -> dx_direct / dmbar rows; edge phase -> per-edge
+//      source-side rows (desrc, reduced later over the transpose) and the sequential per-destination sum (dxdst).
+// 3xTF32 ordering: the two small cross terms are issued before hi*hi so that the accumulator is still small while they
+// are added (the tensor core truncates its FP32 accumulator; pinned by tools/umma_probe.cu, profiles/r01b_umma_probe.log).
+#pragma once
+#include "ngpde_tc.cuh"
+
+namespace ngpde {
+
+constexpr int TCB_THREADS = 512;
+constexpr int TCB_MAXL = 4;     // register accumulators for at most 4 layers
+constexpr int TCB_HALF = 64;    // rows per weight-gradient staging pass
+
+struct TcBwdArgs {
+  TileGraph tg;
+  const float* arr[ARR_COUNT];
+  int ld[ARR_COUNT];
+  int n_segs;
+  Seg segs[8];
+  TcLayout lay;
+  int act[NGPDE_MAX_LAYERS];
+  int w_off[NGPDE_MAX_LAYERS], b_off[NGPDE_MAX_LAYERS];
+  int n_params;
+  const float* wblock;
+  int aggr;
+  int dout;                // width of the MLP output (= N[L-1])
+  const float* gout_ptr;   // edge: dmbar / dy [N][dout]; node: dy [N][dout]
+  float* dparams_partial;  // [gridDim.x][n_params]
+  float* dx_direct;        // node phase
+  float* dmbar;            // node phase
+  float* dxdst;            // edge phase [N][dx]
+  float* desrc;            // edge phase [E][dx]
+  int dx;
+  int need_dz0, has_dst_side;
+  // TMEM columns
+  int c_zs[NGPDE_MAX_LAYERS];  // FP32 copy of Z_l (l >= 1)
+  int c_a, a_width, c_d, c_dw, c_d0, c_dw0, tmem_cols;  // a_width: columns of one A image (hi or lo)
+  // shared memory byte offsets
+  int off_cols, off_stage, off_dz;
+  int nzh, nzl;            // 32-column groups of the staged Z hi / lo images
+};
+
+// float offset inside a staged image of TCB_HALF rows: element (r, c)
+__device__ __forceinline__ uint32_t stage_off(int r, int c) {
+  return umma::sw128b32_offset(c >> 5, TCB_HALF, r, c & 31);
+}
+
+// write 16 consecutive columns [c0, c0+16) of row r into a staged hi image and lo image (c0 % 16 == 0)
+__device__ __forceinline__ void stage_chunk(float* img_hi, float* img_lo, int r, int c0, const float (&f)[16]) {
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {  // two 32-byte blocks
+    const uint32_t o = stage_off(r, c0 + 8 * b);
+    float4 h0, h1, l0, l1;
+    h0.x = umma::tf32_hi(f[8 * b + 0]); h0.y = umma::tf32_hi(f[8 * b + 1]);
+    h0.z = umma::tf32_hi(f[8 * b + 2]); h0.w = umma::tf32_hi(f[8 * b + 3]);
+    h1.x = umma::tf32_hi(f[8 * b + 4]); h1.y = umma::tf32_hi(f[8 * b + 5]);
+    h1.z = umma::tf32_hi(f[8 * b + 6]); h1.w = umma::tf32_hi(f[8 * b + 7]);
+    l0.x = umma::tf32_hi(f[8 * b + 0] - h0.x); l0.y = umma::tf32_hi(f[8 * b + 1] - h0.y);
+    l0.z = umma::tf32_hi(f[8 * b + 2] - h0.z); l0.w = umma::tf32_hi(f[8 * b + 3] - h0.w);
+    l1.x = umma::tf32_hi(f[8 * b + 4] - h1.x); l1.y = umma::tf32_hi(f[8 * b + 5] - h1.y);
+    l1.z = umma::tf32_hi(f[8 * b + 6] - h1.z); l1.w = umma::tf32_hi(f[8 * b + 7] - h1.w);
+    *reinterpret_cast<float4*>(img_hi + o) = h0;
+    *reinterpret_cast<float4*>(img_hi + o + 4) = h1;
+    *reinterpret_cast<float4*>(img_lo + o) = l0;
+    *reinterpret_cast<float4*>(img_lo + o + 4) = l1;
+  }
+}
+
+// the 8-column block (1, 0, ..., 0) at column c0 of row r (hi image only)
+__device__ __forceinline__ void stage_ones(float* img_hi, int r, int c0) {
+  const uint32_t o = stage_off(r, c0);
+  *reinterpret_cast<float4*>(img_hi + o) = make_float4(1.f, 0.f, 0.f, 0.f);
+  *reinterpret_cast<float4*>(img_hi + o + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// dZ_l = G W_l^T: A = G hi/lo in TMEM [128 x Np_l], B = forward weight image of layer l read K-major, N = Kd_l columns
+__device__ __forceinline__ void tcb_issue_dgrad(const TcLayout& lay, int l, uint32_t wblk_smem, uint32_t tD, uint32_t tAhi,
+                                                uint32_t tAlo) {
+  const uint32_t idesc = umma::make_idesc(TC_TILE, lay.Kd[l], 0, 0);
+  const uint32_t hi = wblk_smem + 4u * lay.img_off[l], lo = hi + 4u * lay.img_floats[l];
+  const uint32_t gstride = 128u * lay.Kp[l];  // bytes between 32-column groups of the image
+  const int nks = lay.Np[l] / 8;
+  auto bdesc = [&](uint32_t base, int ks) {
+    return umma::make_sdesc(base + (uint32_t)(ks >> 2) * gstride + (uint32_t)(ks & 3) * 32u, 0, 512, 1);
+  };
+  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAlo + ks * 8, bdesc(hi, ks), idesc, ks > 0);
+  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAhi + ks * 8, bdesc(lo, ks), idesc, 1);
+  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAhi + ks * 8, bdesc(hi, ks), idesc, 1);
+}
+
+// dW_l^T (+ db_l) += G^T Z over one staged half tile: M = 64, K = TCB_HALF rows, N = Kp_l (Kd_l data columns + ones block)
+__device__ __forceinline__ void tcb_issue_wgrad(const TcLayout& lay, int l, uint32_t ghi, uint32_t glo, uint32_t zhi,
+                                                uint32_t zlo, uint32_t tDw, int accumulate) {
+  const uint32_t id_full = umma::make_idesc(64, lay.Kp[l], 1, 1);
+  const uint32_t id_data = umma::make_idesc(64, lay.Kd[l], 1, 1);
+  const uint32_t lbo = 128u * TCB_HALF;
+  auto desc = [&](uint32_t base, int ks) { return umma::make_sdesc(base + ks * 1024u, lbo, 512, 1); };
+  constexpr int nks = TCB_HALF / 8;
+  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ss(tDw, desc(glo, ks), desc(zhi, ks), id_full, accumulate || ks > 0);
+  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ss(tDw, desc(ghi, ks), desc(zlo, ks), id_data, 1);
+  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ss(tDw, desc(ghi, ks), desc(zhi, ks), id_full, 1);
+}
+
+__device__ __forceinline__ float tcb_act_grad_y(int act, float y) {
+  switch (act) {
+    case NGPDE_ACT_IDENTITY: return 1.f;
+    case NGPDE_ACT_TANH: return fmaf(-y, y, 1.f);
+    case NGPDE_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    default: return act_grad_y(act, y);
+  }
+}
+
+// where column c of dZ_0 goes in the node phase
+struct TcDst {
+  float* base;
+  int ld;
+};
+
+template <bool NODE>
+__global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_constant__ TcBwdArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t bar_d, bar_w, wbar;
+  __shared__ uint32_t tmem_slot;
+  const TcLayout& lay = a.lay;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lq = warp & 3;   // TMEM lane quarter this warp may touch
+  const int q = warp >> 2;   // 16-column chunk served by this warp
+  const int row = lq * 32 + lane;
+  const int c0 = 16 * q;
+  float* wblk = reinterpret_cast<float*>(smem);
+  TcCol* cols = reinterpret_cast<TcCol*>(smem + a.off_cols);
+  TcDst* dcols = reinterpret_cast<TcDst*>(cols + lay.Kd[0]);
+  float* st_zhi = reinterpret_cast<float*>(smem + a.off_stage);
+  float* st_zlo = st_zhi + a.nzh * TCB_HALF * 32;
+  float* st_ghi = st_zlo + a.nzl * TCB_HALF * 32;
+  float* st_glo = st_ghi + 2 * TCB_HALF * 32;
+  float* DZ = reinterpret_cast<float*>(smem + a.off_dz);  // edge phase: [128][Kd0 + 1]
+  const int L = lay.L, Kd0 = lay.Kd[0];
+
+  if (tid < 32) umma::tmem_alloc(&tmem_slot, a.tmem_cols);
+  if (tid == 0) {
+    umma::mbar_init(&wbar, 1);
+    umma::mbar_init(&bar_d, 1);
+    umma::mbar_init(&bar_w, 1);
+    umma::fence_mbar_init();
+  }
+  tc_build_cols(a, cols, Kd0, tid, TCB_THREADS);
+  if (NODE) {
+    for (int c = tid; c < Kd0; c += TCB_THREADS) {
+      TcDst t{nullptr, 0};
+      for (int si = 0; si < a.n_segs; ++si) {
+        const Seg sg = a.segs[si];
+        const int f = c - sg.row;
+        if (f < 0 || f >= sg.width || sg.kind != SEG_DST) continue;
+        if (sg.arr == ARR_X && a.dx_direct != nullptr) t = TcDst{a.dx_direct + sg.col + f, a.ld[ARR_X]};
+        if (sg.arr == ARR_M && a.dmbar != nullptr) t = TcDst{a.dmbar + sg.col + f, a.ld[ARR_M]};
+      }
+      dcols[c] = t;
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  if (tid == 0) {
+    const uint32_t bytes = 4u * lay.block_floats;
+    mbar_arrive_expect_tx(&wbar, bytes);
+    for (uint32_t off = 0; off < bytes; off += 16384)
+      bulk_g2s(smem + off, reinterpret_cast<const uint8_t*>(a.wblock) + off, min(16384u, bytes - off), &wbar);
+  }
+  umma::mbar_wait(&wbar, 0);
+
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
+  const uint32_t tAhi = tmem + a.c_a, tAlo = tAhi + a.a_width, tD = tmem + a.c_d, tDw = tmem + a.c_dw;
+  const uint32_t wblk_smem = umma::smem_u32(wblk);
+  const uint32_t s_zhi = umma::smem_u32(st_zhi), s_zlo = umma::smem_u32(st_zlo), s_ghi = umma::smem_u32(st_ghi),
+                 s_glo = umma::smem_u32(st_glo);
+  uint32_t ph_d = 0, ph_w = 0;
+  const int gdiv = a.tg.gdiv, aggr = a.aggr, dout = a.dout;
+
+  // register accumulators of dW^T: per layer 8 values of the 16-column chunk (k = c0 + 8*(lane>=16) + j, n = 16*lq +
+  // lane%16) plus up to 3 values of the columns beyond 64 (k = 64 + 8*t + 2*q + (lane>=16))
+  float dwacc[TCB_MAXL][11];
+#pragma unroll
+  for (int l = 0; l < TCB_MAXL; ++l)
+#pragma unroll
+    for (int j = 0; j < 11; ++j) dwacc[l][j] = 0.f;
+  const bool upper = lane >= 16;
+
+  for (int unit = blockIdx.x; unit < a.tg.n_units; unit += gridDim.x) {
+    int n0, n1, kbeg, kend;
+    if (NODE) {
+      n0 = unit * TC_TILE;
+      n1 = min(a.tg.N, n0 + TC_TILE);
+      kbeg = n0;
+      kend = n1;
+    } else {
+      n0 = a.tg.unit_ptr[unit];
+      n1 = a.tg.unit_ptr[unit + 1];
+      kbeg = a.tg.rowptr[n0];
+      kend = a.tg.rowptr[n1];
+      if (a.has_dst_side) {
+        for (int item = tid; item < (n1 - n0) * a.dx; item += TCB_THREADS) {
+          const int jj = item / a.dx;
+          if (a.tg.rowptr[n0 + jj] == a.tg.rowptr[n0 + jj + 1]) a.dxdst[(size_t)n0 * a.dx + item] = 0.f;
+        }
+      }
+    }
+    for (int k0 = kbeg; k0 < kend; k0 += TC_TILE) {
+      const int ne = min(TC_TILE, kend - k0);
+      const bool valid = row < ne;
+      int s = 0, d = 0, p = 0;
+      if (valid) {
+        if (NODE) {
+          s = d = p = k0 + row;
+        } else {
+          s = a.tg.src[k0 + row];
+          d = a.tg.dst[k0 + row];
+          p = a.tg.perm[k0 + row];
+        }
+      }
+      const int pg = p / gdiv;
+
+      // ---- 1. forward recompute: Z_1 .. Z_{L-1} ----
+      if (L > 1) {
+        for (int cc = c0; cc < Kd0; cc += 64) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float v = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+            const float h = umma::tf32_hi(v);
+            hi[j] = __float_as_uint(h);
+            lo[j] = __float_as_uint(umma::tf32_hi(v - h));
+          }
+          umma::tmem_st16(tAhi + lane_addr + cc, hi);
+          umma::tmem_st16(tAlo + lane_addr + cc, lo);
+        }
+        if (q == 0) tc_store_ones(tAhi + lane_addr, tAlo + lane_addr, Kd0);
+        umma::tmem_wait_st();
+        umma::tc_fence_before();
+        __syncthreads();
+        for (int l = 0; l < L - 1; ++l) {
+          if (tid == 0) {
+            umma::tc_fence_after();
+            tc_issue_layer(lay, l, wblk_smem, tD, tAhi, tAlo);
+            umma::mma_commit(&bar_d);
+            umma::mbar_wait(&bar_d, ph_d);
+          }
+          ph_d ^= 1;
+          __syncthreads();
+          umma::tc_fence_after();
+          const int Np = lay.Np[l];
+          if (c0 < Np) {
+            uint32_t v[16];
+            umma::tmem_ld16(tD + lane_addr + c0, v);
+            umma::tmem_wait_ld();
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            tc_act16(a.act[l], f);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(f[j]);
+            umma::tmem_st16(tmem + a.c_zs[l + 1] + lane_addr + c0, v);
+            if (l < L - 2) {
+              uint32_t lo[16];
+              tc_split16(f, v, lo);
+              umma::tmem_st16(tAhi + lane_addr + c0, v);
+              umma::tmem_st16(tAlo + lane_addr + c0, lo);
+            }
+          }
+          if (l < L - 2 && q == 0) tc_store_ones(tAhi + lane_addr, tAlo + lane_addr, Np);
+          umma::tmem_wait_st();
+          umma::tc_fence_before();
+          __syncthreads();
+        }
+      }
+
+      // ---- 2. cotangent of the MLP output: chunk of G_L ----
+      float g[16];
+      {
+        const int Np = lay.Np[L - 1];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) g[j] = 0.f;
+        if (valid && c0 < Np) {
+          const float* gp = a.gout_ptr + (size_t)(NODE ? (k0 + row) : d) * dout + c0;
+          if ((dout & 3) == 0 && c0 + 16 <= dout) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(gp + j);
+              g[j] = t.x; g[j + 1] = t.y; g[j + 2] = t.z; g[j + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < dout) g[j] = gp[j];
+          }
+          if (!NODE && aggr == NGPDE_AGGR_MEAN) {
+            const float deg = (float)(a.tg.rowptr[d + 1] - a.tg.rowptr[d]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = __fdiv_rn(g[j], deg);
+          }
+        }
+      }
+
+      // ---- 3. back through the layers ----
+#pragma unroll
+      for (int l = TCB_MAXL - 1; l >= 0; --l) {
+        if (l >= L) continue;
+        const int Np = lay.Np[l], Kd = lay.Kd[l];
+        const bool active = c0 < Np;
+        const bool do_dgrad = l > 0 || a.need_dz0;
+        const uint32_t tDl = (l == 0) ? tmem + a.c_d0 : tD;
+        const uint32_t tDwl = (l == 0) ? tmem + a.c_dw0 : tDw;
+        if (do_dgrad && active) {
+          uint32_t hi[16], lo[16];
+          tc_split16(g, hi, lo);
+          umma::tmem_st16(tAhi + lane_addr + c0, hi);
+          umma::tmem_st16(tAlo + lane_addr + c0, lo);
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          if ((lq >> 1) == h) {
+            const int r = row - TCB_HALF * h;
+            if (active) stage_chunk(st_ghi, st_glo, r, c0, g);
+            // Z_l: the gathered input for l == 0, else the FP32 copy kept in TMEM by the recompute
+            for (int cc = c0; cc < Kd; cc += 64) {
+              float z[16];
+              if (l == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) z[j] = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+              } else {
+                uint32_t v[16];
+                umma::tmem_ld16(tmem + a.c_zs[l] + lane_addr + cc, v);
+                umma::tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(v[j]);
+              }
+              stage_chunk(st_zhi, st_zlo, r, cc, z);
+            }
+            if (q == 0) stage_ones(st_zhi, r, Kd);
+          }
+          umma::fence_async_smem();
+          if (h == 0) {
+            umma::tmem_wait_st();
+            umma::tc_fence_before();
+          }
+          __syncthreads();
+          if (tid == 0) {
+            umma::tc_fence_after();
+            tcb_issue_wgrad(lay, l, s_ghi, s_glo, s_zhi, s_zlo, tDwl, h);
+            umma::mma_commit(&bar_w);
+            if (h == 0 && do_dgrad) {
+              tcb_issue_dgrad(lay, l, wblk_smem, tDl, tAhi, tAlo);
+              umma::mma_commit(&bar_d);
+            }
+            umma::mbar_wait(&bar_w, ph_w);  // the staged half has been consumed
+            if (h == 1 && do_dgrad) umma::mbar_wait(&bar_d, ph_d);
+          }
+          ph_w ^= 1;
+          __syncthreads();
+        }
+        if (do_dgrad) ph_d ^= 1;
+        umma::tc_fence_after();
+
+        // ---- dW^T block of this tile -> register accumulators ----
+        {
+          uint32_t v[16];
+          if (c0 < min(lay.Kp[l], 64)) {
+            umma::tmem_ld16(tDwl + lane_addr + c0, v);
+            umma::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float up = __shfl_sync(0xffffffffu, __uint_as_float(v[8 + j]), lane & 15);
+              dwacc[l][j] += upper ? up : __uint_as_float(v[j]);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            if (64 + 8 * t < lay.Kp[l]) {
+              uint32_t w8[8];
+              umma::tmem_ld8(tDwl + lane_addr + 64 + 8 * t, w8);
+              umma::tmem_wait_ld();
+              const uint32_t ev = q == 0 ? w8[0] : (q == 1 ? w8[2] : (q == 2 ? w8[4] : w8[6]));
+              const uint32_t od = q == 0 ? w8[1] : (q == 1 ? w8[3] : (q == 2 ? w8[5] : w8[7]));
+              const float up = __shfl_sync(0xffffffffu, __uint_as_float(od), lane & 15);
+              dwacc[l][8 + t] += upper ? up : __uint_as_float(ev);
+            }
+          }
+        }
+
+        if (l > 0) {
+          // ---- G_l = dZ_l .* act'(Z_l) for this thread's chunk of layer l-1's output ----
+          const int Npm = lay.Np[l - 1];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g[j] = 0.f;
+          if (c0 < Npm) {
+            uint32_t v[16], zz[16];
+            umma::tmem_ld16(tDl + lane_addr + c0, v);
+            umma::tmem_ld16(tmem + a.c_zs[l] + lane_addr + c0, zz);
+            umma::tmem_wait_ld();
+            const int act = a.act[l - 1];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              g[j] = valid ? __uint_as_float(v[j]) * tcb_act_grad_y(act, __uint_as_float(zz[j])) : 0.f;
+          }
+        } else if (a.need_dz0) {
+          // ---- 4. dZ_0 back to its sources ----
+          for (int cc = c0; cc < Kd0; cc += 64) {
+            uint32_t v[16];
+            umma::tmem_ld16(tDl + lane_addr + cc, v);
+            umma::tmem_wait_ld();
+            if (NODE) {
+              if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const TcDst t = dcols[cc + j];
+                  if (t.base != nullptr) t.base[(size_t)(k0 + row) * t.ld] = __uint_as_float(v[j]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) DZ[row * (Kd0 + 1) + cc + j] = __uint_as_float(v[j]);
+            }
+          }
+        }
+        umma::tc_fence_before();
+      }
+
+      if (!NODE && a.need_dz0) {
+        __syncthreads();
+        const int dx = a.dx, ldz = Kd0 + 1;
+        // source side: one row per edge, reduced later over the src-sorted transpose
+        for (int item = tid; item < ne * dx; item += TCB_THREADS) {
+          const int e = item / dx, c = item - e * dx;
+          float v = 0.f;
+          for (int si = 0; si < a.n_segs; ++si) {
+            const Seg sg = a.segs[si];
+            if (sg.arr != ARR_X || c < sg.col || c >= sg.col + sg.width) continue;
+            const float cf = coef_src(sg.kind);
+            if (cf != 0.f) v = fmaf(cf, DZ[e * ldz + sg.row + c - sg.col], v);
+          }
+          a.desrc[(size_t)(k0 + e) * dx + c] = v;
+        }
+        // destination side: sequential over the row's edges, carried across tiles through dxdst itself
+        if (a.has_dst_side) {
+          for (int item = tid; item < (n1 - n0) * dx; item += TCB_THREADS) {
+            const int jj = item / dx, c = item - jj * dx;
+            const int j = n0 + jj;
+            const int r0 = a.tg.rowptr[j], r1 = a.tg.rowptr[j + 1];
+            const int lo = max(r0, k0), hi = min(r1, k0 + ne);
+            if (lo >= hi) continue;
+            float accv = (lo == r0) ? 0.f : a.dxdst[(size_t)j * dx + c];
+            for (int si = 0; si < a.n_segs; ++si) {
+              const Seg sg = a.segs[si];
+              if (sg.arr != ARR_X || c < sg.col || c >= sg.col + sg.width) continue;
+              const float cf = coef_dst(sg.kind);
+              if (cf == 0.f) continue;
+              const float* gr = DZ + sg.row + c - sg.col;
+              for (int e = lo; e < hi; ++e) accv = fmaf(cf, gr[(e - k0) * ldz], accv);
+            }
+            a.dxdst[(size_t)j * dx + c] = accv;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- this CTA's parameter-gradient partial ----
+  {
+    float* dWp = a.dparams_partial + (size_t)blockIdx.x * a.n_params;
+    const int n = 16 * lq + (lane & 15);
+#pragma unroll
+    for (int l = 0; l < TCB_MAXL; ++l) {
+      if (l >= L) continue;
+      const int K = lay.K[l], N = lay.N[l], Kd = lay.Kd[l];
+      if (n >= N) continue;
+      auto put = [&](int k, float v) {
+        if (k < K) dWp[a.w_off[l] + (size_t)k * N + n] = v;
+        else if (k == Kd && a.b_off[l] >= 0) dWp[a.b_off[l] + n] = v;
+      };
+#pragma unroll
+      for (int j = 0; j < 8; ++j) put(c0 + (upper ? 8 : 0) + j, dwacc[l][j]);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) put(64 + 8 * t + 2 * q + (upper ? 1 : 0), dwacc[l][8 + t]);
+    }
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(tmem, a.tmem_cols);
+}
+
+}  // namespace ngpde

@@ -458,3 +458,85 @@ def test_tensor_core_path_odd_widths(dims):
     layer = VMHConv(phi, gam, initialgraph=g, aggr="mean")
     ps, st = setup(rng, layer, DEV)
     check_layer(layer, jl_rand(rng, dx, n, DEV), ps, st, g)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tensor-core BACKWARD (tcgen05 dgrad + wgrad, ngpde_tc_bwd.cuh)
+# ------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("dims,gdims,aggr", [
+    ([6, 64, 64, 64, 64], [66, 64, 64, 64, 2], "mean"),     # the C3 shapes
+    ([6, 16, 48, 5], [7, 40, 3], "+"),                      # narrow / odd widths, 3 and 2 layers
+    ([10, 33, 10], [14, 24, 9, 3], "mean"),
+    ([6, 64], [66, 2], "mean"),                             # single Dense layers (no recompute at all)
+    ([34, 64, 64], [80, 64, 64], "+"),                      # wide inputs: Kd0 = 48 / 80
+])
+def test_tensor_core_backward_shapes(dims, gdims, aggr):
+    rng = np.random.default_rng(77)
+    n = 900
+    s, t = rng.integers(0, n, 7000), rng.integers(0, n, 7000)
+    # a row longer than one tile (two for `mean`; an unnormalised float32 sum over 300 messages is itself only good to
+    # ~1e-5 -- the float32 and float64 oracles differ by that much -- so the `+` cases stop at 130)
+    t[:(300 if aggr == "mean" else 130)] = 11
+    t[300:310] = n - 1
+    dx = dims[0] // 2 - 1              # phi input = [x_i (dx); x_j - x_i (dx); pos (2)]
+    assert gdims[0] == dx + dims[-1]
+    g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"x": jl_rand(rng, 2, n)}).to(DEV)
+    # smooth activations only: relu's derivative is discontinuous, so a pre-activation within rounding distance of 0
+    # flips it and the float32 and float64 ORACLES then disagree with each other by more than the tolerance
+    acts = ["tanh", "sigmoid", "elu", "softplus"]
+    mk = lambda dd: Chain(*[Dense(dd[i], dd[i + 1], acts[i % 4] if i < len(dd) - 2 else "identity") for i in range(len(dd) - 1)])
+    layer = VMHConv(mk(dims), mk(gdims), initialgraph=g, aggr=aggr)
+    ps, st = setup(rng, layer, DEV)
+    check_layer(layer, jl_rand(rng, dx, n, DEV), ps, st, g)
+
+
+def test_tensor_core_backward_relu():
+    """relu in the hidden layers: compared where the comparison is well-posed -- every pre-activation of the float64 oracle
+    is at least 2e-5 away from the kink (inputs are re-drawn until that holds), so no arithmetic can flip a derivative."""
+    rng = np.random.default_rng(78)
+    n = 300
+    s, t = rng.integers(0, n, 2000), rng.integers(0, n, 2000)
+    g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"x": jl_rand(rng, 2, n)}).to(DEV)
+    layer = VMHConv(Chain(Dense(6, 32, "relu"), Dense(32, 8)), Chain(Dense(10, 16, "relu"), Dense(16, 2)), initialgraph=g)
+    ps, st = setup(rng, layer, DEV)
+    og = to_ograph(g, torch.float64)
+    from common import tree_to_cpu
+    pc = tree_to_cpu(ps, torch.float64)
+    for attempt in range(50):
+        x = jl_rand(rng, 2, n, DEV)
+        xc = x.cpu().double()
+        xi, xj = xc[:, og.t], xc[:, og.s]
+        pos = og.ndata["x"]
+        z0 = torch.cat([xi, xj - xi, pos[:, og.s] - pos[:, og.t]], 0)
+        pre_e = pc["\u03d5"]["layer_1"]["weight"] @ z0 + pc["\u03d5"]["layer_1"]["bias"]
+        mbar = orc.scatter("mean", orc.mlp(z0, pc["\u03d5"], ngpde.lux.mlp_spec(layer.ϕ)), og.t, n)
+        pre_n = pc["\u03b3"]["layer_1"]["weight"] @ torch.cat([xc, mbar], 0) + pc["\u03b3"]["layer_1"]["bias"]
+        if pre_e.abs().min() > 2e-5 and pre_n.abs().min() > 2e-5:
+            break
+    else:
+        pytest.skip("no draw keeps every pre-activation away from the relu kink")
+    check_layer(layer, x, ps, st, g)
+
+
+def test_tensor_core_and_ffma_backward_agree():
+    w = workloads.c3_vmh(DEV, side=48)
+    gen = torch.Generator().manual_seed(5)
+    dy = torch.randn(2, w.n_nodes, generator=gen).to(DEV)
+    _, dx_tc, dp_tc = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy)
+    ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, 0)
+    try:
+        _, dx_ff, dp_ff = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy)
+    finally:
+        ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, 1)
+    assert not torch.equal(dp_tc, dp_ff)  # different kernels really ran
+    assert relerr(dx_tc, dx_ff) <= TOL and relerr(dp_tc, dp_ff) <= TOL
+
+
+def test_tensor_core_backward_is_deterministic():
+    w = workloads.c3_vmh(DEV, side=64)
+    gen = torch.Generator().manual_seed(6)
+    dy = torch.randn(2, w.n_nodes, generator=gen).to(DEV)
+    a = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy)
+    b = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy)
+    assert all(torch.equal(u, v) for u, v in zip(a, b))

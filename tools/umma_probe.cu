@@ -199,13 +199,7 @@ __global__ void __launch_bounds__(128) probe_kernel(Params p, const float* __res
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-static float tf32_trunc_host(float x) {
-  uint32_t u;
-  memcpy(&u, &x, 4);
-  u &= 0xFFFFE000u;
-  memcpy(&x, &u, 4);
-  return x;
-}
+static float tf32_trunc_host(float x) { return tf32_hi(x); }  // the same rounding the device split uses
 
 int main(int argc, char** argv) {
   Params p{};
