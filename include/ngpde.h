@@ -226,6 +226,9 @@ int ngpde_rows_segment_add(float* dst, const float* src, const int32_t* seg_rows
  * thread-safe; meant for benchmarks. ---- */
 enum { NGPDE_PROF_FWD_EDGE = 0, NGPDE_PROF_FWD_NODE = 1, NGPDE_PROF_BWD_NODE = 2, NGPDE_PROF_BWD_EDGE = 3, NGPDE_PROF_SLOTS = 4 };
 int ngpde_profile_enable(int32_t on);
+/* developer aid: while a device buffer of 512 int64 is registered, CTA 0 of the tensor-core edge-phase backward writes
+ * clock64() stamps of its phases for its first 16 tiles ([tile][32]); NULL switches it off. */
+int ngpde_debug_buffer(void* device_int64_x512);
 int ngpde_profile_read(double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus

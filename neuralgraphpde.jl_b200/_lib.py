@@ -29,7 +29,7 @@ EXPORTS = [
     "ngpde_mppde_conv_forward", "ngpde_mppde_conv_backward", "ngpde_gno_conv_forward", "ngpde_gno_conv_backward",
     "ngpde_gcn_workspace_bytes", "ngpde_gcn_conv_forward", "ngpde_gcn_conv_backward", "ngpde_axpy_stages",
     "ngpde_profile_enable", "ngpde_profile_read", "ngpde_set_option", "ngpde_rows_gather", "ngpde_rows_put",
-    "ngpde_rows_segment_add",
+    "ngpde_rows_segment_add", "ngpde_debug_buffer",
 ]
 
 
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
     lib.ngpde_rows_gather.argtypes = [vp, vp, i64, i32, vp, vp]
     lib.ngpde_rows_put.argtypes = [vp, vp, vp, vp, i32, i64, i32, vp]
     lib.ngpde_rows_segment_add.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
+    lib.ngpde_debug_buffer.argtypes = [vp]
     lib.ngpde_set_option.argtypes = [i32, i32]
     lib.ngpde_profile_enable.argtypes = [i32]
     lib.ngpde_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]

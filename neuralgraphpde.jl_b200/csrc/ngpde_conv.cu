@@ -39,6 +39,7 @@ struct ProfScope {
 // ---- tensor-core (tcgen05) path selection ----
 constexpr int kSmemMaxTc = 227 * 1024;
 bool g_use_tc = true;
+long long* g_tcb_dbg = nullptr;  // NGPDE_OPT_DEBUG_BUFFER: phase timestamps of the tensor-core backward (edge phase)
 
 int pad16(int x) { return (x + 15) / 16 * 16; }
 
@@ -695,6 +696,7 @@ int launch_bwd_tc(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base, f
   std::memcpy(a.c_zs, t.c_zs, sizeof(a.c_zs));
   a.c_a = t.c_a; a.a_width = t.a_width; a.c_d = t.c_d; a.c_dw = t.c_dw; a.c_d0 = t.c_d0; a.c_dw0 = t.c_dw0; a.tmem_cols = t.tmem_cols;
   a.off_cols = t.off_cols; a.off_stage = t.off_stage; a.off_dz = t.off_dz; a.nzh = t.nzh; a.nzl = t.nzl;
+  a.dbg = NODE ? nullptr : g_tcb_dbg;
   NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_bwd_tc_kernel<NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
   mp_bwd_tc_kernel<NODE><<<t.grid, TCB_THREADS, t.smem, st>>>(a);
   NGPDE_CUDA_TRY(cudaGetLastError());
@@ -926,6 +928,11 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
                                                                         g->tptr, g->tpos, (int)g->N, desc->dx, io->dx);
   }
   NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
+extern "C" int ngpde_debug_buffer(void* device_int64_x512) {
+  g_tcb_dbg = static_cast<long long*>(device_int64_x512);
   return NGPDE_OK;
 }
 

@@ -55,6 +55,7 @@ struct TcBwdArgs {
   // shared memory byte offsets
   int off_cols, off_stage, off_dz;
   int nzh, nzl;            // 32-column groups of the staged Z hi / lo images
+  long long* dbg;          // optional phase timestamps (clock64) of CTA 0, thread 64: [tile][64]; nullptr = off
 };
 
 // float offset inside a staged image of TCB_HALF rows: element (r, c)
@@ -90,32 +91,43 @@ __device__ __forceinline__ void stage_ones(float* img_hi, int r, int c0) {
   *reinterpret_cast<float4*>(img_hi + o + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// dZ_l = G W_l^T: A = G hi/lo in TMEM [128 x Np_l], B = forward weight image of layer l read K-major, N = Kd_l columns
+// dZ_l = G W_l^T: A = G hi/lo in TMEM [128 x Np_l], B = forward weight image of layer l read K-major, N = Kd_l columns.
+// K-step ks covers columns [8 ks, 8 ks + 8) of the image rows: group ks / 4 (gstride bytes apart), 32-byte block ks % 4.
 __device__ __forceinline__ void tcb_issue_dgrad(const TcLayout& lay, int l, uint32_t wblk_smem, uint32_t tD, uint32_t tAhi,
                                                 uint32_t tAlo) {
   const uint32_t idesc = umma::make_idesc(TC_TILE, lay.Kd[l], 0, 0);
-  const uint32_t hi = wblk_smem + 4u * lay.img_off[l], lo = hi + 4u * lay.img_floats[l];
-  const uint32_t gstride = 128u * lay.Kp[l];  // bytes between 32-column groups of the image
+  const uint32_t hi = wblk_smem + 4u * lay.img_off[l];
+  const uint64_t dhi = umma::make_sdesc(hi, 0, 512, 1);
+  const uint64_t dlo = dhi + (uint64_t)(lay.img_floats[l] >> 2);  // image sizes are multiples of 1 KB: no field overflow
+  const uint32_t g16 = 8u * lay.Kp[l];                             // group stride in 16-byte units
   const int nks = lay.Np[l] / 8;
-  auto bdesc = [&](uint32_t base, int ks) {
-    return umma::make_sdesc(base + (uint32_t)(ks >> 2) * gstride + (uint32_t)(ks & 3) * 32u, 0, 512, 1);
-  };
-  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAlo + ks * 8, bdesc(hi, ks), idesc, ks > 0);
-  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAhi + ks * 8, bdesc(lo, ks), idesc, 1);
-  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ts(tD, tAhi + ks * 8, bdesc(hi, ks), idesc, 1);
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+    const uint32_t ta = pass == 0 ? tAlo : tAhi;
+    const uint64_t db = pass == 1 ? dlo : dhi;
+#pragma unroll 4
+    for (int ks = 0; ks < nks; ++ks)
+      umma::mma_tf32_ts(tD, ta + ks * 8, db + (uint64_t)((ks >> 2) * g16 + (ks & 3) * 2u), idesc, (pass | ks) != 0);
+  }
 }
 
-// dW_l^T (+ db_l) += G^T Z over one staged half tile: M = 64, K = TCB_HALF rows, N = Kp_l (Kd_l data columns + ones block)
+// dW_l^T (+ db_l) += G^T Z over one staged half tile: M = 64, K = TCB_HALF rows, N = Kp_l (Kd_l data columns + ones block);
+// one K-step = 8 staged rows = 1024 bytes = 64 descriptor address units
 __device__ __forceinline__ void tcb_issue_wgrad(const TcLayout& lay, int l, uint32_t ghi, uint32_t glo, uint32_t zhi,
                                                 uint32_t zlo, uint32_t tDw, int accumulate) {
   const uint32_t id_full = umma::make_idesc(64, lay.Kp[l], 1, 1);
   const uint32_t id_data = umma::make_idesc(64, lay.Kd[l], 1, 1);
   const uint32_t lbo = 128u * TCB_HALF;
-  auto desc = [&](uint32_t base, int ks) { return umma::make_sdesc(base + ks * 1024u, lbo, 512, 1); };
+  const uint64_t dgh = umma::make_sdesc(ghi, lbo, 512, 1), dgl = umma::make_sdesc(glo, lbo, 512, 1);
+  const uint64_t dzh = umma::make_sdesc(zhi, lbo, 512, 1), dzl = umma::make_sdesc(zlo, lbo, 512, 1);
   constexpr int nks = TCB_HALF / 8;
-  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ss(tDw, desc(glo, ks), desc(zhi, ks), id_full, accumulate || ks > 0);
-  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ss(tDw, desc(ghi, ks), desc(zlo, ks), id_data, 1);
-  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ss(tDw, desc(ghi, ks), desc(zhi, ks), id_full, 1);
+#pragma unroll
+  for (int ks = 0; ks < nks; ++ks)
+    umma::mma_tf32_ss(tDw, dgl + (uint64_t)(ks * 64), dzh + (uint64_t)(ks * 64), id_full, accumulate | (ks > 0));
+#pragma unroll
+  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ss(tDw, dgh + (uint64_t)(ks * 64), dzl + (uint64_t)(ks * 64), id_data, 1);
+#pragma unroll
+  for (int ks = 0; ks < nks; ++ks) umma::mma_tf32_ss(tDw, dgh + (uint64_t)(ks * 64), dzh + (uint64_t)(ks * 64), id_full, 1);
 }
 
 __device__ __forceinline__ float tcb_act_grad_y(int act, float y) {
@@ -132,6 +144,11 @@ struct TcDst {
   float* base;
   int ld;
 };
+
+#define TCB_STAMP(slot)                                                                          \
+  do {                                                                                           \
+    if (a.dbg != nullptr && blockIdx.x == 0 && tid == 64 && dbg_tile < 8) a.dbg[dbg_tile * 64 + (slot)] = clock64(); \
+  } while (0)
 
 template <bool NODE>
 __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_constant__ TcBwdArgs a) {
@@ -204,6 +221,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 #pragma unroll
     for (int j = 0; j < 11; ++j) dwacc[l][j] = 0.f;
   const bool upper = lane >= 16;
+  int dbg_tile = 0;
 
   for (int unit = blockIdx.x; unit < a.tg.n_units; unit += gridDim.x) {
     int n0, n1, kbeg, kend;
@@ -238,6 +256,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         }
       }
       const int pg = p / gdiv;
+      TCB_STAMP(0);
 
       // ---- 1. forward recompute: Z_1 .. Z_{L-1} ----
       if (L > 1) {
@@ -265,13 +284,16 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             umma::mbar_wait(&bar_d, ph_d);
           }
           ph_d ^= 1;
+          if (l == 1) TCB_STAMP(34);
           __syncthreads();
+          if (l == 1) TCB_STAMP(35);
           umma::tc_fence_after();
           const int Np = lay.Np[l];
           if (c0 < Np) {
             uint32_t v[16];
             umma::tmem_ld16(tD + lane_addr + c0, v);
             umma::tmem_wait_ld();
+            if (l == 1) TCB_STAMP(36);
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -287,12 +309,16 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             }
           }
           if (l < L - 2 && q == 0) tc_store_ones(tAhi + lane_addr, tAlo + lane_addr, Np);
+          if (l == 1) TCB_STAMP(37);
           umma::tmem_wait_st();
+          if (l == 1) TCB_STAMP(38);
           umma::tc_fence_before();
           __syncthreads();
+          if (l == 1) TCB_STAMP(39);
         }
       }
 
+      TCB_STAMP(1);
       // ---- 2. cotangent of the MLP output: chunk of G_L ----
       float g[16];
       {
@@ -320,15 +346,62 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         }
       }
 
-      // ---- 3. back through the layers ----
+      TCB_STAMP(2);
+      // ---- 3. back through the layers.  Per layer: G -> TMEM A operand and rows 0..63 staged; warp 1 issues the
+      // weight-gradient MMAs of that half, warp 0 the input-gradient MMAs; rows 64..127 are staged as soon as the first
+      // half has been consumed; second weight-gradient batch; the next G is formed from dZ while that batch still runs
+      // and the dW^T block is collected at the top of the following layer.  (The layer loop is deliberately NOT unrolled:
+      // the unrolled kernel was 250 KB of SASS and spent its time in instruction-cache misses.)
+      auto collect_dw = [&](int l, uint32_t tDwl) {
+        float add[11];
 #pragma unroll
-      for (int l = TCB_MAXL - 1; l >= 0; --l) {
-        if (l >= L) continue;
+        for (int j = 0; j < 11; ++j) add[j] = 0.f;
+        if (c0 < min(lay.Kp[l], 64)) {
+          uint32_t v[16];
+          umma::tmem_ld16(tDwl + lane_addr + c0, v);
+          umma::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float up = __shfl_sync(0xffffffffu, __uint_as_float(v[8 + j]), lane & 15);
+            add[j] = upper ? up : __uint_as_float(v[j]);
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          if (64 + 8 * t < lay.Kp[l]) {
+            uint32_t w8[8];
+            umma::tmem_ld8(tDwl + lane_addr + 64 + 8 * t, w8);
+            umma::tmem_wait_ld();
+            const uint32_t ev = q == 0 ? w8[0] : (q == 1 ? w8[2] : (q == 2 ? w8[4] : w8[6]));
+            const uint32_t od = q == 0 ? w8[1] : (q == 1 ? w8[3] : (q == 2 ? w8[5] : w8[7]));
+            const float up = __shfl_sync(0xffffffffu, __uint_as_float(od), lane & 15);
+            add[8 + t] = upper ? up : __uint_as_float(ev);
+          }
+        }
+        // register accumulators need compile-time indices
+#pragma unroll
+        for (int ll = 0; ll < TCB_MAXL; ++ll) {
+          if (ll == l) {
+#pragma unroll
+            for (int j = 0; j < 11; ++j) dwacc[ll][j] += add[j];
+          }
+        }
+      };
+#pragma unroll 1
+      for (int l = L - 1; l >= 0; --l) {
         const int Np = lay.Np[l], Kd = lay.Kd[l];
         const bool active = c0 < Np;
         const bool do_dgrad = l > 0 || a.need_dz0;
         const uint32_t tDl = (l == 0) ? tmem + a.c_d0 : tD;
         const uint32_t tDwl = (l == 0) ? tmem + a.c_dw0 : tDw;
+        // the previous layer's dW^T block (its second MMA batch also frees the staging buffer)
+        if (l < L - 1) {
+          umma::mbar_wait(&bar_w, ph_w);
+          ph_w ^= 1;
+          umma::tc_fence_after();
+          collect_dw(l + 1, tDw);
+        }
+        TCB_STAMP(3 + 6 * l);
         if (do_dgrad && active) {
           uint32_t hi[16], lo[16];
           tc_split16(g, hi, lo);
@@ -337,6 +410,11 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
+          if (h == 1) {
+            umma::mbar_wait(&bar_w, ph_w);  // the first half has been consumed
+            ph_w ^= 1;
+            TCB_STAMP(5 + 6 * l);
+          }
           if ((lq >> 1) == h) {
             const int r = row - TCB_HALF * h;
             if (active) stage_chunk(st_ghi, st_glo, r, c0, g);
@@ -358,90 +436,85 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             if (q == 0) stage_ones(st_zhi, r, Kd);
           }
           umma::fence_async_smem();
-          if (h == 0) {
-            umma::tmem_wait_st();
-            umma::tc_fence_before();
-          }
+          umma::tmem_wait_st();
+          umma::tc_fence_before();
           __syncthreads();
-          if (tid == 0) {
+          TCB_STAMP(4 + 2 * h + 6 * l);
+          if (tid == 32) {
             umma::tc_fence_after();
             tcb_issue_wgrad(lay, l, s_ghi, s_glo, s_zhi, s_zlo, tDwl, h);
             umma::mma_commit(&bar_w);
-            if (h == 0 && do_dgrad) {
-              tcb_issue_dgrad(lay, l, wblk_smem, tDl, tAhi, tAlo);
-              umma::mma_commit(&bar_d);
-            }
-            umma::mbar_wait(&bar_w, ph_w);  // the staged half has been consumed
-            if (h == 1 && do_dgrad) umma::mbar_wait(&bar_d, ph_d);
+          } else if (tid == 0 && h == 0 && do_dgrad) {
+            umma::tc_fence_after();
+            tcb_issue_dgrad(lay, l, wblk_smem, tDl, tAhi, tAlo);
+            umma::mma_commit(&bar_d);
           }
-          ph_w ^= 1;
-          __syncthreads();
         }
-        if (do_dgrad) ph_d ^= 1;
+        if (do_dgrad) {
+          umma::mbar_wait(&bar_d, ph_d);
+          ph_d ^= 1;
+        }
+        TCB_STAMP(7 + 6 * l);
         umma::tc_fence_after();
-
-        // ---- dW^T block of this tile -> register accumulators ----
-        {
-          uint32_t v[16];
-          if (c0 < min(lay.Kp[l], 64)) {
-            umma::tmem_ld16(tDwl + lane_addr + c0, v);
-            umma::tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float up = __shfl_sync(0xffffffffu, __uint_as_float(v[8 + j]), lane & 15);
-              dwacc[l][j] += upper ? up : __uint_as_float(v[j]);
-            }
-          }
-#pragma unroll
-          for (int t = 0; t < 3; ++t) {
-            if (64 + 8 * t < lay.Kp[l]) {
-              uint32_t w8[8];
-              umma::tmem_ld8(tDwl + lane_addr + 64 + 8 * t, w8);
-              umma::tmem_wait_ld();
-              const uint32_t ev = q == 0 ? w8[0] : (q == 1 ? w8[2] : (q == 2 ? w8[4] : w8[6]));
-              const uint32_t od = q == 0 ? w8[1] : (q == 1 ? w8[3] : (q == 2 ? w8[5] : w8[7]));
-              const float up = __shfl_sync(0xffffffffu, __uint_as_float(od), lane & 15);
-              dwacc[l][8 + t] += upper ? up : __uint_as_float(ev);
-            }
-          }
-        }
-
         if (l > 0) {
-          // ---- G_l = dZ_l .* act'(Z_l) for this thread's chunk of layer l-1's output ----
-          const int Npm = lay.Np[l - 1];
+          // G_l = dZ_l .* act'(Z_l) for this thread's chunk of layer l-1's output
 #pragma unroll
           for (int j = 0; j < 16; ++j) g[j] = 0.f;
-          if (c0 < Npm) {
+          if (c0 < lay.Np[l - 1]) {  // warp-uniform: tcgen05.ld is .sync.aligned (never put `valid` in this condition)
             uint32_t v[16], zz[16];
             umma::tmem_ld16(tDl + lane_addr + c0, v);
             umma::tmem_ld16(tmem + a.c_zs[l] + lane_addr + c0, zz);
             umma::tmem_wait_ld();
             const int act = a.act[l - 1];
+            if (act == NGPDE_ACT_TANH) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              g[j] = valid ? __uint_as_float(v[j]) * tcb_act_grad_y(act, __uint_as_float(zz[j])) : 0.f;
-          }
-        } else if (a.need_dz0) {
-          // ---- 4. dZ_0 back to its sources ----
-          for (int cc = c0; cc < Kd0; cc += 64) {
-            uint32_t v[16];
-            umma::tmem_ld16(tDl + lane_addr + cc, v);
-            umma::tmem_wait_ld();
-            if (NODE) {
-              if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const TcDst t = dcols[cc + j];
-                  if (t.base != nullptr) t.base[(size_t)(k0 + row) * t.ld] = __uint_as_float(v[j]);
-                }
+              for (int j = 0; j < 16; ++j) {
+                const float y = __uint_as_float(zz[j]);
+                g[j] = __uint_as_float(v[j]) * fmaf(-y, y, 1.f);
               }
-            } else {
+            } else if (act == NGPDE_ACT_IDENTITY) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) DZ[row * (Kd0 + 1) + cc + j] = __uint_as_float(v[j]);
+              for (int j = 0; j < 16; ++j) g[j] = __uint_as_float(v[j]);
+            } else {
+#pragma unroll 1
+              for (int j = 0; j < 16; ++j) zz[j] = __float_as_uint(act_grad_y(act, __uint_as_float(zz[j])));
+#pragma unroll
+              for (int j = 0; j < 16; ++j) g[j] = __uint_as_float(v[j]) * __uint_as_float(zz[j]);
+            }
+            if (!valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) g[j] = 0.f;
             }
           }
+        } else {
+          if (a.need_dz0) {
+            // ---- 4. dZ_0 back to its sources ----
+            for (int cc = c0; cc < Kd0; cc += 64) {
+              uint32_t v[16];
+              umma::tmem_ld16(tDl + lane_addr + cc, v);
+              umma::tmem_wait_ld();
+              if (NODE) {
+                if (valid) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    const TcDst t = dcols[cc + j];
+                    if (t.base != nullptr) t.base[(size_t)(k0 + row) * t.ld] = __uint_as_float(v[j]);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) DZ[row * (Kd0 + 1) + cc + j] = __uint_as_float(v[j]);
+              }
+            }
+          }
+          // layer 0's dW^T block closes the tile
+          umma::mbar_wait(&bar_w, ph_w);
+          ph_w ^= 1;
+          umma::tc_fence_after();
+          collect_dw(0, tDwl);
         }
         umma::tc_fence_before();
+        TCB_STAMP(8 + 6 * l);
       }
 
       if (!NODE && a.need_dz0) {
@@ -481,6 +554,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         }
       }
       __syncthreads();
+      TCB_STAMP(27);
+      ++dbg_tile;
     }
   }
 
