@@ -6,8 +6,7 @@
 #include <vector>
 
 #include "ngpde_conv_kernels.cuh"
-#include "ngpde_tc.cuh"
-#include "ngpde_tc_bwd.cuh"
+#include "ngpde_tc_layout.cuh"
 
 namespace ngpde {
 namespace {
@@ -35,123 +34,6 @@ struct ProfScope {
     if (on) cudaEventRecord(e1, st);
   }
 };
-
-// ---- tensor-core (tcgen05) path selection ----
-constexpr int kSmemMaxTc = 227 * 1024;
-bool g_use_tc = true;
-long long* g_tcb_dbg = nullptr;  // NGPDE_OPT_DEBUG_BUFFER: phase timestamps of the tensor-core backward (edge phase)
-
-int pad16(int x) { return (x + 15) / 16 * 16; }
-
-// Shapes and prepared-weight-block offsets of `m` on the tensor-core path; false when a layer is too wide for it.
-bool tc_fill_layout(const MlpDev& m, TcLayout* lay) {
-  if (m.L < 1 || m.L > NGPDE_MAX_LAYERS) return false;
-  *lay = TcLayout{};
-  lay->L = m.L;
-  int off = 0, kmax = 0;
-  for (int l = 0; l < m.L; ++l) {
-    const int K = m.dims[l], N = m.dims[l + 1];
-    if (N > TC_MAXN || K > 192) return false;
-    lay->K[l] = K;
-    lay->N[l] = N;
-    lay->Kd[l] = pad16(K);
-    lay->Kp[l] = lay->Kd[l] + 8;
-    lay->Np[l] = pad16(N);
-    lay->img_floats[l] = ((lay->Np[l] + 31) / 32) * lay->Kp[l] * 32;
-    lay->img_off[l] = off;
-    off += 2 * lay->img_floats[l];  // Kp is a multiple of 8, so every image is a multiple of 1 KB
-    kmax = std::max(kmax, lay->Kp[l]);
-  }
-  lay->block_floats = off;
-  lay->kmax = kmax;
-  lay->cols_group = TC_MAXN + 2 * kmax;
-  return true;
-}
-
-// Backward on tensor cores: TMEM column map, shared-memory map and eligibility (see ngpde_tc_bwd.cuh).
-struct TcBwdPhase {
-  bool on = false;
-  TcLayout lay{};
-  int smem = 0;
-  int c_zs[NGPDE_MAX_LAYERS] = {0};
-  int c_a = 0, a_width = 0, c_d = 0, c_dw = 0, c_d0 = 0, c_dw0 = 0, tmem_cols = 0;
-  int off_cols = 0, off_stage = 0, off_dz = 0, nzh = 0, nzl = 0;
-  size_t ws_off = 0;
-  int grid = 0;
-};
-
-bool tc_bwd_make(const MlpDev& m, bool contract, bool addend, bool node, int aggr, bool need_dz0, TcBwdPhase* t) {
-  *t = TcBwdPhase{};
-  if (!g_use_tc || contract || addend || m.L > TCB_MAXL) return false;
-  if (!node && !(aggr == NGPDE_AGGR_SUM || aggr == NGPDE_AGGR_MEAN)) return false;
-  if (!tc_fill_layout(m, &t->lay)) return false;
-  const TcLayout& lay = t->lay;
-  const int L = lay.L;
-  if (m.act[L - 1] != NGPDE_ACT_IDENTITY) return false;  // Z_L is not recomputed
-  for (int l = 0; l < L; ++l) {
-    if (!act_grad_from_y(m.act[l])) return false;         // swish / gelu need the pre-activation
-    if (lay.Kp[l] > 88) return false;                     // register accumulators cover 64 + 24 columns of dW^T
-  }
-  // TMEM columns
-  int zs = 0, wdw = 0, kdmax = 0;
-  for (int l = 1; l < L; ++l) {
-    t->c_zs[l] = zs;
-    zs += lay.Kd[l];
-    wdw = std::max(wdw, lay.Kp[l]);
-  }
-  for (int l = 0; l < L; ++l) kdmax = std::max(kdmax, lay.Kd[l]);
-  // one A image holds a layer input (Kp columns, forward recompute) or a layer-output cotangent (Np columns, backward)
-  t->a_width = lay.kmax;
-  for (int l = 0; l < L; ++l) t->a_width = std::max(t->a_width, lay.Np[l]);
-  t->c_a = zs;
-  t->c_d = zs + 2 * t->a_width;
-  t->c_dw = t->c_d + 64;
-  if (zs >= lay.Kd[0] + lay.Kp[0]) {  // layer 0's outputs may overwrite the (dead by then) activation copies
-    t->c_d0 = 0;
-    t->c_dw0 = lay.Kd[0];
-  } else {
-    if (lay.Kd[0] > 64) return false;
-    t->c_d0 = t->c_d;
-    t->c_dw0 = t->c_dw;
-    wdw = std::max(wdw, lay.Kp[0]);
-  }
-  const int total = t->c_dw + wdw;
-  if (total > 512) return false;
-  int cols = 32;
-  while (cols < total) cols *= 2;
-  t->tmem_cols = cols;
-  // shared memory
-  t->nzh = (kdmax + 8 + 31) / 32;
-  t->nzl = (kdmax + 31) / 32;
-  t->off_cols = 4 * lay.block_floats;
-  t->off_stage = (t->off_cols + (int)(sizeof(TcCol) + sizeof(TcDst)) * lay.Kd[0] + 1023) & ~1023;
-  t->off_dz = t->off_stage + (t->nzh + t->nzl + 4) * TCB_HALF * 128;
-  const int dz_bytes = (!node && need_dz0) ? TC_TILE * (lay.Kd[0] + 1) * 4 : 0;
-  const int totalb = 1024 + t->off_dz + dz_bytes;
-  if (totalb > kSmemMaxTc) return false;
-  t->smem = std::max(totalb, 116 * 1024);  // one CTA per SM: its TMEM allocation must not wait for a neighbour's
-  t->on = true;
-  return true;
-}
-
-// Lays out the prepared weight block of `m` and decides whether the tcgen05 forward kernels can run it.
-bool tc_make_layout(const MlpDev& m, bool contract, bool addend, int dout, bool node, TcLayout* lay, int* smem_bytes,
-                    int* off_cols, int* off_groups, int* group_bytes) {
-  if (!g_use_tc || contract || addend || m.L < 1 || m.L > NGPDE_MAX_LAYERS) return false;
-  if (!tc_fill_layout(m, lay)) return false;
-  const int need = TC_GROUPS * lay->cols_group;
-  if (need > 512) return false;
-  int cols = 32;
-  while (cols < need) cols *= 2;
-  lay->tmem_cols = cols;
-  *off_cols = 4 * lay->block_floats;
-  *off_groups = (*off_cols + (int)sizeof(TcCol) * lay->Kd[0] + 127) & ~127;
-  *group_bytes = node ? 128 : ((TC_TILE * (dout + 1) * 4 + 127) & ~127);
-  const int total = 1024 + *off_groups + TC_GROUPS * *group_bytes;
-  // at least half of the SM's shared memory, so that two CTAs (and two 512-column TMEM allocations) never share an SM
-  *smem_bytes = std::max(total, 116 * 1024);
-  return total <= kSmemMaxTc;
-}
 
 // host copy of the sign table coef_dst (the device versions live in the kernels header)
 int coef_dst_host(int kind) { return kind == SEG_DST || kind == SEG_SMD || kind == SEG_DMS; }
@@ -601,13 +483,6 @@ using namespace ngpde;
 
 namespace {
 
-struct TcPhase {
-  bool on = false;
-  TcLayout lay{};
-  int smem = 0, off_cols = 0, off_groups = 0, group_bytes = 0;
-  size_t ws_off = 0;  // byte offset of the prepared weight block in the forward workspace
-};
-
 struct FwdPlan {
   TcPhase edge, node;
   size_t ws_bytes = 0;
@@ -637,77 +512,11 @@ FwdPlan fwd_plan(const Plan& p, int aggr) {
   return f;
 }
 
-template <bool NODE>
-int launch_fwd_tc(const ngpde_graph* g, const TcPhase& t, const MlpDev& mlp, const float* params, const FwdArgs& base,
-                  float* wblock, cudaStream_t st) {
-  if (base.tg.n_units <= 0) return NGPDE_OK;
-  tc_prep_weights_kernel<<<32, 256, 0, st>>>(params, mlp, t.lay, wblock);
-  TcFwdArgs a{};
-  a.tg = base.tg;
-  std::memcpy(a.arr, base.arr, sizeof(a.arr));
-  std::memcpy(a.ld, base.ld, sizeof(a.ld));
-  a.n_segs = base.n_segs;
-  std::memcpy(a.segs, base.segs, sizeof(a.segs));
-  a.lay = t.lay;
-  for (int l = 0; l < mlp.L; ++l) a.act[l] = mlp.act[l];
-  a.wblock = wblock;
-  a.aggr = base.aggr;
-  a.dout = base.dout;
-  a.out = base.out;
-  a.off_cols = t.off_cols;
-  a.off_groups = t.off_groups;
-  a.group_bytes = t.group_bytes;
-  NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_fwd_tc_kernel<NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
-  const int grid = std::max(1, std::min((a.tg.n_units + TC_GROUPS - 1) / TC_GROUPS, g->num_sms));
-  mp_fwd_tc_kernel<NODE><<<grid, TC_THREADS, t.smem, st>>>(a);
-  NGPDE_CUDA_TRY(cudaGetLastError());
-  return NGPDE_OK;
-}
-
-template <bool NODE>
-int launch_bwd_tc(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base, float* wblock, cudaStream_t st) {
-  if (base.tg.n_units <= 0) return NGPDE_OK;
-  tc_prep_weights_kernel<<<32, 256, 0, st>>>(base.params, mlp, t.lay, wblock);
-  TcBwdArgs a{};
-  a.tg = base.tg;
-  std::memcpy(a.arr, base.arr, sizeof(a.arr));
-  std::memcpy(a.ld, base.ld, sizeof(a.ld));
-  a.n_segs = base.n_segs;
-  std::memcpy(a.segs, base.segs, sizeof(a.segs));
-  a.lay = t.lay;
-  for (int l = 0; l < mlp.L; ++l) {
-    a.act[l] = mlp.act[l];
-    a.w_off[l] = mlp.w_off[l];
-    a.b_off[l] = mlp.b_off[l];
-  }
-  a.n_params = mlp.n_params;
-  a.wblock = wblock;
-  a.aggr = base.aggr;
-  a.dout = base.dout;
-  a.gout_ptr = base.gout_ptr;
-  a.dparams_partial = base.dparams_partial;
-  a.dx_direct = base.dx_direct;
-  a.dmbar = base.dmbar;
-  a.dxdst = base.dxdst;
-  a.desrc = base.desrc;
-  a.dx = base.dx;
-  a.need_dz0 = base.need_dz0;
-  a.has_dst_side = base.has_dst_side;
-  std::memcpy(a.c_zs, t.c_zs, sizeof(a.c_zs));
-  a.c_a = t.c_a; a.a_width = t.a_width; a.c_d = t.c_d; a.c_dw = t.c_dw; a.c_d0 = t.c_d0; a.c_dw0 = t.c_dw0; a.tmem_cols = t.tmem_cols;
-  a.off_cols = t.off_cols; a.off_stage = t.off_stage; a.off_dz = t.off_dz; a.nzh = t.nzh; a.nzl = t.nzl;
-  a.dbg = NODE ? nullptr : g_tcb_dbg;
-  NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_bwd_tc_kernel<NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
-  mp_bwd_tc_kernel<NODE><<<t.grid, TCB_THREADS, t.smem, st>>>(a);
-  NGPDE_CUDA_TRY(cudaGetLastError());
-  return NGPDE_OK;
-}
-
 }  // namespace
 
 extern "C" int ngpde_set_option(int32_t option, int32_t value) {
   switch (option) {
-    case NGPDE_OPT_TENSOR_CORES: g_use_tc = value != 0; return NGPDE_OK;
+    case NGPDE_OPT_TENSOR_CORES: tc_set_enabled(value != 0); return NGPDE_OK;
     default: set_error("unknown option %d", option); return NGPDE_ERR_INVALID;
   }
 }
@@ -766,7 +575,7 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
     if (fp.edge.on) {
       a.tg.unit_ptr = g->units[2];
       a.tg.n_units = g->n_units[2];
-      if (int rc = launch_fwd_tc<false>(g, fp.edge, p.phi, io->phi_params, a, reinterpret_cast<float*>(fws + fp.edge.ws_off), st))
+      if (int rc = launch_fwd_tc(false, g->num_sms, fp.edge, p.phi, io->phi_params, a, reinterpret_cast<float*>(fws + fp.edge.ws_off), st))
         return rc;
     } else {
       if (int rc = launch_fwd<false>(te, a, smem, g->num_sms, st)) return rc;
@@ -793,7 +602,7 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
     ProfScope prof(NGPDE_PROF_FWD_NODE, st);
     if (fp.node.on) {
       n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
-      if (int rc = launch_fwd_tc<true>(g, fp.node, p.node, io->node_params, n, reinterpret_cast<float*>(fws + fp.node.ws_off), st))
+      if (int rc = launch_fwd_tc(true, g->num_sms, fp.node, p.node, io->node_params, n, reinterpret_cast<float*>(fws + fp.node.ws_off), st))
         return rc;
     } else {
       if (int rc = launch_fwd<true>(te, n, smem, g->num_sms, st)) return rc;
@@ -865,7 +674,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       ProfScope prof(NGPDE_PROF_BWD_NODE, st);
       if (L.tcn.on) {
         n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
-        if (int rc = launch_bwd_tc<true>(L.tcn, p.node, n, reinterpret_cast<float*>(ws + L.tcn.ws_off), st)) return rc;
+        if (int rc = launch_bwd_tc(true, L.tcn, p.node, n, reinterpret_cast<float*>(ws + L.tcn.ws_off), st)) return rc;
       } else {
         if (int rc = launch_bwd<true>(te, n, L.smem_n, L.grid_n, st)) return rc;
       }
@@ -909,7 +718,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       if (L.tce.on) {
         a.tg.unit_ptr = g->units[2];
         a.tg.n_units = g->n_units[2];
-        if (int rc = launch_bwd_tc<false>(L.tce, p.phi, a, reinterpret_cast<float*>(ws + L.tce.ws_off), st)) return rc;
+        if (int rc = launch_bwd_tc(false, L.tce, p.phi, a, reinterpret_cast<float*>(ws + L.tce.ws_off), st)) return rc;
       } else {
         if (int rc = launch_bwd<false>(te, a, L.smem_e, L.grid_e, st)) return rc;
       }
@@ -932,7 +741,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
 }
 
 extern "C" int ngpde_debug_buffer(void* device_int64_x512) {
-  g_tcb_dbg = static_cast<long long*>(device_int64_x512);
+  tc_set_debug_buffer(static_cast<long long*>(device_int64_x512));
   return NGPDE_OK;
 }
 

@@ -79,6 +79,14 @@ struct BwdArgs {
   int offG0, offG1, offW, offH, offDM, offP, offDZ, offDH, offRed;
 };
 
+// sign with which a segment's input gradient flows to the destination / source row
+__device__ __forceinline__ float coef_dst(int kind) {
+  return kind == SEG_DST ? 1.f : (kind == SEG_SMD ? -1.f : (kind == SEG_DMS ? 1.f : 0.f));
+}
+__device__ __forceinline__ float coef_src(int kind) {
+  return kind == SEG_SRC ? 1.f : (kind == SEG_SMD ? 1.f : (kind == SEG_DMS ? -1.f : 0.f));
+}
+
 // bare Dense chains over the node axis (ngpde_conv.cu), used by GCNConv
 int make_mlp_dev(const ngpde_mlp& m, MlpDev* out, const char* what);
 int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, float* y,

@@ -262,12 +262,6 @@ __global__ void __launch_bounds__(NT) mp_fwd_kernel(const FwdArgs a) {
 // backward
 // ------------------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ float coef_dst(int kind) {
-  return kind == SEG_DST ? 1.f : (kind == SEG_SMD ? -1.f : (kind == SEG_DMS ? 1.f : 0.f));
-}
-__device__ __forceinline__ float coef_src(int kind) {
-  return kind == SEG_SRC ? 1.f : (kind == SEG_SMD ? 1.f : (kind == SEG_DMS ? -1.f : 0.f));
-}
 
 template <int TE, bool NODE>
 __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {

@@ -12,32 +12,10 @@
 // epilogue overlaps the other's MMAs.  Operand conventions are pinned by tools/umma_probe.cu.
 #pragma once
 #include "ngpde_conv.cuh"
+#include "ngpde_tc_layout.cuh"
 #include "ngpde_umma.cuh"
 
 namespace ngpde {
-
-constexpr int TC_TILE = 128;    // rows per tile = MMA M
-constexpr int TC_GTHREADS = 256;  // threads per group: 8 warps = 4 TMEM lane quarters x 2 column halves
-constexpr int TC_GROUPS = 2;    // groups per CTA, each with its own tile in flight
-constexpr int TC_MAXN = 64;     // widest layer output the path accepts
-constexpr int TC_THREADS = TC_GTHREADS * TC_GROUPS;
-
-// Shapes of one MLP on the tensor-core path.  Layer l reads A columns [0, Kd) (data, zero padded), a "ones" block at
-// column Kd (1, 0, ..., 0) that multiplies the bias row of the weight image -- so the bias add costs no epilogue
-// instruction -- and writes Np = pad16(N) accumulator columns.
-struct TcLayout {
-  int L;
-  int K[NGPDE_MAX_LAYERS], N[NGPDE_MAX_LAYERS];    // logical layer shapes
-  int Kd[NGPDE_MAX_LAYERS];                        // pad16(K): data columns / rows
-  int Kp[NGPDE_MAX_LAYERS];                        // Kd + 8: rows of the weight image (K extent of the MMAs)
-  int Np[NGPDE_MAX_LAYERS];                        // pad16(N)
-  int img_off[NGPDE_MAX_LAYERS];                   // float offset of the hi image; the lo image follows it
-  int img_floats[NGPDE_MAX_LAYERS];                // floats of one image = ceil(Np/32) * Kp * 32
-  int block_floats;                                // all images
-  int kmax;                                        // widest Kp
-  int cols_group;                                  // TMEM columns per group: TC_MAXN (D) + 2*kmax (A hi, A lo)
-  int tmem_cols;                                   // allocation: power of two >= 32
-};
 
 // how column `c` of the MLP input is produced from the gathered arrays
 struct TcCol {

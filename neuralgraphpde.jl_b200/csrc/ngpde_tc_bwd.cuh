@@ -24,9 +24,6 @@
 
 namespace ngpde {
 
-constexpr int TCB_THREADS = 512;
-constexpr int TCB_MAXL = 4;     // register accumulators for at most 4 layers
-constexpr int TCB_HALF = 64;    // rows per weight-gradient staging pass
 
 struct TcBwdArgs {
   TileGraph tg;
@@ -63,24 +60,33 @@ __device__ __forceinline__ uint32_t stage_off(int r, int c) {
   return umma::sw128b32_offset(c >> 5, TCB_HALF, r, c & 31);
 }
 
-// write 16 consecutive columns [c0, c0+16) of row r into a staged hi image and lo image (c0 % 16 == 0)
+// write 16 consecutive columns [c0, c0+16) of row r into a staged hi image and lo image (c0 % 16 == 0).
+// A quarter warp holds 8 consecutive rows; rows r and r + 4 share the swizzled 32-byte chunk position, so the two 16-byte
+// halves of a chunk are written in opposite order by the rows with bit 2 set: every 128-bit store instruction then
+// covers 8 distinct 16-byte bank groups (conflict-free instead of 2-way conflicted).
 __device__ __forceinline__ void stage_chunk(float* img_hi, float* img_lo, int r, int c0, const float (&f)[16]) {
+  const bool swp = (r & 4) != 0;
 #pragma unroll
   for (int b = 0; b < 2; ++b) {  // two 32-byte blocks
     const uint32_t o = stage_off(r, c0 + 8 * b);
+    const uint32_t o1 = o + (swp ? 4u : 0u), o2 = o + (swp ? 0u : 4u);
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      x[j] = swp ? f[8 * b + 4 + j] : f[8 * b + j];
+      x[4 + j] = swp ? f[8 * b + j] : f[8 * b + 4 + j];
+    }
     float4 h0, h1, l0, l1;
-    h0.x = umma::tf32_hi(f[8 * b + 0]); h0.y = umma::tf32_hi(f[8 * b + 1]);
-    h0.z = umma::tf32_hi(f[8 * b + 2]); h0.w = umma::tf32_hi(f[8 * b + 3]);
-    h1.x = umma::tf32_hi(f[8 * b + 4]); h1.y = umma::tf32_hi(f[8 * b + 5]);
-    h1.z = umma::tf32_hi(f[8 * b + 6]); h1.w = umma::tf32_hi(f[8 * b + 7]);
-    l0.x = umma::tf32_hi(f[8 * b + 0] - h0.x); l0.y = umma::tf32_hi(f[8 * b + 1] - h0.y);
-    l0.z = umma::tf32_hi(f[8 * b + 2] - h0.z); l0.w = umma::tf32_hi(f[8 * b + 3] - h0.w);
-    l1.x = umma::tf32_hi(f[8 * b + 4] - h1.x); l1.y = umma::tf32_hi(f[8 * b + 5] - h1.y);
-    l1.z = umma::tf32_hi(f[8 * b + 6] - h1.z); l1.w = umma::tf32_hi(f[8 * b + 7] - h1.w);
-    *reinterpret_cast<float4*>(img_hi + o) = h0;
-    *reinterpret_cast<float4*>(img_hi + o + 4) = h1;
-    *reinterpret_cast<float4*>(img_lo + o) = l0;
-    *reinterpret_cast<float4*>(img_lo + o + 4) = l1;
+    h0.x = umma::tf32_hi(x[0]); h0.y = umma::tf32_hi(x[1]); h0.z = umma::tf32_hi(x[2]); h0.w = umma::tf32_hi(x[3]);
+    h1.x = umma::tf32_hi(x[4]); h1.y = umma::tf32_hi(x[5]); h1.z = umma::tf32_hi(x[6]); h1.w = umma::tf32_hi(x[7]);
+    l0.x = umma::tf32_hi(x[0] - h0.x); l0.y = umma::tf32_hi(x[1] - h0.y);
+    l0.z = umma::tf32_hi(x[2] - h0.z); l0.w = umma::tf32_hi(x[3] - h0.w);
+    l1.x = umma::tf32_hi(x[4] - h1.x); l1.y = umma::tf32_hi(x[5] - h1.y);
+    l1.z = umma::tf32_hi(x[6] - h1.z); l1.w = umma::tf32_hi(x[7] - h1.w);
+    *reinterpret_cast<float4*>(img_hi + o1) = h0;
+    *reinterpret_cast<float4*>(img_lo + o1) = l0;
+    *reinterpret_cast<float4*>(img_hi + o2) = h1;
+    *reinterpret_cast<float4*>(img_lo + o2) = l1;
   }
 }
 
@@ -171,6 +177,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   float* st_glo = st_ghi + 2 * TCB_HALF * 32;
   float* DZ = reinterpret_cast<float*>(smem + a.off_dz);  // edge phase: [128][Kd0 + 1]
   const int L = lay.L, Kd0 = lay.Kd[0];
+  // edge phase: the gathered layer-0 input is parked in the (not yet used) dZ_0 tile instead of being gathered twice
+  const bool keep_z0 = !NODE && a.need_dz0 && L > 1;
 
   if (tid < 32) umma::tmem_alloc(&tmem_slot, a.tmem_cols);
   if (tid == 0) {
@@ -257,6 +265,11 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       }
       const int pg = p / gdiv;
       TCB_STAMP(0);
+      // the cotangent rows are first needed after the recompute: pull their lines towards L1 now
+      if (valid && c0 < lay.Np[L - 1])
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.gout_ptr + (size_t)(NODE ? (k0 + row) : d) * dout + c0));
+      float degf = 1.f;
+      if (!NODE && aggr == NGPDE_AGGR_MEAN && valid) degf = (float)(a.tg.rowptr[d + 1] - a.tg.rowptr[d]);
 
       // ---- 1. forward recompute: Z_1 .. Z_{L-1} ----
       if (L > 1) {
@@ -265,6 +278,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float v = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+            if (keep_z0) DZ[row * (Kd0 + 1) + cc + j] = v;  // re-read by layer 0's weight-gradient staging
             const float h = umma::tf32_hi(v);
             hi[j] = __float_as_uint(h);
             lo[j] = __float_as_uint(umma::tf32_hi(v - h));
@@ -339,9 +353,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               if (c0 + j < dout) g[j] = gp[j];
           }
           if (!NODE && aggr == NGPDE_AGGR_MEAN) {
-            const float deg = (float)(a.tg.rowptr[d + 1] - a.tg.rowptr[d]);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = __fdiv_rn(g[j], deg);
+            for (int j = 0; j < 16; ++j) g[j] = __fdiv_rn(g[j], degf);
           }
         }
       }
@@ -422,8 +435,13 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             for (int cc = c0; cc < Kd; cc += 64) {
               float z[16];
               if (l == 0) {
+                if (keep_z0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) z[j] = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+                  for (int j = 0; j < 16; ++j) z[j] = DZ[row * (Kd0 + 1) + cc + j];
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) z[j] = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+                }
               } else {
                 uint32_t v[16];
                 umma::tmem_ld16(tmem + a.c_zs[l] + lane_addr + cc, v);
