@@ -2,6 +2,7 @@
 // unit so that the FP32-FFMA engine (ngpde_conv.cu) and these kernels compile independently.
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 #include "ngpde_tc.cuh"
 #include "ngpde_tc_bwd.cuh"
@@ -51,42 +52,47 @@ bool tc_bwd_make_impl(const MlpDev& m, bool contract, bool addend, bool node, in
   if (m.act[L - 1] != NGPDE_ACT_IDENTITY) return false;  // Z_L is not recomputed
   for (int l = 0; l < L; ++l) {
     if (!act_grad_from_y(m.act[l])) return false;         // swish / gelu need the pre-activation
-    if (lay.Kp[l] > 88) return false;                     // register accumulators cover 64 + 24 columns of dW^T
+    if (lay.Kd[l] > 80) return false;                     // register accumulators cover 64 + 16 columns of dW^T
   }
-  // TMEM columns
-  int zs = 0, wdw = 0, kdmax = 0;
+  // TMEM columns: FP32 copies of Z_1..Z_{L-1} | A hi, A lo | D | Dw.  D / Dw double as the two accumulators of a
+  // recomputed layer (two issuing warps), so they are as wide as the widest hidden output as well.
+  int zs = 0, kdmax = 0, awidth = 0, dmax = 0, wmax = 0;
   for (int l = 1; l < L; ++l) {
     t->c_zs[l] = zs;
     zs += lay.Kd[l];
-    wdw = std::max(wdw, lay.Kp[l]);
+    dmax = std::max(dmax, lay.Kd[l]);   // dZ_l
+    wmax = std::max(wmax, lay.Kd[l]);   // dW_l^T has Kd_l columns
   }
-  for (int l = 0; l < L; ++l) kdmax = std::max(kdmax, lay.Kd[l]);
-  // one A image holds a layer input (Kp columns, forward recompute) or a layer-output cotangent (Np columns, backward)
-  t->a_width = lay.kmax;
-  for (int l = 0; l < L; ++l) t->a_width = std::max(t->a_width, lay.Np[l]);
+  for (int l = 0; l < L; ++l) {
+    kdmax = std::max(kdmax, lay.Kd[l]);
+    awidth = std::max(awidth, std::max(lay.Kd[l], lay.Np[l]));
+    if (l < L - 1) {
+      dmax = std::max(dmax, lay.Np[l]);
+      wmax = std::max(wmax, lay.Np[l]);
+    }
+  }
+  const bool alias0 = zs >= 2 * lay.Kd[0];  // layer 0's outputs may overwrite the (dead by then) activation copies
+  if (!alias0) {
+    dmax = std::max(dmax, lay.Kd[0]);
+    wmax = std::max(wmax, lay.Kd[0]);
+  }
+  t->a_width = awidth;
   t->c_a = zs;
-  t->c_d = zs + 2 * t->a_width;
-  t->c_dw = t->c_d + 64;
-  if (zs >= lay.Kd[0] + lay.Kp[0]) {  // layer 0's outputs may overwrite the (dead by then) activation copies
-    t->c_d0 = 0;
-    t->c_dw0 = lay.Kd[0];
-  } else {
-    if (lay.Kd[0] > 64) return false;
-    t->c_d0 = t->c_d;
-    t->c_dw0 = t->c_dw;
-    wdw = std::max(wdw, lay.Kp[0]);
-  }
-  const int total = t->c_dw + wdw;
+  t->c_d = zs + 2 * awidth;
+  t->c_dw = t->c_d + dmax;
+  t->c_d0 = alias0 ? 0 : t->c_d;
+  t->c_dw0 = alias0 ? lay.Kd[0] : t->c_dw;
+  const int total = t->c_dw + wmax;
   if (total > 512) return false;
   int cols = 32;
   while (cols < total) cols *= 2;
   t->tmem_cols = cols;
-  // shared memory
-  t->nzh = (kdmax + 8 + 31) / 32;
-  t->nzl = (kdmax + 31) / 32;
+  // shared memory: weight block | column tables | staging (Z hi, Z lo: nzh groups each; G hi, G lo: 2 groups each) | dZ_0
+  t->nzh = (kdmax + 31) / 32;
+  t->nzl = t->nzh;
   t->off_cols = 4 * lay.block_floats;
   t->off_stage = (t->off_cols + (int)(sizeof(TcCol) + sizeof(TcDst)) * lay.Kd[0] + 1023) & ~1023;
-  t->off_dz = t->off_stage + (t->nzh + t->nzl + 4) * TCB_HALF * 128;
+  t->off_dz = t->off_stage + (2 * t->nzh + 4) * TCB_HALF * 128;
   const int dz_bytes = (!node && need_dz0) ? TC_TILE * (lay.Kd[0] + 1) * 4 : 0;
   const int totalb = 1024 + t->off_dz + dz_bytes;
   if (totalb > kSmemMaxTc) return false;
@@ -175,6 +181,7 @@ int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base,
   a.c_a = t.c_a; a.a_width = t.a_width; a.c_d = t.c_d; a.c_dw = t.c_dw; a.c_d0 = t.c_d0; a.c_dw0 = t.c_dw0; a.tmem_cols = t.tmem_cols;
   a.off_cols = t.off_cols; a.off_stage = t.off_stage; a.off_dz = t.off_dz; a.nzh = t.nzh; a.nzl = t.nzl;
   a.dbg = NODE ? nullptr : g_tcb_dbg;
+  { const char* e = getenv("NGPDE_TCB_OPT"); a.opt = e ? atoi(e) : 0; }
   NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_bwd_tc_kernel<NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
   mp_bwd_tc_kernel<NODE><<<t.grid, TCB_THREADS, t.smem, st>>>(a);
   NGPDE_CUDA_TRY(cudaGetLastError());

@@ -116,6 +116,8 @@ __device__ __forceinline__ float tc_tanh(float x) {
   return fmaf(-2.f, r, 1.f);
 }
 
+__device__ __noinline__ float tc_act_slow(int act, float x) { return act_fwd(act, x); }
+
 // activation of a 16-value chunk with the dispatch hoisted out of the element loop (accurate float32 variants)
 __device__ __forceinline__ void tc_act16(int act, float (&f)[16]) {
   switch (act) {
@@ -138,7 +140,7 @@ __device__ __forceinline__ void tc_act16(int act, float (&f)[16]) {
       break;
     default:
 #pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = act_fwd(act, f[j]);
+      for (int j = 0; j < 16; ++j) f[j] = tc_act_slow(act, f[j]);
       break;
   }
 }
@@ -186,7 +188,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
   __shared__ __align__(8) uint64_t wbar;
   __shared__ uint32_t tmem_slot;
   const TcLayout& lay = a.lay;
-  const int tid = threadIdx.x, grp = tid / TC_GTHREADS, gt = tid % TC_GTHREADS;
+  const int tid = threadIdx.x, grp = umma::uniform_i32(threadIdx.x / TC_GTHREADS), gt = tid % TC_GTHREADS;
+  const int gwarp = umma::uniform_i32((threadIdx.x % TC_GTHREADS) >> 5);  // warp index inside the group
   const int row = gt & 127;  // tile row this thread serves: lane quarter (gt>>5)&3, lane gt&31
   const int half = gt >> 7;  // which 16-column chunks of a layer's output it handles (chunk & 1 == half)
   float* wblk = reinterpret_cast<float*>(smem);
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
   }
   umma::mbar_wait(&wbar, 0);
 
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = umma::uniform_u32(tmem_slot);
   const uint32_t lane_addr = (uint32_t)(((gt >> 5) & 3) * 32) << 16;
   const uint32_t tD = tmem + grp * lay.cols_group, tAhi = tD + TC_MAXN, tAlo = tAhi + lay.kmax;
   const uint32_t wblk_smem = umma::smem_u32(wblk);
@@ -271,10 +274,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
       group_bar(grp);
 
       for (int l = 0; l < L; ++l) {
-        if (gt < 32) {
-          // one elected lane issues the MMAs and waits for their completion; everybody else parks on barriers
-          // (a spinning try_wait loop in 255 threads would steal issue slots from the other group's epilogue)
-          if (gt == 0) {
+        if (gwarp == 0) {
+          // one elected lane issues the MMAs (elect.sync keeps the operands in uniform registers: no R2UR waterfall per
+          // MMA) and waits for their completion; everybody else parks on barriers (a spinning try_wait loop in 255
+          // threads would steal issue slots from the other group's epilogue)
+          if (umma::elect_one_sync()) {
             umma::tc_fence_after();
             tc_issue_layer(lay, l, wblk_smem, tD, tAhi, tAlo);
             umma::mma_commit(&bars[grp]);

@@ -9,8 +9,8 @@
 //        input gradient   dZ_l = G_{l+1} W_l^T     M = 128 rows, A = G (TMEM, hi/lo), B = the FORWARD weight image read
 //                                                  K-major (same shared-memory bytes serve both directions);
 //        weight gradient  dW_l^T = G_{l+1}^T Z_l   M = 64 (output features), K = 64 rows per half tile, both operands
-//                                                  staged in shared memory as MN-major SWIZZLE_128B_BASE32B images; a
-//                                                  "ones" column appended to Z_l makes the same MMA produce db_l;
+//                                                  staged in shared memory as MN-major SWIZZLE_128B_BASE32B images;
+//        bias gradient    db_l = column sums of G_{l+1}: warp butterfly over the 32 rows a warp owns, fixed order;
 //        G_l = dZ_l .* act'(Z_l)                   in registers, from TMEM.
 //      Each tile's dW^T block is read out of TMEM and added to per-thread FP32 register accumulators (so the running sum
 //      is rounded once per tile in FP32, not inside the tensor core), written as this CTA's partial at kernel end and
@@ -52,6 +52,7 @@ struct TcBwdArgs {
   // shared memory byte offsets
   int off_cols, off_stage, off_dz;
   int nzh, nzl;            // 32-column groups of the staged Z hi / lo images
+  int opt;                 // experiment switches (NGPDE_TCB_OPT)
   long long* dbg;          // optional phase timestamps (clock64) of CTA 0, thread 64: [tile][64]; nullptr = off
 };
 
@@ -90,11 +91,24 @@ __device__ __forceinline__ void stage_chunk(float* img_hi, float* img_lo, int r,
   }
 }
 
-// the 8-column block (1, 0, ..., 0) at column c0 of row r (hi image only)
-__device__ __forceinline__ void stage_ones(float* img_hi, int r, int c0) {
-  const uint32_t o = stage_off(r, c0);
-  *reinterpret_cast<float4*>(img_hi + o) = make_float4(1.f, 0.f, 0.f, 0.f);
-  *reinterpret_cast<float4*>(img_hi + o + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+// MMAs [i0, i1) of the 3 * (Kd/8) that make up one recomputed Dense layer (pass = i / nks: lo*hi, hi*lo, hi*hi), into the
+// accumulator tDpart.  Two issuing warps take one half each, into separate accumulators (one thread sustains only one MMA
+// per ~65 cycles, tools/tmem_bench.cu); the bias is added by the epilogue, so no "ones" column is involved.
+__device__ __forceinline__ void tcb_issue_fwd_part(const TcLayout& lay, int l, uint32_t wblk_smem, uint32_t tDpart, uint32_t tAhi,
+                                                   uint32_t tAlo, int i0, int i1) {
+  const uint32_t idesc = umma::make_idesc(TC_TILE, lay.Np[l], /*a_mn=*/0, /*b_mn=*/1);
+  const uint32_t hi = wblk_smem + 4u * lay.img_off[l], lo = hi + 4u * lay.img_floats[l];
+  const uint32_t lbo = 128u * lay.Kp[l];
+  const uint64_t dhi = umma::make_sdesc(hi, lbo, 512, 1), dlo = umma::make_sdesc(lo, lbo, 512, 1);
+  const int nks = lay.Kd[l] / 8;
+  int pass = i0 / nks, ks = i0 - pass * nks;
+#pragma unroll 1
+  for (int i = i0; i < i1; ++i) {
+    const uint32_t ta = (pass == 0 ? tAlo : tAhi) + ks * 8;
+    const uint64_t db = (pass == 1 ? dlo : dhi) + (uint64_t)(ks * 64);
+    umma::mma_tf32_ts(tDpart, ta, db, idesc, i > i0);
+    if (++ks == nks) { ks = 0; ++pass; }
+  }
 }
 
 // dZ_l = G W_l^T: A = G hi/lo in TMEM [128 x Np_l], B = forward weight image of layer l read K-major, N = Kd_l columns.
@@ -117,12 +131,12 @@ __device__ __forceinline__ void tcb_issue_dgrad(const TcLayout& lay, int l, uint
   }
 }
 
-// dW_l^T (+ db_l) += G^T Z over one staged half tile: M = 64, K = TCB_HALF rows, N = Kp_l (Kd_l data columns + ones block);
+// dW_l^T += G^T Z over one staged half tile: M = 64, K = TCB_HALF rows, N = Kd_l;
 // one K-step = 8 staged rows = 1024 bytes = 64 descriptor address units
 __device__ __forceinline__ void tcb_issue_wgrad(const TcLayout& lay, int l, uint32_t ghi, uint32_t glo, uint32_t zhi,
                                                 uint32_t zlo, uint32_t tDw, int accumulate) {
-  const uint32_t id_full = umma::make_idesc(64, lay.Kp[l], 1, 1);
-  const uint32_t id_data = umma::make_idesc(64, lay.Kd[l], 1, 1);
+  const uint32_t id_full = umma::make_idesc(64, lay.Kd[l], 1, 1);
+  const uint32_t id_data = id_full;
   const uint32_t lbo = 128u * TCB_HALF;
   const uint64_t dgh = umma::make_sdesc(ghi, lbo, 512, 1), dgl = umma::make_sdesc(glo, lbo, 512, 1);
   const uint64_t dzh = umma::make_sdesc(zhi, lbo, 512, 1), dzl = umma::make_sdesc(zlo, lbo, 512, 1);
@@ -151,10 +165,48 @@ struct TcDst {
   int ld;
 };
 
+// One lane per warp polls the mbarrier, the others park on __syncwarp: 512 threads spinning on mbarrier.try_wait slow the
+// MMA-issuing lanes down by 2x and more (measured with the phase stamps).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int opt) {
+  if ((opt & 2) || (threadIdx.x & 31) == 0) umma::mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 #define TCB_STAMP(slot)                                                                          \
   do {                                                                                           \
-    if (a.dbg != nullptr && blockIdx.x == 0 && tid == 64 && dbg_tile < 8) a.dbg[dbg_tile * 64 + (slot)] = clock64(); \
+    if (a.dbg != nullptr && blockIdx.x == 0 && tid == TCB_STAMP_TID && dbg_tile < 8) a.dbg[dbg_tile * 64 + (slot)] = clock64(); \
   } while (0)
+#define TCB_STAMP_ANY(slot)                                                                      \
+  do {                                                                                           \
+    if (a.dbg != nullptr && blockIdx.x == 0 && dbg_tile < 8) a.dbg[dbg_tile * 64 + (slot)] = clock64(); \
+  } while (0)
+constexpr int TCB_STAMP_TID = 160;  // warp 5 (rows 32..63, chunk 1): a worker that never issues MMAs
+
+// column sums of a 16-value chunk over the 32 rows of a warp (fixed butterfly order): afterwards every lane holds the
+// total of column  8*bit4 + 4*bit3 + 2*bit2 + bit1  of its lane id (lanes 2i and 2i+1 hold the same column)
+__device__ __forceinline__ float tcb_colsum16(const float (&g)[16], int lane) {
+  float w[8], x[4], y[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float send = b4 ? g[j] : g[8 + j], keep = b4 ? g[8 + j] : g[j];
+    w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = b3 ? w[j] : w[4 + j], keep = b3 ? w[4 + j] : w[j];
+    x[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = b2 ? x[j] : x[2 + j], keep = b2 ? x[2 + j] : x[j];
+    y[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = b1 ? y[0] : y[1], keep = b1 ? y[1] : y[0];
+  float z = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  z += __shfl_xor_sync(0xffffffffu, z, 1);
+  return z;
+}
 
 template <bool NODE>
 __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_constant__ TcBwdArgs a) {
@@ -163,7 +215,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   __shared__ __align__(8) uint64_t bar_d, bar_w, wbar;
   __shared__ uint32_t tmem_slot;
   const TcLayout& lay = a.lay;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = umma::uniform_i32(threadIdx.x >> 5), lane = tid & 31;
   const int lq = warp & 3;   // TMEM lane quarter this warp may touch
   const int q = warp >> 2;   // 16-column chunk served by this warp
   const int row = lq * 32 + lane;
@@ -171,11 +223,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   float* wblk = reinterpret_cast<float*>(smem);
   TcCol* cols = reinterpret_cast<TcCol*>(smem + a.off_cols);
   TcDst* dcols = reinterpret_cast<TcDst*>(cols + lay.Kd[0]);
-  float* st_zhi = reinterpret_cast<float*>(smem + a.off_stage);
-  float* st_zlo = st_zhi + a.nzh * TCB_HALF * 32;
-  float* st_ghi = st_zlo + a.nzl * TCB_HALF * 32;
+  float* st_base = reinterpret_cast<float*>(smem + a.off_stage);  // Z hi | Z lo | G hi | G lo, each nz (2 for G) groups
+  float* st_ghi = st_base + 2 * a.nzh * TCB_HALF * 32;
   float* st_glo = st_ghi + 2 * TCB_HALF * 32;
-  float* DZ = reinterpret_cast<float*>(smem + a.off_dz);  // edge phase: [128][Kd0 + 1]
+  float* DZ = reinterpret_cast<float*>(smem + a.off_dz);  // edge phase: [128][Kd0 + 1]; later reused for the db exchange
   const int L = lay.L, Kd0 = lay.Kd[0];
   // edge phase: the gathered layer-0 input is parked in the (not yet used) dZ_0 tile instead of being gathered twice
   const bool keep_z0 = !NODE && a.need_dz0 && L > 1;
@@ -212,22 +263,24 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   }
   umma::mbar_wait(&wbar, 0);
 
-  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem = umma::uniform_u32(tmem_slot);
   const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
   const uint32_t tAhi = tmem + a.c_a, tAlo = tAhi + a.a_width, tD = tmem + a.c_d, tDw = tmem + a.c_dw;
   const uint32_t wblk_smem = umma::smem_u32(wblk);
-  const uint32_t s_zhi = umma::smem_u32(st_zhi), s_zlo = umma::smem_u32(st_zlo), s_ghi = umma::smem_u32(st_ghi),
-                 s_glo = umma::smem_u32(st_glo);
+  const uint32_t s_ghi = umma::smem_u32(st_ghi), s_glo = umma::smem_u32(st_glo);
   uint32_t ph_d = 0, ph_w = 0;
   const int gdiv = a.tg.gdiv, aggr = a.aggr, dout = a.dout;
 
   // register accumulators of dW^T: per layer 8 values of the 16-column chunk (k = c0 + 8*(lane>=16) + j, n = 16*lq +
-  // lane%16) plus up to 3 values of the columns beyond 64 (k = 64 + 8*t + 2*q + (lane>=16))
-  float dwacc[TCB_MAXL][11];
+  // lane%16) plus up to 2 values of the columns beyond 64 (k = 64 + 8*t + 2*q + (lane>=16)), and one bias-gradient value
+  float dwacc[TCB_MAXL][10];
+  float dbacc[TCB_MAXL];
 #pragma unroll
-  for (int l = 0; l < TCB_MAXL; ++l)
+  for (int l = 0; l < TCB_MAXL; ++l) {
+    dbacc[l] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 11; ++j) dwacc[l][j] = 0.f;
+    for (int j = 0; j < 10; ++j) dwacc[l][j] = 0.f;
+  }
   const bool upper = lane >= 16;
   int dbg_tile = 0;
 
@@ -271,7 +324,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       float degf = 1.f;
       if (!NODE && aggr == NGPDE_AGGR_MEAN && valid) degf = (float)(a.tg.rowptr[d + 1] - a.tg.rowptr[d]);
 
-      // ---- 1. forward recompute: Z_1 .. Z_{L-1} ----
+      // ---- 1. forward recompute: Z_1 .. Z_{L-1} (two issuing warps, accumulators tD and tDw, bias added here) ----
       if (L > 1) {
         for (int cc = c0; cc < Kd0; cc += 64) {
           uint32_t hi[16], lo[16];
@@ -286,31 +339,51 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           umma::tmem_st16(tAhi + lane_addr + cc, hi);
           umma::tmem_st16(tAlo + lane_addr + cc, lo);
         }
-        if (q == 0) tc_store_ones(tAhi + lane_addr, tAlo + lane_addr, Kd0);
         umma::tmem_wait_st();
         umma::tc_fence_before();
         __syncthreads();
+#pragma unroll 1
         for (int l = 0; l < L - 1; ++l) {
-          if (tid == 0) {
-            umma::tc_fence_after();
-            tc_issue_layer(lay, l, wblk_smem, tD, tAhi, tAlo);
-            umma::mma_commit(&bar_d);
-            umma::mbar_wait(&bar_d, ph_d);
+          const int nmma = 3 * (lay.Kd[l] / 8), isplit = (nmma + 1) / 2;
+          // the other 31 lanes of an issuing warp park on __syncwarp: lanes spinning on an mbarrier would keep the
+          // issuing lane from being scheduled for > 1000 cycles (measured)
+          if (warp == 0) {
+            if (umma::elect_one_sync()) {
+              umma::tc_fence_after();
+              tcb_issue_fwd_part(lay, l, wblk_smem, tD, tAhi, tAlo, 0, isplit);
+              umma::mma_commit(&bar_d);
+            }
+            __syncwarp();
+          } else if (warp == 1) {
+            if (umma::elect_one_sync()) {
+              umma::tc_fence_after();
+              tcb_issue_fwd_part(lay, l, wblk_smem, tDw, tAhi, tAlo, isplit, nmma);
+              umma::mma_commit(&bar_w);
+            }
+            __syncwarp();
           }
+          mbar_wait_warp(&bar_d, ph_d, a.opt);
+          mbar_wait_warp(&bar_w, ph_w, a.opt);
           ph_d ^= 1;
-          if (l == 1) TCB_STAMP(34);
-          __syncthreads();
-          if (l == 1) TCB_STAMP(35);
+          ph_w ^= 1;
           umma::tc_fence_after();
           const int Np = lay.Np[l];
           if (c0 < Np) {
-            uint32_t v[16];
+            uint32_t v[16], w[16];
             umma::tmem_ld16(tD + lane_addr + c0, v);
-            umma::tmem_wait_ld();
-            if (l == 1) TCB_STAMP(36);
+            umma::tmem_ld16(tDw + lane_addr + c0, w);
+            // bias row of the weight image (row Kd, unswizzled because Kd % 4 == 0): hi + lo
+            const float* bh = wblk + lay.img_off[l] + (c0 >> 5) * lay.Kp[l] * 32 + lay.Kd[l] * 32 + (c0 & 31);
+            const float* bl = bh + lay.img_floats[l];
             float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 16; j += 4) {
+              const float4 h4 = *reinterpret_cast<const float4*>(bh + j), l4 = *reinterpret_cast<const float4*>(bl + j);
+              f[j] = h4.x + l4.x; f[j + 1] = h4.y + l4.y; f[j + 2] = h4.z + l4.z; f[j + 3] = h4.w + l4.w;
+            }
+            umma::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
             tc_act16(a.act[l], f);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(f[j]);
@@ -322,13 +395,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               umma::tmem_st16(tAlo + lane_addr + c0, lo);
             }
           }
-          if (l < L - 2 && q == 0) tc_store_ones(tAhi + lane_addr, tAlo + lane_addr, Np);
-          if (l == 1) TCB_STAMP(37);
           umma::tmem_wait_st();
-          if (l == 1) TCB_STAMP(38);
           umma::tc_fence_before();
           __syncthreads();
-          if (l == 1) TCB_STAMP(39);
         }
       }
 
@@ -360,16 +429,16 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       }
 
       TCB_STAMP(2);
-      // ---- 3. back through the layers.  Per layer: G -> TMEM A operand and rows 0..63 staged; warp 1 issues the
-      // weight-gradient MMAs of that half, warp 0 the input-gradient MMAs; rows 64..127 are staged as soon as the first
-      // half has been consumed; second weight-gradient batch; the next G is formed from dZ while that batch still runs
-      // and the dW^T block is collected at the top of the following layer.  (The layer loop is deliberately NOT unrolled:
-      // the unrolled kernel was 250 KB of SASS and spent its time in instruction-cache misses.)
+      // ---- 3. back through the layers.  Per layer: G -> TMEM A operand, then warp 2 (idle while rows 0..63 are staged)
+      // issues the input-gradient MMAs; rows 0..63 of G and Z are staged and warp 3 issues their weight-gradient MMAs;
+      // rows 64..127 are staged as soon as that batch has drained the buffer, warp 1 issues the second batch; the next G
+      // is formed from dZ while it runs and the dW^T block is collected at the top of the following layer.  (The layer
+      // loop is deliberately NOT unrolled: the unrolled kernel spent its time in instruction-cache misses.)
       auto collect_dw = [&](int l, uint32_t tDwl) {
-        float add[11];
+        float add[10];
 #pragma unroll
-        for (int j = 0; j < 11; ++j) add[j] = 0.f;
-        if (c0 < min(lay.Kp[l], 64)) {
+        for (int j = 0; j < 10; ++j) add[j] = 0.f;
+        if (c0 < min(lay.Kd[l], 64)) {
           uint32_t v[16];
           umma::tmem_ld16(tDwl + lane_addr + c0, v);
           umma::tmem_wait_ld();
@@ -380,8 +449,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           }
         }
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          if (64 + 8 * t < lay.Kp[l]) {
+        for (int t = 0; t < 2; ++t) {
+          if (64 + 8 * t < lay.Kd[l]) {
             uint32_t w8[8];
             umma::tmem_ld8(tDwl + lane_addr + 64 + 8 * t, w8);
             umma::tmem_wait_ld();
@@ -396,7 +465,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         for (int ll = 0; ll < TCB_MAXL; ++ll) {
           if (ll == l) {
 #pragma unroll
-            for (int j = 0; j < 11; ++j) dwacc[ll][j] += add[j];
+            for (int j = 0; j < 10; ++j) dwacc[ll][j] += add[j];
           }
         }
       };
@@ -407,26 +476,49 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         const bool do_dgrad = l > 0 || a.need_dz0;
         const uint32_t tDl = (l == 0) ? tmem + a.c_d0 : tD;
         const uint32_t tDwl = (l == 0) ? tmem + a.c_dw0 : tDw;
+        const int gz = (Kd + 31) >> 5;  // 32-column groups of this layer's staged Z images
+        float* st_zhi = st_base;
+        float* st_zlo = st_base + gz * TCB_HALF * 32;
         // the previous layer's dW^T block (its second MMA batch also frees the staging buffer)
         if (l < L - 1) {
-          umma::mbar_wait(&bar_w, ph_w);
+          mbar_wait_warp(&bar_w, ph_w, a.opt);
           ph_w ^= 1;
           umma::tc_fence_after();
           collect_dw(l + 1, tDw);
         }
         TCB_STAMP(3 + 6 * l);
-        if (do_dgrad && active) {
-          uint32_t hi[16], lo[16];
-          tc_split16(g, hi, lo);
-          umma::tmem_st16(tAhi + lane_addr + c0, hi);
-          umma::tmem_st16(tAlo + lane_addr + c0, lo);
+        if (active) {
+          if (do_dgrad) {
+            uint32_t hi[16], lo[16];
+            tc_split16(g, hi, lo);
+            umma::tmem_st16(tAhi + lane_addr + c0, hi);
+            umma::tmem_st16(tAlo + lane_addr + c0, lo);
+          }
+          // bias gradient: column sums over this warp's 32 rows
+          const float cs = tcb_colsum16(g, lane);
+#pragma unroll
+          for (int ll = 0; ll < TCB_MAXL; ++ll)
+            if (ll == l) dbacc[ll] += cs;
+        }
+        const bool early = (a.opt & 1) == 0;
+        if (do_dgrad && early) {
+          umma::tmem_wait_st();
+          umma::tc_fence_before();
+          __syncthreads();
+          if (warp == 2) {
+            if (umma::elect_one_sync()) {
+              umma::tc_fence_after();
+              tcb_issue_dgrad(lay, l, wblk_smem, tDl, tAhi, tAlo);
+              umma::mma_commit(&bar_d);
+            }
+            __syncwarp();
+          }
         }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           if (h == 1) {
-            umma::mbar_wait(&bar_w, ph_w);  // the first half has been consumed
+            mbar_wait_warp(&bar_w, ph_w, a.opt);  // the first half has been consumed
             ph_w ^= 1;
-            TCB_STAMP(5 + 6 * l);
           }
           if ((lq >> 1) == h) {
             const int r = row - TCB_HALF * h;
@@ -451,25 +543,30 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               }
               stage_chunk(st_zhi, st_zlo, r, cc, z);
             }
-            if (q == 0) stage_ones(st_zhi, r, Kd);
           }
           umma::fence_async_smem();
-          umma::tmem_wait_st();
+          if (!early) umma::tmem_wait_st();
           umma::tc_fence_before();
           __syncthreads();
-          TCB_STAMP(4 + 2 * h + 6 * l);
-          if (tid == 32) {
-            umma::tc_fence_after();
-            tcb_issue_wgrad(lay, l, s_ghi, s_glo, s_zhi, s_zlo, tDwl, h);
-            umma::mma_commit(&bar_w);
-          } else if (tid == 0 && h == 0 && do_dgrad) {
-            umma::tc_fence_after();
-            tcb_issue_dgrad(lay, l, wblk_smem, tDl, tAhi, tAlo);
-            umma::mma_commit(&bar_d);
+          if (!early && do_dgrad && h == 0 && warp == 2) {
+            if (umma::elect_one_sync()) {
+              umma::tc_fence_after();
+              tcb_issue_dgrad(lay, l, wblk_smem, tDl, tAhi, tAlo);
+              umma::mma_commit(&bar_d);
+            }
+            __syncwarp();
+          }
+          if (warp == (h == 0 ? 3 : 1)) {
+            if (umma::elect_one_sync()) {
+              umma::tc_fence_after();
+              tcb_issue_wgrad(lay, l, s_ghi, s_glo, umma::smem_u32(st_zhi), umma::smem_u32(st_zlo), tDwl, h);
+              umma::mma_commit(&bar_w);
+            }
+            __syncwarp();
           }
         }
         if (do_dgrad) {
-          umma::mbar_wait(&bar_d, ph_d);
+          mbar_wait_warp(&bar_d, ph_d, a.opt);
           ph_d ^= 1;
         }
         TCB_STAMP(7 + 6 * l);
@@ -526,13 +623,12 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             }
           }
           // layer 0's dW^T block closes the tile
-          umma::mbar_wait(&bar_w, ph_w);
+          mbar_wait_warp(&bar_w, ph_w, a.opt);
           ph_w ^= 1;
           umma::tc_fence_after();
           collect_dw(0, tDwl);
         }
         umma::tc_fence_before();
-        TCB_STAMP(8 + 6 * l);
       }
 
       if (!NODE && a.need_dz0) {
@@ -584,16 +680,32 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 #pragma unroll
     for (int l = 0; l < TCB_MAXL; ++l) {
       if (l >= L) continue;
-      const int K = lay.K[l], N = lay.N[l], Kd = lay.Kd[l];
+      const int K = lay.K[l], N = lay.N[l];
       if (n >= N) continue;
       auto put = [&](int k, float v) {
         if (k < K) dWp[a.w_off[l] + (size_t)k * N + n] = v;
-        else if (k == Kd && a.b_off[l] >= 0) dWp[a.b_off[l] + n] = v;
       };
 #pragma unroll
       for (int j = 0; j < 8; ++j) put(c0 + (upper ? 8 : 0) + j, dwacc[l][j]);
 #pragma unroll
-      for (int t = 0; t < 3; ++t) put(64 + 8 * t + 2 * q + (upper ? 1 : 0), dwacc[l][8 + t]);
+      for (int t = 0; t < 2; ++t) put(64 + 8 * t + 2 * q + (upper ? 1 : 0), dwacc[l][8 + t]);
+    }
+    // bias gradients: the four row quarters of a column are summed in fixed order through shared memory
+    float* dbx = reinterpret_cast<float*>(smem + a.off_stage);  // [L][4 quarters][64 columns]; the staging buffer is free now
+    __syncthreads();
+    if ((lane & 1) == 0) {
+      const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+#pragma unroll
+      for (int l = 0; l < TCB_MAXL; ++l)
+        if (l < L) dbx[(l * 4 + lq) * 64 + col] = dbacc[l];
+    }
+    __syncthreads();
+    for (int item = tid; item < L * 64; item += TCB_THREADS) {
+      const int l = item >> 6, col = item & 63;
+      if (col < lay.N[l] && a.b_off[l] >= 0) {
+        const float* pq = dbx + l * 256 + col;
+        dWp[a.b_off[l] + col] = ((pq[0] + pq[64]) + pq[128]) + pq[192];
+      }
     }
   }
   umma::tc_fence_before();

@@ -101,6 +101,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// ---- warp-uniform helpers ----
+// tcgen05.mma takes its operands from UNIFORM registers.  Issued under a divergent `if (lane == 0)` the compiler wraps every
+// MMA in an ELECT / R2UR.BROADCAST x6 / BRA.U.ANY "waterfall" (~65 cycles per MMA, measured); issued under elect.sync with
+// operands the compiler can prove warp-uniform it is a plain back-to-back UTCHMMA stream.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// tells the compiler that `x` is the same in every lane of the (converged) warp
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }
+__device__ __forceinline__ int uniform_i32(int x) { return __shfl_sync(0xffffffffu, x, 0); }
+
 // ---- MMA issue (one thread) ----
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, int accumulate) {
   asm volatile(

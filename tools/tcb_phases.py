@@ -31,6 +31,11 @@ for tile in (3,):
         prev = v
 
 t3 = t[3]
-print("recompute layer 1: reach barrier (tid64 idle until tid0's wait returns)", int(t3[34] - t3[0]), "| sync", int(t3[35] - t3[34]), "| ld D + wait", int(t3[36] - t3[35]),
-      "| act+split+st issue", int(t3[37] - t3[36]), "| wait::st", int(t3[38] - t3[37]), "| fence+sync", int(t3[39] - t3[38]))
-print("F (l=2): ld issue", int(t3[32] - t3[3 + 6 * 2 + 4]), "| wait::ld", int(t3[33] - t3[32]), "| compute+fence", int(t3[3 + 6 * 2 + 5] - t3[33]))
+base = int(t3[0])
+for l in (3, 2, 1, 0):
+    b = 32 + 6 * l
+    f = lambda i: int(t3[i]) - base
+    print(f"L{l}: layer top {f(3 + 6 * l)} | dgrad issue {f(b)}..{f(b + 1)} | S2 {f(4 + 6 * l)} | wgrad0 issue {f(b + 2)}..{f(b + 3)} | wgrad0 done(seen) {f(5 + 6 * l)} | "
+          f"S3 {f(6 + 6 * l)} | wgrad1 issue {f(b + 4)}..{f(b + 5)} | dgrad done(seen) {f(7 + 6 * l)} | next G done {f(8 + 6 * l)} | dgrad done (issuer polls) {f(56 + l)}")
+
+print("last layer: S3", int(t3[6]) - base, "| before bar_d wait", int(t3[60]) - base, "| lane 0 after wait", int(t3[61]) - base, "| after syncwarp", int(t3[7]) - base)

@@ -141,6 +141,15 @@ __global__ void __launch_bounds__(512) mma_kernel(int kind, int n, int nmma, int
             for (int i = 0; i < 8; ++i) mma_tf32_ts(tmem, tmem + 256 + i * 8, db + (uint64_t)(i * 64), idesc, (i0 | i) > 0);
           }
         }
+      } else if (kind == 6) {  // dgrad-style: B read K-major from the MN-major image (SBO = 512, LBO = 0), N = n rows
+        const uint32_t idesc = make_idesc(128, n, 0, 0);
+        const uint64_t db = make_sdesc(sb, 0, 512, 1);
+        const uint32_t g16 = 8u * 72;
+        for (int i0 = 0; i0 < nmma; i0 += 8) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            mma_tf32_ts(tmem, tmem + 256 + i * 8, db + (uint64_t)((i >> 2) * g16 + (i & 3) * 2u), idesc, (i0 | i) > 0);
+        }
       } else if (kind == 5) {
         const uint32_t idesc = make_idesc(128, n, 0, 1);
         const uint64_t db = make_sdesc(sb, 128u * 72, 512, 1);
@@ -226,6 +235,8 @@ int main() {
                         {4, 32, 24, "TS M=128 N=32 unrolled, 24 MMAs"}, {4, 16, 24, "TS M=128 N=16 unrolled, 24 MMAs"},
                         {4, 96, 24, "TS M=128 N=96 unrolled, 24 MMAs"},
                         {3, 64, 24, "TS M=128 N=64 two accumulators, 24 MMAs"},
+                        {6, 64, 24, "TS M=128 N=64 B K-major (dgrad), 24 MMAs"},
+                        {6, 16, 24, "TS M=128 N=16 B K-major (dgrad L0), 24 MMAs"},
                         {5, 64, 24, "TS M=128 N=64 two issuing warps, 24 MMAs each"}};
   for (const Case& c : cases) {
     for (int ldw : {0, 12}) {
