@@ -82,8 +82,12 @@ bool tc_bwd_make_impl(const MlpDev& m, bool contract, bool addend, bool node, in
   t->c_dw = t->c_d + dmax;
   t->c_d0 = alias0 ? 0 : t->c_d;
   t->c_dw0 = alias0 ? lay.Kd[0] : t->c_dw;
-  const int total = t->c_dw + wmax;
+  int total = t->c_dw + wmax;
   if (total > 512) return false;
+  if (total + wmax <= 512 && L > 1) {  // room for a second dW^T accumulator: collection moves off the critical path
+    t->dw_alt = wmax;
+    total += wmax;
+  }
   int cols = 32;
   while (cols < total) cols *= 2;
   t->tmem_cols = cols;
@@ -178,7 +182,7 @@ int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base,
   a.need_dz0 = base.need_dz0;
   a.has_dst_side = base.has_dst_side;
   std::memcpy(a.c_zs, t.c_zs, sizeof(a.c_zs));
-  a.c_a = t.c_a; a.a_width = t.a_width; a.c_d = t.c_d; a.c_dw = t.c_dw; a.c_d0 = t.c_d0; a.c_dw0 = t.c_dw0; a.tmem_cols = t.tmem_cols;
+  a.c_a = t.c_a; a.a_width = t.a_width; a.c_d = t.c_d; a.c_dw = t.c_dw; a.c_d0 = t.c_d0; a.c_dw0 = t.c_dw0; a.tmem_cols = t.tmem_cols; a.dw_alt = t.dw_alt;
   a.off_cols = t.off_cols; a.off_stage = t.off_stage; a.off_dz = t.off_dz; a.nzh = t.nzh; a.nzl = t.nzl;
   a.dbg = NODE ? nullptr : g_tcb_dbg;
   { const char* e = getenv("NGPDE_TCB_OPT"); a.opt = e ? atoi(e) : 0; }

@@ -150,7 +150,7 @@ __device__ __forceinline__ void tc_split16(const float (&f)[16], uint32_t (&hi)[
   for (int j = 0; j < 16; ++j) {
     const float h = umma::tf32_hi(f[j]);
     hi[j] = __float_as_uint(h);
-    lo[j] = __float_as_uint(umma::tf32_hi(f[j] - h));
+    lo[j] = __float_as_uint(umma::tf32_lo(f[j], h));
   }
 }
 
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
           const float v = valid ? tc_gather_col(cols[c0 + j], s, d, p, pg) : 0.f;
           const float h = umma::tf32_hi(v);
           hi[j] = __float_as_uint(h);
-          lo[j] = __float_as_uint(umma::tf32_hi(v - h));
+          lo[j] = __float_as_uint(umma::tf32_lo(v, h));
         }
         umma::tmem_st8(tAhi + lane_addr + c0, hi);
         umma::tmem_st8(tAlo + lane_addr + c0, lo);

@@ -49,6 +49,7 @@ struct TcBwdArgs {
   // TMEM columns
   int c_zs[NGPDE_MAX_LAYERS];  // FP32 copy of Z_l (l >= 1)
   int c_a, a_width, c_d, c_dw, c_d0, c_dw0, tmem_cols;  // a_width: columns of one A image (hi or lo)
+  int dw_alt;              // > 0: layers alternate between the accumulators c_dw and c_dw + dw_alt (deferred collection)
   // shared memory byte offsets
   int off_cols, off_stage, off_dz;
   int nzh, nzl;            // 32-column groups of the staged Z hi / lo images
@@ -80,10 +81,10 @@ __device__ __forceinline__ void stage_chunk(float* img_hi, float* img_lo, int r,
     float4 h0, h1, l0, l1;
     h0.x = umma::tf32_hi(x[0]); h0.y = umma::tf32_hi(x[1]); h0.z = umma::tf32_hi(x[2]); h0.w = umma::tf32_hi(x[3]);
     h1.x = umma::tf32_hi(x[4]); h1.y = umma::tf32_hi(x[5]); h1.z = umma::tf32_hi(x[6]); h1.w = umma::tf32_hi(x[7]);
-    l0.x = umma::tf32_hi(x[0] - h0.x); l0.y = umma::tf32_hi(x[1] - h0.y);
-    l0.z = umma::tf32_hi(x[2] - h0.z); l0.w = umma::tf32_hi(x[3] - h0.w);
-    l1.x = umma::tf32_hi(x[4] - h1.x); l1.y = umma::tf32_hi(x[5] - h1.y);
-    l1.z = umma::tf32_hi(x[6] - h1.z); l1.w = umma::tf32_hi(x[7] - h1.w);
+    l0.x = umma::tf32_lo(x[0], h0.x); l0.y = umma::tf32_lo(x[1], h0.y);
+    l0.z = umma::tf32_lo(x[2], h0.z); l0.w = umma::tf32_lo(x[3], h0.w);
+    l1.x = umma::tf32_lo(x[4], h1.x); l1.y = umma::tf32_lo(x[5], h1.y);
+    l1.z = umma::tf32_lo(x[6], h1.z); l1.w = umma::tf32_lo(x[7], h1.w);
     *reinterpret_cast<float4*>(img_hi + o1) = h0;
     *reinterpret_cast<float4*>(img_lo + o1) = l0;
     *reinterpret_cast<float4*>(img_hi + o2) = h1;
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             if (keep_z0) DZ[row * (Kd0 + 1) + cc + j] = v;  // re-read by layer 0's weight-gradient staging
             const float h = umma::tf32_hi(v);
             hi[j] = __float_as_uint(h);
-            lo[j] = __float_as_uint(umma::tf32_hi(v - h));
+            lo[j] = __float_as_uint(umma::tf32_lo(v, h));
           }
           umma::tmem_st16(tAhi + lane_addr + cc, hi);
           umma::tmem_st16(tAlo + lane_addr + cc, lo);
@@ -475,7 +476,11 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         const bool active = c0 < Np;
         const bool do_dgrad = l > 0 || a.need_dz0;
         const uint32_t tDl = (l == 0) ? tmem + a.c_d0 : tD;
-        const uint32_t tDwl = (l == 0) ? tmem + a.c_dw0 : tDw;
+        // with two dW^T accumulators (dw_alt) layer l + 1's block is collected while layer l is being staged, by the
+        // warps that are idle in that half; with one it has to be collected before this layer's first MMA batch
+        const bool defer = a.dw_alt > 0;
+        const uint32_t tDwl = (l == 0) ? tmem + a.c_dw0 : tDw + ((l & 1) ? a.dw_alt : 0);
+        const uint32_t tDwp = tDw + (((l + 1) & 1) ? a.dw_alt : 0);  // layer l + 1's accumulator (l + 1 >= 1)
         const int gz = (Kd + 31) >> 5;  // 32-column groups of this layer's staged Z images
         float* st_zhi = st_base;
         float* st_zlo = st_base + gz * TCB_HALF * 32;
@@ -484,7 +489,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           mbar_wait_warp(&bar_w, ph_w, a.opt);
           ph_w ^= 1;
           umma::tc_fence_after();
-          collect_dw(l + 1, tDw);
+          if (!defer) collect_dw(l + 1, tDwp);
         }
         TCB_STAMP(3 + 6 * l);
         if (active) {
@@ -494,11 +499,6 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             umma::tmem_st16(tAhi + lane_addr + c0, hi);
             umma::tmem_st16(tAlo + lane_addr + c0, lo);
           }
-          // bias gradient: column sums over this warp's 32 rows
-          const float cs = tcb_colsum16(g, lane);
-#pragma unroll
-          for (int ll = 0; ll < TCB_MAXL; ++ll)
-            if (ll == l) dbacc[ll] += cs;
         }
         const bool early = (a.opt & 1) == 0;
         if (do_dgrad && early) {
@@ -520,7 +520,16 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             mbar_wait_warp(&bar_w, ph_w, a.opt);  // the first half has been consumed
             ph_w ^= 1;
           }
-          if ((lq >> 1) == h) {
+          if ((lq >> 1) != h) {
+            // idle in this half: bias gradient (column sums of G over this warp's 32 rows) and the deferred dW^T block
+            if (active) {
+              const float cs = tcb_colsum16(g, lane);
+#pragma unroll
+              for (int ll = 0; ll < TCB_MAXL; ++ll)
+                if (ll == l) dbacc[ll] += cs;
+            }
+            if (defer && l < L - 1) collect_dw(l + 1, tDwp);
+          } else {
             const int r = row - TCB_HALF * h;
             if (active) stage_chunk(st_ghi, st_glo, r, c0, g);
             // Z_l: the gathered input for l == 0, else the FP32 copy kept in TMEM by the recompute

@@ -39,7 +39,7 @@ struct TcBwdPhase {
   TcLayout lay{};
   int smem = 0;
   int c_zs[NGPDE_MAX_LAYERS] = {0};
-  int c_a = 0, a_width = 0, c_d = 0, c_dw = 0, c_d0 = 0, c_dw0 = 0, tmem_cols = 0;
+  int c_a = 0, a_width = 0, c_d = 0, c_dw = 0, c_d0 = 0, c_dw0 = 0, tmem_cols = 0, dw_alt = 0;
   int off_cols = 0, off_stage = 0, off_dz = 0, nzh = 0, nzl = 0;
   size_t ws_off = 0;
   int grid = 0;

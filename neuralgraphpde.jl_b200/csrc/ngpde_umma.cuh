@@ -32,6 +32,20 @@ __host__ __device__ __forceinline__ float tf32_hi(float x) {
 #endif
 }
 
+// low part of the split.  The tensor core ignores the 13 low mantissa bits of a TF32 operand, so leaving x - hi unrounded
+// truncates lo instead of rounding it: an error of at most 2^-11 |lo| <= 2^-22 |x|, the size of the dropped lo*lo term,
+// for two integer instructions less per element in every epilogue (set to 1 to round).
+#ifndef NGPDE_TF32_ROUND_LO
+#define NGPDE_TF32_ROUND_LO 0
+#endif
+__host__ __device__ __forceinline__ float tf32_lo(float x, float hi) {
+#if NGPDE_TF32_ROUND_LO
+  return tf32_hi(x - hi);
+#else
+  return x - hi;
+#endif
+}
+
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int group, int rows, int r, int c) {
   return (uint32_t)(group * rows * 32 + r * 32 + ((((c >> 2) ^ (r & 7))) << 2) + (c & 3));
 }
