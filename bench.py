@@ -289,14 +289,27 @@ def main():
     alg_flops = f_phase * (1.0 if dom.startswith("fwd") else 2.0)
     ach_tflops = alg_flops / (dom_ms * 1e-3) / 1e12
     step_kernel_ms = sum(v[0] for v in prof.values()) / K
+    paths = _lib.kernel_paths(runner.handle, runner.desc)
+    on_tc = paths.get(dom, 0) == 1
+    kname = {"fwd_edge": "mp_fwd{}_kernel<edge>", "fwd_node": "mp_fwd{}_kernel<node>", "bwd_node": "mp_bwd{}_kernel<node>",
+             "bwd_edge": "mp_bwd{}_kernel<edge>"}[dom].format("_tc" if on_tc else "")
+    # the pipe that can hold the 1e-5 tolerance: 3xTF32 on tcgen05 = a third of the TF32 rate = a sixth of the dense BF16
+    # peak; the FP32-FFMA engine: 148 SMs x 128 lanes x 2 flop x 1.965 GHz = 74.4 TFLOP/s
+    pipe_peak = peaks["bf16_tflops"] / 6.0 if on_tc else 74.4
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get(kname)
     roofline = {
-        "kernel": {"fwd_edge": "mp_fwd_kernel<edge>", "fwd_node": "mp_fwd_kernel<node>", "bwd_node": "mp_bwd_kernel<node>",
-                   "bwd_edge": "mp_bwd_kernel<edge>"}[dom],
+        "kernel": kname,
         "bound": "tensor", "achieved": ach_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": ach_tflops / peaks["bf16_tflops"], "traffic": None,
+        "frac": ach_tflops / peaks["bf16_tflops"], "traffic": traffic,
         "peak_source": peaks["source"] + " bf16 cuBLAS burst (MEASURED_PEAKS.json)",
-        "pipe": "fp32 FFMA (fp32-accurate; tolerance 1e-5 excludes plain TF32/BF16)",
-        "pipe_peak_tflops": 74.4, "pipe_frac": ach_tflops / 74.4,
+        "pipe": ("tcgen05 3xTF32 (fp32-accurate split: 3 TF32 MMAs per product; peak = bf16 peak / 6)" if on_tc else
+                 "fp32 FFMA (fp32-accurate; tolerance 1e-5 excludes plain TF32/BF16)"),
+        "pipe_peak_tflops": pipe_peak, "pipe_frac": ach_tflops / pipe_peak,
+        "kernel_paths": {k: {1: "tcgen05", 0: "ffma", -1: "none"}[v] for k, v in paths.items()},
         "avg_launch_ms": dom_ms, "algorithmic_flops_per_launch": alg_flops,
         "share_of_step_kernel_time": (prof[dom][0] / K) / step_kernel_ms if step_kernel_ms else None,
         "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items()},

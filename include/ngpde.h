@@ -230,6 +230,9 @@ int ngpde_profile_enable(int32_t on);
  * clock64() stamps of its phases for its first 16 tiles ([tile][32]); NULL switches it off. */
 int ngpde_debug_buffer(void* device_int64_x512);
 int ngpde_profile_read(double* total_ms, int64_t* launches);
+/* which engine a layer's four fused kernels run on for this graph/descriptor: paths[NGPDE_PROF_*] = 1 for the tcgen05
+ * tensor-core kernels (3xTF32), 0 for the FP32-FFMA engine, -1 when the layer has no such phase. */
+int ngpde_conv_kernel_paths(ngpde_graph_t g, const ngpde_conv_desc* desc, int32_t* paths);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ EXPORTS = [
     "ngpde_mppde_conv_forward", "ngpde_mppde_conv_backward", "ngpde_gno_conv_forward", "ngpde_gno_conv_backward",
     "ngpde_gcn_workspace_bytes", "ngpde_gcn_conv_forward", "ngpde_gcn_conv_backward", "ngpde_axpy_stages",
     "ngpde_profile_enable", "ngpde_profile_read", "ngpde_set_option", "ngpde_rows_gather", "ngpde_rows_put",
-    "ngpde_rows_segment_add", "ngpde_debug_buffer",
+    "ngpde_rows_segment_add", "ngpde_debug_buffer", "ngpde_conv_kernel_paths",
 ]
 
 
@@ -101,6 +101,7 @@ def load() -> C.CDLL:
     lib.ngpde_set_option.argtypes = [i32, i32]
     lib.ngpde_profile_enable.argtypes = [i32]
     lib.ngpde_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.ngpde_conv_kernel_paths.argtypes = [vp, C.POINTER(ConvDesc), C.POINTER(i32)]
     _lib = lib
     return lib
 
@@ -125,6 +126,13 @@ def profile_read() -> dict:
     n = (C.c_int64 * 4)()
     check(load().ngpde_profile_read(ms, n))
     return {k: (ms[i], int(n[i])) for i, k in enumerate(PROF_SLOTS)}
+
+
+def kernel_paths(graph_handle, desc) -> dict:
+    """{slot: 1 (tcgen05 kernels) | 0 (FP32-FFMA engine) | -1 (no such phase)} for a conv descriptor on a graph."""
+    out = (C.c_int32 * 4)()
+    check(load().ngpde_conv_kernel_paths(graph_handle, C.byref(desc), out))
+    return {k: int(out[i]) for i, k in enumerate(PROF_SLOTS)}
 
 
 def check(rc: int) -> None:

@@ -531,6 +531,20 @@ extern "C" size_t ngpde_conv_workspace_bytes(ngpde_graph_t g, const ngpde_conv_d
   return L.total + 256;
 }
 
+extern "C" int ngpde_conv_kernel_paths(ngpde_graph_t g, const ngpde_conv_desc* desc, int32_t* paths) {
+  NGPDE_REQUIRE(g && desc && paths, "null argument");
+  Plan p;
+  if (int rc = make_plan(g, *desc, &p)) return rc;
+  const FwdPlan fp = fwd_plan(p, desc->aggr);
+  BwdLayout L;
+  if (int rc = bwd_layout(g, *desc, p, &L)) return rc;
+  paths[NGPDE_PROF_FWD_EDGE] = fp.edge.on ? 1 : 0;
+  paths[NGPDE_PROF_FWD_NODE] = p.has_node ? (fp.node.on ? 1 : 0) : -1;
+  paths[NGPDE_PROF_BWD_EDGE] = L.tce.on ? 1 : 0;
+  paths[NGPDE_PROF_BWD_NODE] = p.has_node ? (L.tcn.on ? 1 : 0) : -1;
+  return NGPDE_OK;
+}
+
 extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_conv_io* io,
                                   void* workspace, size_t workspace_bytes, void* stream) {
   NGPDE_REQUIRE(g && desc && io, "null argument");

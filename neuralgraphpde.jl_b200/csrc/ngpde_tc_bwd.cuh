@@ -169,7 +169,10 @@ struct TcDst {
 // One lane per warp polls the mbarrier, the others park on __syncwarp: 512 threads spinning on mbarrier.try_wait slow the
 // MMA-issuing lanes down by 2x and more (measured with the phase stamps).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int opt) {
-  if ((opt & 2) || (threadIdx.x & 31) == 0) umma::mbar_wait(bar, parity);
+  if ((threadIdx.x & 31) == 0) {
+    if (opt & 2) umma::mbar_wait(bar, parity);
+    else umma::mbar_spin(bar, parity);  // test_wait poll: try_wait may suspend the lane and wake it ~200 cycles late
+  }
   __syncwarp();
 }
 

@@ -115,6 +115,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// busy poll (test_wait returns at once; try_wait may suspend the thread and wake it late)
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "SPIN_LOOP:\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra SPIN_DONE;\n\t"
+      "bra SPIN_LOOP;\n\t"
+      "SPIN_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // ---- warp-uniform helpers ----
 // tcgen05.mma takes its operands from UNIFORM registers.  Issued under a divergent `if (lane == 0)` the compiler wraps every
 // MMA in an ELECT / R2UR.BROADCAST x6 / BRA.U.ANY "waterfall" (~65 cycles per MMA, measured); issued under elect.sync with

@@ -540,3 +540,21 @@ def test_tensor_core_backward_is_deterministic():
     a = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy)
     b = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy)
     assert all(torch.equal(u, v) for u, v in zip(a, b))
+
+
+def test_kernel_path_query_reports_the_engine_that_runs():
+    """ngpde_conv_kernel_paths: C3 runs all four fused kernels on tcgen05; with the option off, or for GNOConv's bilinear
+    contraction, the FP32-FFMA engine takes over (bench.py labels its roofline line with this)."""
+    from ngpde import engine
+    w = workloads.c3_vmh(DEV, side=16)
+    r = engine.RhsRunner(w.layer, w.x, w.ps, w.st)
+    assert ngpde._lib.kernel_paths(r.handle, r.desc) == dict(fwd_edge=1, fwd_node=1, bwd_node=1, bwd_edge=1)
+    ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, 0)
+    try:
+        assert ngpde._lib.kernel_paths(r.handle, r.desc) == dict(fwd_edge=0, fwd_node=0, bwd_node=0, bwd_edge=0)
+    finally:
+        ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, 1)
+    w4 = workloads.c4_gno(DEV, n_nodes=500)
+    r4 = engine.RhsRunner(w4.layer, w4.x, w4.ps, w4.st)
+    p4 = ngpde._lib.kernel_paths(r4.handle, r4.desc)
+    assert p4["fwd_edge"] == 0 and p4["bwd_edge"] == 0
