@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
     for (int j = 0; j < 10; ++j) dwacc[l][j] = 0.f;
   }
   const bool upper = lane >= 16;
+  const int n_items = NODE ? a.tg.N : a.tg.rowptr[a.tg.N];  // edges in the edge phase
   int dbg_tile = 0;
 
   for (int unit = blockIdx.x; unit < a.tg.n_units; unit += gridDim.x) {
@@ -320,13 +321,23 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           p = a.tg.perm[k0 + row];
         }
       }
+      if (!NODE) {  // the next tile of this CTA: pull its index lines towards L1 while this one is processed
+        const int kn = (k0 + TC_TILE < kend) ? k0 + TC_TILE + row
+                                             : (unit + (int)gridDim.x < a.tg.n_units ? a.tg.rowptr[a.tg.unit_ptr[unit + gridDim.x]] + row : -1);
+        if (kn >= 0 && kn < n_items && (lane & 7) == 0 && q < 3) {
+          const int* ip = q == 0 ? a.tg.src : (q == 1 ? a.tg.dst : a.tg.perm);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(ip + kn));
+        }
+      }
       const int pg = p / gdiv;
       TCB_STAMP(0);
       // the cotangent rows are first needed after the recompute: pull their lines towards L1 now
       if (valid && c0 < lay.Np[L - 1])
         asm volatile("prefetch.global.L1 [%0];" ::"l"(a.gout_ptr + (size_t)(NODE ? (k0 + row) : d) * dout + c0));
-      float degf = 1.f;
-      if (!NODE && aggr == NGPDE_AGGR_MEAN && valid) degf = (float)(a.tg.rowptr[d + 1] - a.tg.rowptr[d]);
+      // mean: the cotangent of a message is dmbar / deg -- formed as dmbar * rn(1 / deg) (one rounding more than the true
+      // division, far inside the gradient tolerance; sixteen IEEE divisions per thread cost ~1,000 cycles per tile)
+      float rdeg = 1.f;
+      if (!NODE && aggr == NGPDE_AGGR_MEAN && valid) rdeg = __frcp_rn((float)(a.tg.rowptr[d + 1] - a.tg.rowptr[d]));
 
       // ---- 1. forward recompute: Z_1 .. Z_{L-1} (two issuing warps, accumulators tD and tDw, bias added here) ----
       if (L > 1) {
@@ -427,7 +438,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           }
           if (!NODE && aggr == NGPDE_AGGR_MEAN) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = __fdiv_rn(g[j], degf);
+            for (int j = 0; j < 16; ++j) g[j] *= rdeg;
           }
         }
       }
