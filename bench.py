@@ -291,8 +291,12 @@ def main():
     step_kernel_ms = sum(v[0] for v in prof.values()) / K
     paths = _lib.kernel_paths(runner.handle, runner.desc)
     on_tc = paths.get(dom, 0) == 1
+    factored = paths.get(dom, 0) == 2
     kname = {"fwd_edge": "mp_fwd{}_kernel<edge>", "fwd_node": "mp_fwd{}_kernel<node>", "bwd_node": "mp_bwd{}_kernel<node>",
              "bwd_edge": "mp_bwd{}_kernel<edge>"}[dom].format("_tc" if on_tc else "")
+    if factored:
+        kname = {"fwd_edge": "gno factored edge phase: mp_fwd_kernel<edge> (S builder) + gno_gemm (mbar = S B)",
+                 "bwd_edge": "gno factored edge phase: gno_gemm (T = DM B') + mp_bwd_kernel<edge> + gno_gemm (dB = S' DM)"}[dom]
     # the pipe that can hold the 1e-5 tolerance: 3xTF32 on tcgen05 = a third of the TF32 rate = a sixth of the dense BF16
     # peak; the FP32-FFMA engine: 148 SMs x 128 lanes x 2 flop x 1.965 GHz = 74.4 TFLOP/s
     pipe_peak = peaks["bf16_tflops"] / 6.0 if on_tc else 74.4
@@ -308,8 +312,15 @@ def main():
         "peak_source": peaks["source"] + " bf16 cuBLAS burst (MEASURED_PEAKS.json)",
         "pipe": ("tcgen05 3xTF32 (fp32-accurate split: 3 TF32 MMAs per product; peak = bf16 peak / 6)" if on_tc else
                  "fp32 FFMA (fp32-accurate; tolerance 1e-5 excludes plain TF32/BF16)"),
+        **({"executed_flops_per_launch": w.notes.get("flops_executed_" + dom),
+            "executed_tflops": w.notes.get("flops_executed_" + dom, 0.0) / (dom_ms * 1e-3) / 1e12,
+            "executed_pipe_frac": w.notes.get("flops_executed_" + dom, 0.0) / (dom_ms * 1e-3) / 1e12 / pipe_peak,
+            "note": "factored GNOConv (csrc/ngpde_gno.cuh): the contraction with phi's affine last layer is done once per "
+                    "destination node on per-node outer-product sums instead of once per edge, so the flops EXECUTED are "
+                    "fewer than SURVEY 8d's algorithmic count; `achieved`/`pipe_frac` use the algorithmic count (and can "
+                    "exceed the pipe), `executed_*` the flops actually issued"} if factored else {}),
         "pipe_peak_tflops": pipe_peak, "pipe_frac": ach_tflops / pipe_peak,
-        "kernel_paths": {k: {1: "tcgen05", 0: "ffma", -1: "none"}[v] for k, v in paths.items()},
+        "kernel_paths": {k: {1: "tcgen05", 0: "ffma", 2: "factored (ffma + fp32 gemm)", -1: "none"}[v] for k, v in paths.items()},
         "avg_launch_ms": dom_ms, "algorithmic_flops_per_launch": alg_flops,
         "share_of_step_kernel_time": (prof[dom][0] / K) / step_kernel_ms if step_kernel_ms else None,
         "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items()},

@@ -133,7 +133,9 @@ int ngpde_version(void);
 const char* ngpde_last_error(void);
 /* Process-wide switches (benchmarks and tests only).  NGPDE_OPT_TENSOR_CORES: 1 (default) runs MLPs whose layers are at
  * most 64 wide on the tcgen05 tensor-core kernels (3xTF32, fp32-accurate); 0 forces the FP32-FFMA kernels everywhere. */
-enum { NGPDE_OPT_TENSOR_CORES = 0 };
+enum { NGPDE_OPT_TENSOR_CORES = 0, NGPDE_OPT_GNO_FACTORED = 1 };
+/* NGPDE_OPT_GNO_FACTORED: 1 (default) evaluates GNOConv whose phi ends in an affine layer, with aggr = + or mean, in
+ * factored form (per-destination outer-product sums + dense GEMMs; csrc/ngpde_gno.cuh); 0 forces the per-edge contraction. */
 int ngpde_set_option(int32_t option, int32_t value);
 
 /* ---- graph handle: replaces GNNGraph's per-call gather/scatter index use and GCNConv's per-call
@@ -231,7 +233,8 @@ int ngpde_profile_enable(int32_t on);
 int ngpde_debug_buffer(void* device_int64_x512);
 int ngpde_profile_read(double* total_ms, int64_t* launches);
 /* which engine a layer's four fused kernels run on for this graph/descriptor: paths[NGPDE_PROF_*] = 1 for the tcgen05
- * tensor-core kernels (3xTF32), 0 for the FP32-FFMA engine, -1 when the layer has no such phase. */
+ * tensor-core kernels (3xTF32), 0 for the FP32-FFMA engine, 2 for the factored GNOConv evaluation (FFMA edge kernel + dense
+ * FP32 GEMMs), -1 when the layer has no such phase. */
 int ngpde_conv_kernel_paths(ngpde_graph_t g, const ngpde_conv_desc* desc, int32_t* paths);
 
 #ifdef __cplusplus

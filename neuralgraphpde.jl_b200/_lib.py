@@ -107,6 +107,7 @@ def load() -> C.CDLL:
 
 
 OPT_TENSOR_CORES = 0
+OPT_GNO_FACTORED = 1
 
 
 def set_option(option: int, value: int) -> None:
@@ -129,7 +130,8 @@ def profile_read() -> dict:
 
 
 def kernel_paths(graph_handle, desc) -> dict:
-    """{slot: 1 (tcgen05 kernels) | 0 (FP32-FFMA engine) | -1 (no such phase)} for a conv descriptor on a graph."""
+    """{slot: 1 (tcgen05 kernels) | 0 (FP32-FFMA engine) | 2 (factored GNOConv: FFMA edge kernel + dense GEMMs) |
+    -1 (no such phase)} for a conv descriptor on a graph."""
     out = (C.c_int32 * 4)()
     check(load().ngpde_conv_kernel_paths(graph_handle, C.byref(desc), out))
     return {k: int(out[i]) for i, k in enumerate(PROF_SLOTS)}

@@ -7,6 +7,7 @@
 
 #include "ngpde_conv_kernels.cuh"
 #include "ngpde_tc_layout.cuh"
+#include "ngpde_gno.cuh"
 
 namespace ngpde {
 namespace {
@@ -17,6 +18,7 @@ struct ProfSlot {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
 };
 bool g_prof_on = false;
+bool g_gno_factored = true;  // NGPDE_OPT_GNO_FACTORED
 ProfSlot g_prof[NGPDE_PROF_SLOTS];
 
 struct ProfScope {
@@ -72,7 +74,8 @@ struct Plan {
   Seg nsegs[8];
   int n_nsegs = 0;
   MlpDev phi{}, node{};
-  int contract = 0;
+  int contract = 0;  // 1: per-edge GNO contraction, 2: factored (ngpde_gno.cuh)
+  int gno_K = 0, gno_Ka = 0;  // factored: width of phi's last hidden layer, +1 with a bias row
   int dm = 0;  // width of the aggregated message
   int dy = 0;  // width of the layer output
   int ds = 0;
@@ -147,6 +150,17 @@ int make_plan(const ngpde_graph* g, const ngpde_conv_desc& d, Plan* p) {
       NGPDE_REQUIRE(p->phi.dims[p->phi.L] == d.gno_in * d.gno_out, "GNOConv: phi must output in*out=%d values, got %d",
                     d.gno_in * d.gno_out, p->phi.dims[p->phi.L]);
       p->contract = 1;
+      {
+        // factored evaluation: affine last layer, linear aggregation, vectorisable widths (else the per-edge engine)
+        const int l = p->phi.L - 1;
+        const bool bias_adjacent = p->phi.b_off[l] < 0 || p->phi.b_off[l] == p->phi.w_off[l] + p->phi.dims[l] * p->phi.dims[l + 1];
+        if (g_gno_factored && p->phi.act[l] == NGPDE_ACT_IDENTITY && (d.aggr == NGPDE_AGGR_SUM || d.aggr == NGPDE_AGGR_MEAN) &&
+            d.gno_in % 8 == 0 && d.gno_out % 4 == 0 && g->E > 0 && bias_adjacent) {
+          p->contract = 2;
+          p->gno_K = p->phi.dims[l];
+          p->gno_Ka = p->gno_K + (p->phi.b_off[l] >= 0 ? 1 : 0);
+        }
+      }
       p->dm = d.gno_out;
       push_seg(p->nsegs, &p->n_nsegs, &nrow, SEG_DST, ARR_X, 0, d.dx);
       NGPDE_REQUIRE(p->node.L == 1 && p->node.dims[1] == d.gno_out, "GNOConv: node must be the 1-layer linear map");
@@ -174,32 +188,33 @@ int make_plan(const ngpde_graph* g, const ngpde_conv_desc& d, Plan* p) {
 }
 
 struct FwdSmem {
-  int offA, offB, offW, offH, floats;
+  int offA, offB, offW, offH, offZt, floats;
 };
 
-FwdSmem fwd_smem(const MlpDev& m, int contract, int gin, int gout, int te) {
+FwdSmem fwd_smem(const MlpDev& m, int contract, int gin, int gout, int te, int Ka = 0) {
   const int ld = te + 4;
   const int npass = (te == 32) ? 128 : 64;
   const int Lp = contract ? m.L - 1 : m.L;
   int rows[2] = {0, 0};
   for (int l = 0; l <= Lp; ++l) rows[l & 1] = std::max(rows[l & 1], m.dims[l]);
-  if (contract) rows[(Lp + 1) & 1] = std::max(rows[(Lp + 1) & 1], gout);
+  if (contract == 1) rows[(Lp + 1) & 1] = std::max(rows[(Lp + 1) & 1], gout);
   FwdSmem s;
   s.offA = 0;
   s.offB = rows[0] * ld;
   s.offH = s.offB + rows[1] * ld;
-  s.offW = s.offH + (contract ? gin * ld : 0);
+  s.offZt = s.offH + (contract == 2 ? te * (gin + 4) : (contract ? gin * ld : 0));
+  s.offW = s.offZt + (contract == 2 ? te * gno_ldz(Ka) : 0);
   s.floats = 3 * te + s.offW + 2 * KC * npass;
   return s;
 }
 
 struct BwdSmem {
   int zoff[NGPDE_MAX_LAYERS + 1];
-  int offG0, offG1, offW, offH, offDM, offP, offDH, offRed, floats;
+  int offG0, offG1, offW, offH, offDM, offP, offDH, offRed, offZt, offTs, floats;
   int store_last;
 };
 
-BwdSmem bwd_smem(const MlpDev& m, int contract, int gin, int gout, int aggr, bool node, bool need_dz0, int te) {
+BwdSmem bwd_smem(const MlpDev& m, int contract, int gin, int gout, int aggr, bool node, bool need_dz0, int te, int Ka = 0) {
   const int ld = te + 4;
   const int npass = (te == 32) ? 128 : 64;
   const int nth = (te == 32) ? 16 : 8;
@@ -228,7 +243,11 @@ BwdSmem bwd_smem(const MlpDev& m, int contract, int gin, int gout, int aggr, boo
   off += rows[0] * ld;
   s.offG1 = off;
   off += rows[1] * ld;
-  if (contract) {
+  if (contract == 2) {
+    s.offH = off;  off += te * (gin + 4);
+    s.offZt = off; off += te * gno_ldz(Ka);
+    s.offTs = off; off += ((Ka + 3) & ~3) * (gin + 4);
+  } else if (contract) {
     s.offH = off;  off += gin * ld;
     s.offDH = off; off += gin * ld;
     s.offDM = off; off += gout * ld;
@@ -340,6 +359,9 @@ struct BwdLayout {
   BwdSmem se, sn;
   TcBwdPhase tce, tcn;  // tensor-core variants of the two phases (when eligible)
   size_t off_wt_phi, off_wt_node, off_dmbar, off_dxdirect, off_dxdst, off_desrc, off_part_phi, off_part_node, total;
+  // factored GNO
+  size_t off_S = 0, off_T = 0, off_DM = 0, off_dBpart = 0;
+  int part_stride = 0, gno_splits = 1;
 };
 
 int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, BwdLayout* L) {
@@ -350,11 +372,11 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
   } else {
     if (int rc = pick_tile(
             [&](int te) {
-              return 4 * bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, te).floats;
+              return 4 * bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, te, p.gno_Ka).floats;
             },
             &L->te_e, &L->smem_e))
       return rc;
-    L->se = bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, L->te_e);
+    L->se = bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, L->te_e, p.gno_Ka);
     if (int rc = bwd_grid<false>(L->te_e, L->smem_e, std::max(1, g->n_units[tile_index(L->te_e)]), g->num_sms, &L->grid_e))
       return rc;
   }
@@ -382,7 +404,17 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
   L->off_dxdirect = off;  off = align256(off + (p.has_node ? sizeof(float) * g->N * d.dx : 0));
   L->off_dxdst = off;     off = align256(off + (p.edge_dst_side ? sizeof(float) * g->N * d.dx : 0));
   L->off_desrc = off;     off = align256(off + sizeof(float) * g->E * d.dx);
-  L->off_part_phi = off;  off = align256(off + sizeof(float) * (size_t)L->grid_e * p.phi.n_params);
+  L->part_stride = p.phi.n_params;
+  if (p.contract == 2) {
+    const size_t R = (size_t)p.gno_Ka * d.gno_in;
+    L->part_stride = p.phi.w_off[p.phi.L - 1];  // the last layer's gradient comes from the GEMM dB = S' DM
+    L->gno_splits = (int)std::min<int64_t>(32, std::max<int64_t>(1, g->N / 1024));
+    L->off_S = off;      off = align256(off + sizeof(float) * (size_t)g->N * R);
+    L->off_T = off;      off = align256(off + sizeof(float) * (size_t)g->N * R);
+    L->off_DM = off;     off = align256(off + sizeof(float) * (size_t)g->N * d.gno_out);
+    L->off_dBpart = off; off = align256(off + sizeof(float) * (size_t)L->gno_splits * R * d.gno_out);
+  }
+  L->off_part_phi = off;  off = align256(off + sizeof(float) * (size_t)L->grid_e * L->part_stride);
   L->off_part_node = off; off = align256(off + sizeof(float) * (size_t)L->grid_n * p.node.n_params);
   L->total = off;
   return NGPDE_OK;
@@ -465,6 +497,7 @@ int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* para
   n.dout = mlp.dims[mlp.L];
   n.gout_ptr = dy;
   n.dparams_partial = part;
+  n.part_stride = mlp.n_params;
   n.dx_direct = dx;
   n.dx = mlp.dims[0];
   n.need_dz0 = 1;
@@ -486,9 +519,10 @@ namespace {
 struct FwdPlan {
   TcPhase edge, node;
   size_t ws_bytes = 0;
+  size_t off_S = 0;
 };
 
-FwdPlan fwd_plan(const Plan& p, int aggr) {
+FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin) {
   FwdPlan f;
   size_t off = 0;
   // max/min: the backward's tie mask compares recomputed messages with the forward's bit for bit, so both must run
@@ -508,6 +542,10 @@ FwdPlan fwd_plan(const Plan& p, int aggr) {
       off = align256(off + 4 * (size_t)f.node.lay.block_floats);
     }
   }
+  if (p.contract == 2) {
+    f.off_S = off;
+    off = align256(off + sizeof(float) * (size_t)N * p.gno_Ka * gin);
+  }
   f.ws_bytes = off;
   return f;
 }
@@ -517,6 +555,7 @@ FwdPlan fwd_plan(const Plan& p, int aggr) {
 extern "C" int ngpde_set_option(int32_t option, int32_t value) {
   switch (option) {
     case NGPDE_OPT_TENSOR_CORES: tc_set_enabled(value != 0); return NGPDE_OK;
+    case NGPDE_OPT_GNO_FACTORED: g_gno_factored = value != 0; return NGPDE_OK;
     default: set_error("unknown option %d", option); return NGPDE_ERR_INVALID;
   }
 }
@@ -525,7 +564,7 @@ extern "C" size_t ngpde_conv_workspace_bytes(ngpde_graph_t g, const ngpde_conv_d
   if (!g || !desc) return 0;
   Plan p;
   if (make_plan(g, *desc, &p)) return 0;
-  if (!backward) return fwd_plan(p, desc->aggr).ws_bytes + 256;
+  if (!backward) return fwd_plan(p, desc->aggr, g->N, desc->gno_in).ws_bytes + 256;
   BwdLayout L;
   if (bwd_layout(g, *desc, p, &L)) return 0;
   return L.total + 256;
@@ -535,12 +574,12 @@ extern "C" int ngpde_conv_kernel_paths(ngpde_graph_t g, const ngpde_conv_desc* d
   NGPDE_REQUIRE(g && desc && paths, "null argument");
   Plan p;
   if (int rc = make_plan(g, *desc, &p)) return rc;
-  const FwdPlan fp = fwd_plan(p, desc->aggr);
+  const FwdPlan fp = fwd_plan(p, desc->aggr, g->N, desc->gno_in);
   BwdLayout L;
   if (int rc = bwd_layout(g, *desc, p, &L)) return rc;
-  paths[NGPDE_PROF_FWD_EDGE] = fp.edge.on ? 1 : 0;
+  paths[NGPDE_PROF_FWD_EDGE] = fp.edge.on ? 1 : (p.contract == 2 ? 2 : 0);
   paths[NGPDE_PROF_FWD_NODE] = p.has_node ? (fp.node.on ? 1 : 0) : -1;
-  paths[NGPDE_PROF_BWD_EDGE] = L.tce.on ? 1 : 0;
+  paths[NGPDE_PROF_BWD_EDGE] = L.tce.on ? 1 : (p.contract == 2 ? 2 : 0);
   paths[NGPDE_PROF_BWD_NODE] = p.has_node ? (L.tcn.on ? 1 : 0) : -1;
   return NGPDE_OK;
 }
@@ -553,7 +592,7 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
   if (g->N == 0) return NGPDE_OK;
   if (int rc = check_io(*desc, p, *io, false)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const FwdPlan fp = fwd_plan(p, desc->aggr);
+  const FwdPlan fp = fwd_plan(p, desc->aggr, g->N, desc->gno_in);
   if (fp.ws_bytes > 0 && (workspace == nullptr || workspace_bytes < fp.ws_bytes)) {
     set_error("forward workspace too small: %zu bytes given, %zu needed (ngpde_conv_workspace_bytes(g, desc, 0))",
               workspace_bytes, fp.ws_bytes);
@@ -564,9 +603,9 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
   // ---- edge phase ----
   int te = 0, smem = 0;
   if (int rc = pick_tile(
-          [&](int t) { return 4 * fwd_smem(p.phi, p.contract, desc->gno_in, desc->gno_out, t).floats; }, &te, &smem))
+          [&](int t) { return 4 * fwd_smem(p.phi, p.contract, desc->gno_in, desc->gno_out, t, p.gno_Ka).floats; }, &te, &smem))
     return rc;
-  FwdSmem fs = fwd_smem(p.phi, p.contract, desc->gno_in, desc->gno_out, te);
+  FwdSmem fs = fwd_smem(p.phi, p.contract, desc->gno_in, desc->gno_out, te, p.gno_Ka);
   FwdArgs a{};
   const int ti = tile_index(te);
   a.tg = TileGraph{g->rowptr, g->src, g->dst, g->perm, g->units[ti], g->n_units[ti], (int)g->N,
@@ -583,7 +622,9 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
   a.dout = p.dm;
   a.out = io->mbar;
   a.addend = nullptr;
-  a.offA = fs.offA; a.offB = fs.offB; a.offW = fs.offW; a.offH = fs.offH;
+  a.offA = fs.offA; a.offB = fs.offB; a.offW = fs.offW; a.offH = fs.offH; a.offZt = fs.offZt;
+  a.gno_Ka = p.gno_Ka;
+  a.gno_S = p.contract == 2 ? reinterpret_cast<float*>(fws + fp.off_S) : nullptr;
   {
     ProfScope prof(NGPDE_PROF_FWD_EDGE, st);
     if (fp.edge.on) {
@@ -593,6 +634,14 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
         return rc;
     } else {
       if (int rc = launch_fwd<false>(te, a, smem, g->num_sms, st)) return rc;
+    }
+    if (p.contract == 2) {
+      // mbar = (S B) ./ deg,  B = [W3; b3] = the last layer's flat parameter segment viewed as [Ka*gin][gout]
+      const int R = p.gno_Ka * desc->gno_in;
+      if (int rc = gno_gemm(a.gno_S, R, false, io->phi_params + p.phi.w_off[p.phi.L - 1], desc->gno_out, true, io->mbar,
+                            desc->gno_out, g->N, desc->gno_out, R, 1,
+                            desc->aggr == NGPDE_AGGR_MEAN ? g->rowptr : nullptr, st))
+        return rc;
     }
   }
 
@@ -654,6 +703,12 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   float* desrc = reinterpret_cast<float*>(ws + L.off_desrc);
   float* part_phi = reinterpret_cast<float*>(ws + L.off_part_phi);
   float* part_node = reinterpret_cast<float*>(ws + L.off_part_node);
+  float* gS = reinterpret_cast<float*>(ws + L.off_S);
+  float* gT = reinterpret_cast<float*>(ws + L.off_T);
+  float* gDM = reinterpret_cast<float*>(ws + L.off_DM);
+  float* gdB = reinterpret_cast<float*>(ws + L.off_dBpart);
+  const int gR = p.gno_Ka * desc->gno_in;
+  const float* gB = p.contract == 2 ? io->phi_params + p.phi.w_off[p.phi.L - 1] : nullptr;
 
   NGPDE_CUDA_TRY(cudaMemsetAsync(part_phi, 0, L.total - L.off_part_phi, st));
   transpose_weights_kernel<<<64, 256, 0, st>>>(io->phi_params, wt_phi, p.phi);
@@ -677,6 +732,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     n.fwd_out = io->y;
     n.addend = p.node_addend ? io->mbar : nullptr;
     n.dparams_partial = part_node;
+    n.part_stride = p.node.n_params;
     n.dx_direct = dxdirect;
     n.dmbar = dmbar;
     n.dx = desc->dx;
@@ -718,6 +774,9 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     a.gout_ptr = p.has_node ? dmbar : io->dy;
     a.fwd_out = io->mbar;
     a.dparams_partial = part_phi;
+    a.part_stride = L.part_stride;
+    a.gno_S = gS; a.gno_T = gT; a.gno_Ka = p.gno_Ka;
+    a.offZt = L.se.offZt; a.offTs = L.se.offTs;
     a.dxdst = dxdst;
     a.desrc = desrc;
     a.dx = desc->dx;
@@ -729,6 +788,12 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     a.offDM = L.se.offDM; a.offP = L.se.offP; a.offDH = L.se.offDH; a.offRed = L.se.offRed;
     if (g->E > 0) {
       ProfScope prof(NGPDE_PROF_BWD_EDGE, st);
+      if (p.contract == 2) {
+        // DM = dmbar ./ deg;  T = DM B'  (the message cotangent is the same for every in-edge of a node)
+        if (int rc = gno_dm_scale(dmbar, g->rowptr, desc->aggr == NGPDE_AGGR_MEAN, g->N, desc->gno_out, gDM, st)) return rc;
+        if (int rc = gno_gemm(gDM, desc->gno_out, false, gB, desc->gno_out, false, gT, gR, g->N, gR, desc->gno_out, 1, nullptr, st))
+          return rc;
+      }
       if (L.tce.on) {
         a.tg.unit_ptr = g->units[2];
         a.tg.n_units = g->n_units[2];
@@ -736,11 +801,18 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       } else {
         if (int rc = launch_bwd<false>(te, a, L.smem_e, L.grid_e, st)) return rc;
       }
+      if (p.contract == 2) {
+        // dB = S' DM over the nodes, split-K slices reduced in fixed order
+        if (int rc = gno_gemm(gS, gR, true, gDM, desc->gno_out, true, gdB, desc->gno_out, gR, desc->gno_out, g->N, L.gno_splits, nullptr, st))
+          return rc;
+        const int PB = gR * desc->gno_out;
+        reduce_partials_kernel<<<(PB + 255) / 256, 256, 0, st>>>(gdB, L.gno_splits, PB, io->dphi_params + p.phi.w_off[p.phi.L - 1]);
+      }
     } else if (dxdst) {
       NGPDE_CUDA_TRY(cudaMemsetAsync(dxdst, 0, sizeof(float) * g->N * desc->dx, st));
     }
-    const int P = p.phi.n_params;
-    reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_phi, L.grid_e, P, io->dphi_params);
+    const int P = L.part_stride;
+    if (P > 0) reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_phi, L.grid_e, P, io->dphi_params);
   }
 
   // ---- dx = dx_direct + dxdst + transpose-gather(desrc) ----

@@ -42,8 +42,11 @@ struct FwdArgs {
   Seg segs[8];
   MlpDev mlp;
   const float* params;
-  int contract;  // GNO: last layer is contracted with x[src] instead of materialised
+  int contract;  // GNO: 1 = last layer contracted with x[src] per edge; 2 = factored evaluation (ngpde_gno.cuh)
   int gin, gout;
+  float* gno_S;  // contract == 2: [N][gno_Ka * gin] per-destination outer-product sums (workspace)
+  int gno_Ka;    // rows of S_n: width of phi's last hidden layer (+1 when its last layer has a bias)
+  int offZt;
   int aggr;
   int dout;             // rows of the result tile
   float* out;           // edge phase: mbar [N][dout]; node phase: y [N][dout]
@@ -77,6 +80,11 @@ struct BwdArgs {
   int has_dst_side;
   int zoff[NGPDE_MAX_LAYERS + 1];
   int offG0, offG1, offW, offH, offDM, offP, offDZ, offDH, offRed;
+  float* gno_S;        // contract == 2 (ngpde_gno.cuh): [N][gno_Ka * gin], rebuilt here for dB = S' DM
+  const float* gno_T;  // contract == 2: [N][gno_Ka * gin] = DM B'
+  int gno_Ka;
+  int part_stride;     // floats per CTA in dparams_partial
+  int offZt, offTs;
 };
 
 // sign with which a segment's input gradient flows to the destination / source row

@@ -6,6 +6,7 @@
 // -> NNlib.scatter  that GraphNeuralNetworks.propagate executes.
 #pragma once
 #include "ngpde_conv.cuh"
+#include "ngpde_gno_tile.cuh"
 
 namespace ngpde {
 
@@ -167,9 +168,13 @@ __global__ void __launch_bounds__(NT) mp_fwd_kernel(const FwdArgs a) {
       kend = a.tg.rowptr[n1];
       // isolated destinations get the identity of the reduction (0 for sum and mean)
       const float ident = aggr_identity(a.aggr);
-      for (int item = tid; item < (n1 - n0) * a.dout; item += NT) {
-        const int jj = item / a.dout;
-        if (a.tg.rowptr[n0 + jj] == a.tg.rowptr[n0 + jj + 1]) a.out[(size_t)n0 * a.dout + item] = ident;
+      if (a.contract == 2) {
+        gno_zero_isolated(a.tg.rowptr, n0, n1, (size_t)a.gno_Ka * a.gin, a.gno_S);
+      } else {
+        for (int item = tid; item < (n1 - n0) * a.dout; item += NT) {
+          const int jj = item / a.dout;
+          if (a.tg.rowptr[n0 + jj] == a.tg.rowptr[n0 + jj + 1]) a.out[(size_t)n0 * a.dout + item] = ident;
+        }
       }
     }
     for (int k0 = kbeg; k0 < kend; k0 += TE) {
@@ -177,7 +182,9 @@ __global__ void __launch_bounds__(NT) mp_fwd_kernel(const FwdArgs a) {
       load_ids<TE>(a.tg, NODE, k0, ne, s_src, s_dst, s_perm);
       __syncthreads();
       gather_tile<TE>(bufA, a, ne, s_src, s_dst, s_perm);
-      if (a.contract) {
+      if (a.contract == 2) {
+        gno_gather_h<TE>(a.arr[ARR_X], a.ld[ARR_X], a.gin, s_src, ne, H, a.gin + 4);
+      } else if (a.contract) {
         const float* __restrict__ X = a.arr[ARR_X];
         const int ldx = a.ld[ARR_X];
         for (int item = tid; item < a.gin * TE; item += NT) {
@@ -195,6 +202,17 @@ __global__ void __launch_bounds__(NT) mp_fwd_kernel(const FwdArgs a) {
         dense_tile<TE>(cur, nxt, mlp.dims[l], mlp.dims[l + 1], a.params + mlp.w_off[l], bias, mlp.act[l], ws, add,
                        k0, ne);
         float* t = cur; cur = nxt; nxt = t;
+      }
+      if (a.contract == 2) {
+        // GNOConv, factored: S_n += [z_e; 1] h_e' for the rows of this tile; mbar = S B follows as one GEMM
+        const int K = mlp.dims[mlp.L - 1];
+        float* Zt = base + a.offZt;
+        const int ldz = gno_ldz(a.gno_Ka);
+        gno_transpose_z<TE>(cur, K, a.gno_Ka > K, ne, Zt, ldz);
+        __syncthreads();
+        gno_outer_rows<TE>(Zt, ldz, H, a.gin + 4, a.gno_Ka, a.gin, a.tg.rowptr, n0, n1, k0, ne, a.gno_S);
+        __syncthreads();
+        continue;
       }
       if (a.contract) {
         // GNOConv: m[o][e] = sum_i act(phi_L(z))[o + gout*i][e] * h_src[i][e]; the (in*out) kernel matrix of an
@@ -277,7 +295,13 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
   const MlpDev& mlp = a.mlp;
   const int L = mlp.L;
   const int Lp = a.contract ? L - 1 : L;
-  float* dWp = a.dparams_partial + (size_t)blockIdx.x * mlp.n_params;
+  float* dWp = a.dparams_partial + (size_t)blockIdx.x * a.part_stride;
+  if (a.contract == 2) {
+    // pad rows of the staged T_n (read by the 4-row groups of gno_apply_T) stay zero for the whole kernel
+    float* Ts = base + a.offTs;
+    const int lds = a.gin + 4;
+    for (int i = tid + a.gno_Ka * lds; i < ((a.gno_Ka + 3) & ~3) * lds; i += NT) Ts[i] = 0.f;
+  }
   const int nfwd = (a.store_last || a.contract) ? Lp : Lp - 1;
 
   for (int unit = blockIdx.x; unit < a.tg.n_units; unit += gridDim.x) {
@@ -292,6 +316,7 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
       n1 = a.tg.unit_ptr[unit + 1];
       kbeg = a.tg.rowptr[n0];
       kend = a.tg.rowptr[n1];
+      if (a.contract == 2) gno_zero_isolated(a.tg.rowptr, n0, n1, (size_t)a.gno_Ka * a.gin, a.gno_S);
       if (a.has_dst_side) {
         for (int item = tid; item < (n1 - n0) * a.dx; item += NT) {
           const int jj = item / a.dx;
@@ -338,6 +363,34 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
           }
           G[c * C::LD + e] = v;
         }
+        __syncthreads();
+      } else if (a.contract == 2) {
+        // ---- GNOConv, factored (ngpde_gno.cuh): d h_e = T_n' [z_e; 1], d z_e = T_n h_e, S rebuilt for dB = S' DM ----
+        const int K = mlp.dims[L - 1], Ka = a.gno_Ka;
+        const float* Zin = base + a.zoff[Lp];
+        float* Ht = base + a.offH;
+        float* Zt = base + a.offZt;
+        float* Ts = base + a.offTs;
+        const int ldh = a.gin + 4, ldz = gno_ldz(Ka), lds = a.gin + 4;
+        const size_t R = (size_t)Ka * a.gin;
+        gno_gather_h<TE>(a.arr[ARR_X], a.ld[ARR_X], a.gin, s_src, ne, Ht, ldh);
+        gno_transpose_z<TE>(Zin, K, Ka > K, ne, Zt, ldz);
+        for (int item = tid; item < K * C::LD; item += NT) G[item] = 0.f;
+        for (int n = n0; n < n1; ++n) {
+          const int r0 = a.tg.rowptr[n], r1 = a.tg.rowptr[n + 1];
+          const int lo = max(r0, k0) - k0, hi = min(r1, k0 + ne) - k0;
+          if (lo >= hi) continue;
+          __syncthreads();
+          const float* __restrict__ Tn = a.gno_T + (size_t)n * R;
+          const int q = a.gin >> 2;
+          for (int item = tid; item < Ka * q; item += NT) {
+            const int j = item / q, c4 = (item - j * q) * 4;
+            *reinterpret_cast<float4*>(Ts + j * lds + c4) = __ldg(reinterpret_cast<const float4*>(Tn + (size_t)j * a.gin + c4));
+          }
+          __syncthreads();
+          gno_apply_T<TE>(Ts, lds, Zt, ldz, Ht, ldh, K, Ka, a.gin, lo, hi, k0, a.desrc, a.dx, G);
+        }
+        gno_outer_rows<TE>(Zt, ldz, Ht, ldh, Ka, a.gin, a.tg.rowptr, n0, n1, k0, ne, a.gno_S);
         __syncthreads();
       } else {
         // ---- GNOConv: backward of m[o] = sum_i act(phi_L(z))[o + gout*i] * h_src[i] ----

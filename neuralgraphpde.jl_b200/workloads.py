@@ -212,9 +212,16 @@ def c4_gno(device="cuda", n_nodes: int = 1_000_000, mean_deg: float = 16.0, chs:
     fe = _mlp_flops([(6, hidden), (hidden, hidden), (hidden, chs * chs)]) + 2 * chs * chs
     fn = 2 * chs * chs
     bf, bb = _bytes(N, E, chs, 3, 0, chs, layer.parameterlength())
+    # flops the factored evaluation (csrc/ngpde_gno.cuh) actually issues: hidden layers + outer product per edge, the
+    # contraction with the affine last layer once per NODE (R = (hidden + 1) * chs rows of B = [W3; b3])
+    R = (hidden + 1) * chs
+    f_hidden = _mlp_flops([(6, hidden), (hidden, hidden)])
+    ex_fwd = E * (f_hidden + 2 * R) + N * 2 * R * chs
+    ex_bwd = E * (3 * f_hidden + 3 * 2 * R) + N * 2 * (2 * R * chs)
     return Workload("C4 GNOConv %d=>%d radius graph N=%d" % (chs, chs, N), layer, ps, st, _x(rng, chs, N, device), g, N, E,
                     float(E * fe + N * fn), bf, bb,
-                    notes={"flops_edge_fwd": float(E * fe), "flops_node_fwd": float(N * fn)})
+                    notes={"flops_edge_fwd": float(E * fe), "flops_node_fwd": float(N * fn),
+                           "flops_executed_fwd_edge": float(ex_fwd), "flops_executed_bwd_edge": float(ex_bwd)})
 
 
 def c5_gcn_vmh(device="cuda", n_graphs: int = 512, side: int = 64, hidden: int = 64, seed: int = 0) -> Workload:

@@ -289,6 +289,52 @@ def test_gno_conv_sum_aggregation_no_bias():
     check_layer(layer, jl_rand(rng, 6, 60, DEV), ps, st, g)
 
 
+@pytest.mark.parametrize("factored", [1, 0])
+@pytest.mark.parametrize("aggr,phi_bias,depth,cin,cout", [("mean", True, 3, 16, 12), ("+", False, 2, 8, 4),
+                                                          ("mean", True, 1, 24, 8), ("+", True, 3, 64, 64)])
+def test_gno_conv_factored_and_per_edge_paths(factored, aggr, phi_bias, depth, cin, cout):
+    """GNOConv with an affine last phi layer runs the factored evaluation (per-destination outer-product sums + GEMMs,
+    csrc/ngpde_gno.cuh); NGPDE_OPT_GNO_FACTORED=0 forces the per-edge contraction.  Both must meet the oracle bar.  The
+    graph has isolated nodes, edge features and one destination with 400 in-edges (a row carried across tiles)."""
+    rng = np.random.default_rng(31 + cin)
+    n, e = 300, 2400
+    s, t = rng.integers(0, n - 5, e), rng.integers(0, n - 5, e)  # last 5 nodes isolated
+    t[:400] = 7
+    g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"a": jl_rand(rng, 1, n), "x": jl_rand(rng, 2, n)},
+                 edata={"e": jl_rand(rng, 2, e)}).to(DEV)
+    din = 3 + 3 + 2
+    dims = [din] + [20] * (depth - 1) + [cin * cout]
+    layers = [Dense(dims[i], dims[i + 1], "relu" if i < depth - 1 else "identity", bias=(phi_bias or i < depth - 1))
+              for i in range(depth)]
+    phi = layers[0] if depth == 1 else Chain(*layers)
+    layer = GNOConv((cin, cout), phi, "relu", initialgraph=g, aggr=aggr)
+    ps, st = setup(rng, layer, DEV)
+    ngpde._lib.set_option(ngpde._lib.OPT_GNO_FACTORED, factored)
+    try:
+        from ngpde import engine
+        x = jl_rand(rng, cin, n, DEV)
+        r = engine.RhsRunner(layer, x, ps, st)
+        assert ngpde._lib.kernel_paths(r.handle, r.desc)["bwd_edge"] == (2 if factored else 0)
+        check_layer(layer, x, ps, st, g)
+    finally:
+        ngpde._lib.set_option(ngpde._lib.OPT_GNO_FACTORED, 1)
+
+
+def test_gno_conv_factored_matches_per_edge_at_c4_widths():
+    w = workloads.c4_gno(DEV, n_nodes=6000)
+    dy = torch.randn(64, w.n_nodes, generator=torch.Generator().manual_seed(2)).to(DEV)
+    a = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy)
+    a2 = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy)
+    assert all(torch.equal(u, v) for u, v in zip(a, a2)), "factored GNOConv must be run-to-run deterministic"
+    ngpde._lib.set_option(ngpde._lib.OPT_GNO_FACTORED, 0)
+    try:
+        b = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy)
+    finally:
+        ngpde._lib.set_option(ngpde._lib.OPT_GNO_FACTORED, 1)
+    for u, v in zip(a, b):
+        assert relerr(u, v) <= TOL
+
+
 @pytest.mark.parametrize("cin,cout,loops,act", [(2, 64, True, "tanh"), (64, 64, True, "tanh"), (16, 4, True, "relu"),
                                                (7, 7, False, "identity"), (12, 5, False, "swish")])
 def test_gcn_conv(cin, cout, loops, act):
@@ -557,4 +603,10 @@ def test_kernel_path_query_reports_the_engine_that_runs():
     w4 = workloads.c4_gno(DEV, n_nodes=500)
     r4 = engine.RhsRunner(w4.layer, w4.x, w4.ps, w4.st)
     p4 = ngpde._lib.kernel_paths(r4.handle, r4.desc)
-    assert p4["fwd_edge"] == 0 and p4["bwd_edge"] == 0
+    assert p4["fwd_edge"] == 2 and p4["bwd_edge"] == 2  # factored GNOConv evaluation (csrc/ngpde_gno.cuh)
+    ngpde._lib.set_option(ngpde._lib.OPT_GNO_FACTORED, 0)
+    try:
+        p4 = ngpde._lib.kernel_paths(r4.handle, r4.desc)
+        assert p4["fwd_edge"] == 0 and p4["bwd_edge"] == 0
+    finally:
+        ngpde._lib.set_option(ngpde._lib.OPT_GNO_FACTORED, 1)
