@@ -19,6 +19,7 @@ struct ProfSlot {
 };
 bool g_prof_on = false;
 bool g_gno_factored = true;  // NGPDE_OPT_GNO_FACTORED
+int g_debug_skip = 0;          // NGPDE_OPT_DEBUG_SKIP
 ProfSlot g_prof[NGPDE_PROF_SLOTS];
 
 struct ProfScope {
@@ -243,10 +244,15 @@ BwdSmem bwd_smem(const MlpDev& m, int contract, int gin, int gout, int aggr, boo
   off += rows[0] * ld;
   s.offG1 = off;
   off += rows[1] * ld;
+  int ws_floats = 2 * KC * npass;
   if (contract == 2) {
-    s.offH = off;  off += te * (gin + 4);
+    // the edge-major h tile is dead before the MLP backward first writes G1, and the staged T_n lives only between the
+    // recompute and the MLP backward (the two users of the weight staging buffer): both are aliased, which is what lets a
+    // 64-edge tile of the C4 shape fit two CTAs per SM
+    s.offH = s.offG1;
+    off = s.offG1 + std::max(rows[1] * ld, te * (gin + 4));
     s.offZt = off; off += te * gno_ldz(Ka);
-    s.offTs = off; off += ((Ka + 3) & ~3) * (gin + 4);
+    ws_floats = std::max(ws_floats, ((Ka + 3) & ~3) * (gin + 4));
   } else if (contract) {
     s.offH = off;  off += gin * ld;
     s.offDH = off; off += gin * ld;
@@ -255,7 +261,8 @@ BwdSmem bwd_smem(const MlpDev& m, int contract, int gin, int gout, int aggr, boo
     s.offRed = off; off += nth * te;
   }
   s.offW = off;
-  off += 2 * KC * npass;
+  s.offTs = off;
+  off += ws_floats;
   s.floats = 3 * te + off;
   return s;
 }
@@ -556,6 +563,7 @@ extern "C" int ngpde_set_option(int32_t option, int32_t value) {
   switch (option) {
     case NGPDE_OPT_TENSOR_CORES: tc_set_enabled(value != 0); return NGPDE_OK;
     case NGPDE_OPT_GNO_FACTORED: g_gno_factored = value != 0; return NGPDE_OK;
+    case NGPDE_OPT_DEBUG_SKIP: g_debug_skip = value; return NGPDE_OK;
     default: set_error("unknown option %d", option); return NGPDE_ERR_INVALID;
   }
 }
@@ -777,6 +785,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     a.part_stride = L.part_stride;
     a.gno_S = gS; a.gno_T = gT; a.gno_Ka = p.gno_Ka;
     a.offZt = L.se.offZt; a.offTs = L.se.offTs;
+    a.debug_skip = g_debug_skip;
     a.dxdst = dxdst;
     a.desrc = desrc;
     a.dx = desc->dx;

@@ -85,6 +85,7 @@ struct BwdArgs {
   int gno_Ka;
   int part_stride;     // floats per CTA in dparams_partial
   int offZt, offTs;
+  int debug_skip;      // developer aid (NGPDE_OPT_DEBUG_SKIP): bitmask of phases left out, for phase timing only
 };
 
 // sign with which a segment's input gradient flows to the destination / source row

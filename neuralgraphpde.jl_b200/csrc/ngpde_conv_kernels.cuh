@@ -296,12 +296,7 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
   const int L = mlp.L;
   const int Lp = a.contract ? L - 1 : L;
   float* dWp = a.dparams_partial + (size_t)blockIdx.x * a.part_stride;
-  if (a.contract == 2) {
-    // pad rows of the staged T_n (read by the 4-row groups of gno_apply_T) stay zero for the whole kernel
-    float* Ts = base + a.offTs;
-    const int lds = a.gin + 4;
-    for (int i = tid + a.gno_Ka * lds; i < ((a.gno_Ka + 3) & ~3) * lds; i += NT) Ts[i] = 0.f;
-  }
+
   const int nfwd = (a.store_last || a.contract) ? Lp : Lp - 1;
 
   for (int unit = blockIdx.x; unit < a.tg.n_units; unit += gridDim.x) {
@@ -331,7 +326,7 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
       gather_tile<TE>(base + a.zoff[0], a, ne, s_src, s_dst, s_perm);
       __syncthreads();
       // ---- recompute the forward activations of this tile (nothing per-edge was saved by the forward) ----
-      for (int l = 0; l < nfwd; ++l) {
+      for (int l = (a.debug_skip & 16) ? nfwd : 0; l < nfwd; ++l) {
         const float* bias = mlp.b_off[l] >= 0 ? a.params + mlp.b_off[l] : nullptr;
         const float* add = (NODE && l == L - 1) ? a.addend : nullptr;
         dense_tile<TE>(base + a.zoff[l], base + a.zoff[l + 1], mlp.dims[l], mlp.dims[l + 1], a.params + mlp.w_off[l],
@@ -376,6 +371,8 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
         gno_gather_h<TE>(a.arr[ARR_X], a.ld[ARR_X], a.gin, s_src, ne, Ht, ldh);
         gno_transpose_z<TE>(Zin, K, Ka > K, ne, Zt, ldz);
         for (int item = tid; item < K * C::LD; item += NT) G[item] = 0.f;
+        // pad rows of the staged T_n (read by the 4-row groups of gno_apply_T); Ts shares the weight staging buffer
+        for (int i = tid + Ka * lds; i < ((Ka + 3) & ~3) * lds; i += NT) Ts[i] = 0.f;
         for (int n = n0; n < n1; ++n) {
           const int r0 = a.tg.rowptr[n], r1 = a.tg.rowptr[n + 1];
           const int lo = max(r0, k0) - k0, hi = min(r1, k0 + ne) - k0;
@@ -383,14 +380,15 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
           __syncthreads();
           const float* __restrict__ Tn = a.gno_T + (size_t)n * R;
           const int q = a.gin >> 2;
+          if (!(a.debug_skip & 8))
           for (int item = tid; item < Ka * q; item += NT) {
             const int j = item / q, c4 = (item - j * q) * 4;
             *reinterpret_cast<float4*>(Ts + j * lds + c4) = __ldg(reinterpret_cast<const float4*>(Tn + (size_t)j * a.gin + c4));
           }
           __syncthreads();
-          gno_apply_T<TE>(Ts, lds, Zt, ldz, Ht, ldh, K, Ka, a.gin, lo, hi, k0, a.desrc, a.dx, G);
+          if (!(a.debug_skip & 1)) gno_apply_T<TE>(Ts, lds, Zt, ldz, Ht, ldh, K, Ka, a.gin, lo, hi, k0, a.desrc, a.dx, G);
         }
-        gno_outer_rows<TE>(Zt, ldz, Ht, ldh, Ka, a.gin, a.tg.rowptr, n0, n1, k0, ne, a.gno_S);
+        if (!(a.debug_skip & 2)) gno_outer_rows<TE>(Zt, ldz, Ht, ldh, Ka, a.gin, a.tg.rowptr, n0, n1, k0, ne, a.gno_S);
         __syncthreads();
       } else {
         // ---- GNOConv: backward of m[o] = sum_i act(phi_L(z))[o + gout*i] * h_src[i] ----
@@ -500,7 +498,7 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
       }
 
       // ---- back through the Dense layers ----
-      for (int l = Lp - 1; l >= 0; --l) {
+      for (int l = (a.debug_skip & 4) ? -1 : Lp - 1; l >= 0; --l) {
         const int K = mlp.dims[l], N = mlp.dims[l + 1];
         const float* W = a.params + mlp.w_off[l];
         const float* bias = mlp.b_off[l] >= 0 ? a.params + mlp.b_off[l] : nullptr;
