@@ -1,6 +1,6 @@
 // GNOConv, factored evaluation (layers.jl:509-547).
 //
-// When phi's last Dense layer is affine (no activation -- the reference's documented use, layers.jl:469-476) and the
+// When phi's last Dense layer is affine (no activation -- the reference's documented use, layers.jl:463-470) and the
 // aggregation is + or mean, the per-edge kernel matrix never has to exist.  With z_e = phi_{1..L-1}(edge inputs) (K wide),
 // h_e = x[src(e)] (gin wide) and the last layer  W_e = reshape(W3' z_e + b3, gout, gin):
 //
