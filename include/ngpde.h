@@ -237,6 +237,14 @@ int ngpde_profile_read(double* total_ms, int64_t* launches);
  * FP32 GEMMs), -1 when the layer has no such phase. */
 int ngpde_conv_kernel_paths(ngpde_graph_t g, const ngpde_conv_desc* desc, int32_t* paths);
 
+/* developer/test aid: the dense GEMM of the factored GNOConv evaluation (csrc/ngpde_gno.cuh) on its own.
+ * C[M][N] = op(A) op(B) over K; a_kmajor: A stored [K][M] (else [M][K]); b_kmajor: B stored [K][N] (else [N][K]);
+ * splits > 1 writes split-K slices C + s*M*ldc; deg_rowptr: divide row m by rowptr[m+1]-rowptr[m] (0 for empty rows);
+ * engine 0 = FP32 FFMA, 1 = tcgen05 3xTF32. */
+int ngpde_debug_gemm(const float* A, int32_t lda, int32_t a_kmajor, const float* B, int32_t ldb, int32_t b_kmajor, float* C,
+                     int32_t ldc, int64_t M, int32_t N, int64_t K, int32_t splits, const int32_t* deg_rowptr,
+                     int32_t engine, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ EXPORTS = [
     "ngpde_mppde_conv_forward", "ngpde_mppde_conv_backward", "ngpde_gno_conv_forward", "ngpde_gno_conv_backward",
     "ngpde_gcn_workspace_bytes", "ngpde_gcn_conv_forward", "ngpde_gcn_conv_backward", "ngpde_axpy_stages",
     "ngpde_profile_enable", "ngpde_profile_read", "ngpde_set_option", "ngpde_rows_gather", "ngpde_rows_put",
-    "ngpde_rows_segment_add", "ngpde_debug_buffer", "ngpde_conv_kernel_paths",
+    "ngpde_rows_segment_add", "ngpde_debug_buffer", "ngpde_conv_kernel_paths", "ngpde_debug_gemm",
 ]
 
 
@@ -102,6 +102,7 @@ def load() -> C.CDLL:
     lib.ngpde_profile_enable.argtypes = [i32]
     lib.ngpde_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]
     lib.ngpde_conv_kernel_paths.argtypes = [vp, C.POINTER(ConvDesc), C.POINTER(i32)]
+    lib.ngpde_debug_gemm.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i64, i32, i64, i32, vp, i32, vp]
     _lib = lib
     return lib
 

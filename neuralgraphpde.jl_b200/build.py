@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libngpde.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["ngpde_graph.cu", "ngpde_conv.cu", "ngpde_tc.cu", "ngpde_gcn.cu", "ngpde_halo.cu", "ngpde_gno.cu"]
+SOURCES = ["ngpde_graph.cu", "ngpde_conv.cu", "ngpde_tc.cu", "ngpde_gcn.cu", "ngpde_halo.cu", "ngpde_gno.cu", "ngpde_gno_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

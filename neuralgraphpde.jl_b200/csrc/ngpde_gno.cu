@@ -168,6 +168,13 @@ __global__ void gno_dm_scale_kernel(const float* __restrict__ dmbar, const int* 
 
 int gno_gemm(const float* A, int lda, bool a_kmajor, const float* B, int ldb, bool b_kmajor, float* C, int ldc, int64_t M,
              int N, int64_t K, int splits, const int* deg_rowptr, cudaStream_t st) {
+  if (tc_get_enabled() && gno_gemm_tc_supported(lda, a_kmajor, ldb, b_kmajor, ldc, N, K))
+    return gno_gemm_tc(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, splits, deg_rowptr, st);
+  return gno_gemm_ffma(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, splits, deg_rowptr, st);
+}
+
+int gno_gemm_ffma(const float* A, int lda, bool a_kmajor, const float* B, int ldb, bool b_kmajor, float* C, int ldc,
+                  int64_t M, int N, int64_t K, int splits, const int* deg_rowptr, cudaStream_t st) {
   if (M <= 0 || N <= 0) return NGPDE_OK;
   NGPDE_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && (ldc & 3) == 0 && (N & 3) == 0, "gno_gemm: strides must be multiples of 4");
   NGPDE_REQUIRE(a_kmajor ? (M & 3) == 0 : (K & 3) == 0, "gno_gemm: contiguous extent of A must be a multiple of 4");
@@ -197,3 +204,12 @@ int gno_dm_scale(const float* dmbar, const int* rowptr, int mean, int64_t N, int
 }
 
 }  // namespace ngpde
+
+extern "C" int ngpde_debug_gemm(const float* A, int32_t lda, int32_t a_kmajor, const float* B, int32_t ldb, int32_t b_kmajor,
+                                float* C, int32_t ldc, int64_t M, int32_t N, int64_t K, int32_t splits,
+                                const int32_t* deg_rowptr, int32_t engine, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (engine == 1)
+    return ngpde::gno_gemm_tc(A, lda, a_kmajor != 0, B, ldb, b_kmajor != 0, C, ldc, M, N, K, splits, deg_rowptr, st);
+  return ngpde::gno_gemm_ffma(A, lda, a_kmajor != 0, B, ldb, b_kmajor != 0, C, ldc, M, N, K, splits, deg_rowptr, st);
+}

@@ -27,6 +27,14 @@ namespace ngpde {
 // Requires lda, ldb, ldc, and the contiguous extents to be multiples of 4 floats and 16-byte aligned bases.
 int gno_gemm(const float* A, int lda, bool a_kmajor, const float* B, int ldb, bool b_kmajor, float* C, int ldc, int64_t M,
              int N, int64_t K, int splits, const int* deg_rowptr, cudaStream_t st);
+// the two engines behind gno_gemm: FP32 FFMA (ngpde_gno.cu) and tcgen05 3xTF32 (ngpde_gno_tc.cu; taken when
+// NGPDE_OPT_TENSOR_CORES is on and the strides allow it)
+int gno_gemm_ffma(const float* A, int lda, bool a_kmajor, const float* B, int ldb, bool b_kmajor, float* C, int ldc,
+                  int64_t M, int N, int64_t K, int splits, const int* deg_rowptr, cudaStream_t st);
+bool gno_gemm_tc_supported(int lda, bool a_kmajor, int ldb, bool b_kmajor, int ldc, int N, int64_t K);
+int gno_gemm_tc(const float* A, int lda, bool a_kmajor, const float* B, int ldb, bool b_kmajor, float* C, int ldc, int64_t M,
+                int N, int64_t K, int splits, const int* deg_rowptr, cudaStream_t st);
+bool tc_get_enabled();  // ngpde_tc.cu
 
 // DM[n][:] = dmbar[n][:] / deg(n) for mean (true division, 0 for isolated nodes), plain copy for sum
 int gno_dm_scale(const float* dmbar, const int* rowptr, int mean, int64_t N, int d, float* DM, cudaStream_t st);

@@ -1,0 +1,249 @@
+// tcgen05 / TMEM GEMM of the factored GNOConv evaluation (ngpde_gno.cuh): C[M][N] = op(A) op(B), FP32-accurate through
+// the 3xTF32 split (ngpde_umma.cuh), FP32 accumulation in tensor memory.
+//
+// One CTA of 128 threads owns a 128 x 64 output tile.  Per k-block of 32 floats both operand tiles are staged by all
+// four warps as K-major SWIZZLE_128B images (rows = m resp. n, 128-byte rows of 32 k-values; hi and lo image each):
+// global -> registers (prefetched one block ahead) -> TF32 split -> shared memory; one elected thread then issues
+// 4 k-steps x 3 products  lo*hi, hi*lo, hi*hi  of tcgen05.mma kind::tf32 (M = 128, N = 64, K = 8) and commits them to the
+// stage's mbarrier; two stages, so the staging of block i+1 overlaps the MMAs of block i.  Sources stored with the
+// OTHER index contiguous (B = [K][N] of mbar = S B; both operands of dB = S' DM) are transposed on the way in with a lane
+// map (8 rows x 4 k per warp store) that is bank-conflict free under the swizzle and reads full 32-byte sectors.
+// Epilogue: tcgen05.ld, thread = output row, 256 contiguous bytes per row.
+//
+// Operand conventions (K-major SWIZZLE_128B read with SBO = 1024, k-step = +32 bytes) are the ones pinned on hardware by
+// tools/umma_probe.cu mode 1 img 0; tools/gemm_check.py checks every variant of this kernel against a float64 product.
+#include "ngpde_gno.cuh"
+#include "ngpde_umma.cuh"
+
+namespace ngpde {
+namespace {
+
+using namespace umma;
+
+constexpr int TBM = 128, TBN = 64, TBK = 32, TGT = 128;
+constexpr int A_IMG = TBM * TBK;                     // floats per A image (16 KB)
+constexpr int B_IMG = TBN * TBK;                     // floats per B image (8 KB)
+constexpr int STAGE_FLOATS = 2 * A_IMG + 2 * B_IMG;  // A hi | A lo | B hi | B lo   (48 KB)
+constexpr int TC_SMEM_BYTES = 2 * STAGE_FLOATS * 4 + 1024;
+constexpr int TMEM_COLS = 64;
+
+struct TcGemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  const int* deg_rowptr;
+  long long M, K;
+  int N, lda, ldb, ldc;
+  long long k_per_split;
+};
+
+// ---- global -> registers.  ROWS = 128 (A) or 64 (B).  NV values per thread = ROWS * 32 / 128.
+// SRC_T == false: source [rows][K] (k contiguous): float4 along k; thread's v-th float4: row = tid/8 + 16 v, kq = tid % 8.
+// SRC_T == true : source [K][rows] (row index contiguous): scalars; combo = warp + 4 v, row = 8 (combo / 8) + lane / 4,
+//                 k = 4 (combo % 8) + lane % 4.
+template <int ROWS, bool SRC_T>
+__device__ __forceinline__ void tile_load(float (&r)[ROWS / 4], const float* __restrict__ P, int ld, long long row0,
+                                          long long nrows, long long k0, long long kend, int tid) {
+  if (!SRC_T) {
+#pragma unroll
+    for (int v = 0; v < ROWS / 16; ++v) {
+      const int row = (tid >> 3) + 16 * v, kq = tid & 7;
+      const long long gr = row0 + row, gk = k0 + 4 * kq;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < nrows && gk < kend) x = __ldg(reinterpret_cast<const float4*>(P + (size_t)gr * ld + gk));
+      r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+    }
+  } else {
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int v = 0; v < ROWS / 4; ++v) {
+      const int combo = warp + 4 * v;
+      const int row = 8 * (combo >> 3) + (lane >> 2), k = 4 * (combo & 7) + (lane & 3);
+      const long long gr = row0 + row, gk = k0 + k;
+      r[v] = (gr < nrows && gk < kend) ? __ldg(P + (size_t)gk * ld + gr) : 0.f;
+    }
+  }
+}
+
+// ---- registers -> hi / lo images (K-major SWIZZLE_128B, rows of 32 floats)
+template <int ROWS, bool SRC_T>
+__device__ __forceinline__ void tile_store(const float (&r)[ROWS / 4], float* __restrict__ hi, float* __restrict__ lo,
+                                           int tid) {
+  if (!SRC_T) {
+#pragma unroll
+    for (int v = 0; v < ROWS / 16; ++v) {
+      const int row = (tid >> 3) + 16 * v, kq = tid & 7;
+      const uint32_t off = (uint32_t)(row * 32 + ((kq ^ (row & 7)) << 2));
+      float4 h, l;
+      h.x = tf32_hi(r[4 * v + 0]); l.x = tf32_lo(r[4 * v + 0], h.x);
+      h.y = tf32_hi(r[4 * v + 1]); l.y = tf32_lo(r[4 * v + 1], h.y);
+      h.z = tf32_hi(r[4 * v + 2]); l.z = tf32_lo(r[4 * v + 2], h.z);
+      h.w = tf32_hi(r[4 * v + 3]); l.w = tf32_lo(r[4 * v + 3], h.w);
+      *reinterpret_cast<float4*>(hi + off) = h;
+      *reinterpret_cast<float4*>(lo + off) = l;
+    }
+  } else {
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int v = 0; v < ROWS / 4; ++v) {
+      const int combo = warp + 4 * v;
+      const int row = 8 * (combo >> 3) + (lane >> 2), k = 4 * (combo & 7) + (lane & 3);
+      const uint32_t off = sw128_offset(0, ROWS, row, k);
+      const float h = tf32_hi(r[v]);
+      hi[off] = h;
+      lo[off] = tf32_lo(r[v], h);
+    }
+  }
+}
+
+template <bool A_T, bool B_T>
+__global__ void __launch_bounds__(TGT) gno_gemm_tc_kernel(const TcGemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bar[2];
+  const int tid = threadIdx.x;
+  const int warp = uniform_i32(tid >> 5);
+  const long long m0 = (long long)blockIdx.x * TBM;
+  const int n0 = blockIdx.y * TBN;
+  const long long kbeg = (long long)blockIdx.z * g.k_per_split;
+  const long long kend = min(g.K, kbeg + g.k_per_split);
+  const int nkb = kend > kbeg ? (int)((kend - kbeg + TBK - 1) / TBK) : 0;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = uniform_u32(tmem_slot);
+  const uint32_t smem_base = uniform_u32(smem_u32(smem));
+  const uint32_t idesc = make_idesc(TBM, TBN, 0, 0);
+
+  float ra[TBM / 4], rb[TBN / 4];
+  if (nkb > 0) {
+    tile_load<TBM, A_T>(ra, g.A, g.lda, m0, g.M, kbeg, kend, tid);
+    tile_load<TBN, B_T>(rb, g.B, g.ldb, n0, g.N, kbeg, kend, tid);
+  }
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb & 1;
+    float* st = smem + s * STAGE_FLOATS;
+    if (kb >= 2) mbar_wait(&bar[s], (uint32_t)(((kb >> 1) - 1) & 1));  // the MMAs that read this stage have completed
+    tile_store<TBM, A_T>(ra, st, st + A_IMG, tid);
+    tile_store<TBN, B_T>(rb, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid);
+    if (kb + 1 < nkb) {
+      tile_load<TBM, A_T>(ra, g.A, g.lda, m0, g.M, kbeg + (long long)(kb + 1) * TBK, kend, tid);
+      tile_load<TBN, B_T>(rb, g.B, g.ldb, n0, g.N, kbeg + (long long)(kb + 1) * TBK, kend, tid);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one_sync()) {
+        tc_fence_after();
+        const uint32_t a_hi = smem_base + (uint32_t)(s * STAGE_FLOATS) * 4u;
+        const uint32_t a_lo = a_hi + A_IMG * 4u;
+        const uint32_t b_hi = a_hi + 2u * A_IMG * 4u;
+        const uint32_t b_lo = b_hi + B_IMG * 4u;
+#pragma unroll
+        for (int ks = 0; ks < TBK / 8; ++ks) {
+          const uint64_t dah = make_sdesc(a_hi + ks * 32, 0, 1024, 2), dal = make_sdesc(a_lo + ks * 32, 0, 1024, 2);
+          const uint64_t dbh = make_sdesc(b_hi + ks * 32, 0, 1024, 2), dbl = make_sdesc(b_lo + ks * 32, 0, 1024, 2);
+          mma_tf32_ss(tmem_d, dal, dbh, idesc, (kb > 0 || ks > 0) ? 1 : 0);  // small cross terms first
+          mma_tf32_ss(tmem_d, dah, dbl, idesc, 1);
+          mma_tf32_ss(tmem_d, dah, dbh, idesc, 1);
+        }
+        mma_commit(&bar[s]);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- epilogue: thread = output row ----
+  float* C = g.C + (size_t)blockIdx.z * (size_t)g.M * g.ldc;
+  const long long m = m0 + tid;
+  float den = 1.f;
+  bool zero = nkb == 0;
+  if (g.deg_rowptr != nullptr && m < g.M) {
+    const int deg = g.deg_rowptr[m + 1] - g.deg_rowptr[m];
+    den = (float)deg;
+    zero = zero || deg == 0;
+  }
+  if (nkb > 0) {
+    const int last = nkb - 1;
+    mbar_wait(&bar[last & 1], (uint32_t)((last >> 1) & 1));  // MMAs complete in issue order: the last commit covers all
+    tc_fence_after();
+  }
+  const uint32_t trow = tmem_d + ((uint32_t)((tid >> 5) * 32) << 16);
+#pragma unroll
+  for (int c = 0; c < TBN; c += 16) {
+    uint32_t v[16];
+    if (nkb > 0) {
+      tmem_ld16(trow + c, v);
+      tmem_wait_ld();
+    }
+    if (m < g.M) {
+#pragma unroll
+      for (int q = 0; q < 16; q += 4) {
+        const int n = n0 + c + q;
+        if (n >= g.N) continue;  // N % 4 == 0
+        float4 o;
+        if (zero) {
+          o = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          o = make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
+          if (g.deg_rowptr != nullptr) {
+            o.x = __fdiv_rn(o.x, den); o.y = __fdiv_rn(o.y, den); o.z = __fdiv_rn(o.z, den); o.w = __fdiv_rn(o.w, den);
+          }
+        }
+        *reinterpret_cast<float4*>(C + (size_t)m * g.ldc + n) = o;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+template <bool A_T, bool B_T>
+int launch(const TcGemmArgs& g, dim3 grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    NGPDE_CUDA_TRY(cudaFuncSetAttribute(gno_gemm_tc_kernel<A_T, B_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    configured = true;
+  }
+  gno_gemm_tc_kernel<A_T, B_T><<<grid, TGT, TC_SMEM_BYTES, st>>>(g);
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
+}  // namespace
+
+bool gno_gemm_tc_supported(int lda, bool a_kmajor, int ldb, bool b_kmajor, int ldc, int N, int64_t K) {
+  if ((ldc & 3) || (N & 3)) return false;
+  if (!a_kmajor && ((lda & 3) || (K & 3))) return false;  // float4 reads along k
+  if (!b_kmajor && ((ldb & 3) || (K & 3))) return false;
+  return true;
+}
+
+int gno_gemm_tc(const float* A, int lda, bool a_kmajor, const float* B, int ldb, bool b_kmajor, float* C, int ldc, int64_t M,
+                int N, int64_t K, int splits, const int* deg_rowptr, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return NGPDE_OK;
+  NGPDE_REQUIRE(gno_gemm_tc_supported(lda, a_kmajor, ldb, b_kmajor, ldc, N, K), "gno_gemm_tc: unsupported strides");
+  TcGemmArgs g;
+  g.A = A; g.B = B; g.C = C; g.deg_rowptr = deg_rowptr;
+  g.M = M; g.K = K; g.N = N; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  splits = splits < 1 ? 1 : splits;
+  long long kps = (K + splits - 1) / splits;
+  kps = (kps + TBK - 1) / TBK * TBK;
+  g.k_per_split = kps > 0 ? kps : TBK;
+  dim3 grid((unsigned)((M + TBM - 1) / TBM), (unsigned)((N + TBN - 1) / TBN), (unsigned)splits);
+  if (a_kmajor && b_kmajor) return launch<true, true>(g, grid, st);
+  if (!a_kmajor && b_kmajor) return launch<false, true>(g, grid, st);
+  if (!a_kmajor && !b_kmajor) return launch<false, false>(g, grid, st);
+  return launch<true, false>(g, grid, st);
+}
+
+}  // namespace ngpde

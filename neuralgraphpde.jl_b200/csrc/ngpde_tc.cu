@@ -210,6 +210,7 @@ int launch_bwd_tc(bool node, const TcBwdPhase& t, const MlpDev& mlp, const BwdAr
   return node ? launch_bwd_tc_t<true>(t, mlp, base, wblock, st) : launch_bwd_tc_t<false>(t, mlp, base, wblock, st);
 }
 void tc_set_enabled(bool on) { g_use_tc = on; }
+bool tc_get_enabled() { return g_use_tc; }
 void tc_set_debug_buffer(long long* p) { g_tcb_dbg = p; }
 
 }  // namespace ngpde
