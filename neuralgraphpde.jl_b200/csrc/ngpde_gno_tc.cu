@@ -25,7 +25,8 @@ constexpr int A_IMG = TBM * TBK;                     // floats per A image (16 K
 constexpr int B_IMG = TBN * TBK;                     // floats per B image (8 KB)
 constexpr int STAGE_FLOATS = 2 * A_IMG + 2 * B_IMG;  // A hi | A lo | B hi | B lo   (48 KB)
 constexpr int TC_SMEM_BYTES = 2 * STAGE_FLOATS * 4 + 1024;
-constexpr int TMEM_COLS = 64;
+constexpr int TMEM_COLS = 128;                      // two accumulators of 64 columns
+constexpr int CHUNK = 8;                             // k-blocks (256 k-values) accumulated in TMEM before an FP32 flush
 
 struct TcGemmArgs {
   const float* A;
@@ -123,21 +124,42 @@ __global__ void __launch_bounds__(TGT) gno_gemm_tc_kernel(const TcGemmArgs g) {
   const uint32_t smem_base = uniform_u32(smem_u32(smem));
   const uint32_t idesc = make_idesc(TBM, TBN, 0, 0);
 
-  float ra[TBM / 4], rb[TBN / 4];
-  if (nkb > 0) {
-    tile_load<TBM, A_T>(ra, g.A, g.lda, m0, g.M, kbeg, kend, tid);
-    tile_load<TBN, B_T>(rb, g.B, g.ldb, n0, g.N, kbeg, kend, tid);
-  }
-  for (int kb = 0; kb < nkb; ++kb) {
+  // FP32 accumulators of this thread's output row.  The tensor core truncates its FP32 accumulator at every MMA, so a long
+  // K would drift (measured 3e-5 at K = 4160): every CHUNK k-blocks the partial sum leaves TMEM and is added here with a
+  // rounded FP32 add, while the next chunk already accumulates into the other TMEM buffer (no pipeline bubble).
+  float acc[TBN];
+#pragma unroll
+  for (int c = 0; c < TBN; ++c) acc[c] = 0.f;
+  const uint32_t trow = tmem_d + ((uint32_t)((tid >> 5) * 32) << 16);
+  auto flush = [&](int buf) {
+#pragma unroll
+    for (int c = 0; c < TBN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(trow + buf * TBN + c, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[c + q] += __uint_as_float(v[q]);
+    }
+    tc_fence_before();
+  };
+
+  // operand registers, prefetched two k-blocks ahead (the loop is unrolled by two so both sets are statically indexed)
+  float ra0[TBM / 4], rb0[TBN / 4], ra1[TBM / 4], rb1[TBN / 4];
+  auto fetch = [&](float (&ra)[TBM / 4], float (&rb)[TBN / 4], int kb) {
+    if (kb < nkb) {
+      tile_load<TBM, A_T>(ra, g.A, g.lda, m0, g.M, kbeg + (long long)kb * TBK, kend, tid);
+      tile_load<TBN, B_T>(rb, g.B, g.ldb, n0, g.N, kbeg + (long long)kb * TBK, kend, tid);
+    }
+  };
+  auto block = [&](float (&ra)[TBM / 4], float (&rb)[TBN / 4], int kb) {
     const int s = kb & 1;
+    const int buf = (kb / CHUNK) & 1;
+    const bool chunk_start = (kb % CHUNK) == 0;
     float* st = smem + s * STAGE_FLOATS;
     if (kb >= 2) mbar_wait(&bar[s], (uint32_t)(((kb >> 1) - 1) & 1));  // the MMAs that read this stage have completed
     tile_store<TBM, A_T>(ra, st, st + A_IMG, tid);
     tile_store<TBN, B_T>(rb, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid);
-    if (kb + 1 < nkb) {
-      tile_load<TBM, A_T>(ra, g.A, g.lda, m0, g.M, kbeg + (long long)(kb + 1) * TBK, kend, tid);
-      tile_load<TBN, B_T>(rb, g.B, g.ldb, n0, g.N, kbeg + (long long)(kb + 1) * TBK, kend, tid);
-    }
+    fetch(ra, rb, kb + 2);
     fence_async_smem();
     __syncthreads();
     if (warp == 0) {
@@ -147,62 +169,63 @@ __global__ void __launch_bounds__(TGT) gno_gemm_tc_kernel(const TcGemmArgs g) {
         const uint32_t a_lo = a_hi + A_IMG * 4u;
         const uint32_t b_hi = a_hi + 2u * A_IMG * 4u;
         const uint32_t b_lo = b_hi + B_IMG * 4u;
+        const uint32_t d = tmem_d + (uint32_t)(buf * TBN);
 #pragma unroll
         for (int ks = 0; ks < TBK / 8; ++ks) {
           const uint64_t dah = make_sdesc(a_hi + ks * 32, 0, 1024, 2), dal = make_sdesc(a_lo + ks * 32, 0, 1024, 2);
           const uint64_t dbh = make_sdesc(b_hi + ks * 32, 0, 1024, 2), dbl = make_sdesc(b_lo + ks * 32, 0, 1024, 2);
-          mma_tf32_ss(tmem_d, dal, dbh, idesc, (kb > 0 || ks > 0) ? 1 : 0);  // small cross terms first
-          mma_tf32_ss(tmem_d, dah, dbl, idesc, 1);
-          mma_tf32_ss(tmem_d, dah, dbh, idesc, 1);
+          mma_tf32_ss(d, dal, dbh, idesc, (!chunk_start || ks > 0) ? 1 : 0);  // small cross terms first
+          mma_tf32_ss(d, dah, dbl, idesc, 1);
+          mma_tf32_ss(d, dah, dbh, idesc, 1);
         }
         mma_commit(&bar[s]);
       }
       __syncwarp();
     }
+    if (chunk_start && kb > 0) {
+      // the previous chunk ended with block kb-1: its commit covers every MMA of that chunk
+      mbar_wait(&bar[(kb - 1) & 1], (uint32_t)(((kb - 1) >> 1) & 1));
+      tc_fence_after();
+      flush(buf ^ 1);
+    }
+  };
+  fetch(ra0, rb0, 0);
+  fetch(ra1, rb1, 1);
+  for (int kb = 0; kb < nkb; kb += 2) {
+    block(ra0, rb0, kb);
+    if (kb + 1 < nkb) block(ra1, rb1, kb + 1);
   }
 
   // ---- epilogue: thread = output row ----
   float* C = g.C + (size_t)blockIdx.z * (size_t)g.M * g.ldc;
   const long long m = m0 + tid;
   float den = 1.f;
-  bool zero = nkb == 0;
+  bool zero = false;
   if (g.deg_rowptr != nullptr && m < g.M) {
     const int deg = g.deg_rowptr[m + 1] - g.deg_rowptr[m];
     den = (float)deg;
-    zero = zero || deg == 0;
+    zero = deg == 0;
   }
   if (nkb > 0) {
     const int last = nkb - 1;
     mbar_wait(&bar[last & 1], (uint32_t)((last >> 1) & 1));  // MMAs complete in issue order: the last commit covers all
     tc_fence_after();
+    flush((last / CHUNK) & 1);
   }
-  const uint32_t trow = tmem_d + ((uint32_t)((tid >> 5) * 32) << 16);
+  if (m < g.M) {
 #pragma unroll
-  for (int c = 0; c < TBN; c += 16) {
-    uint32_t v[16];
-    if (nkb > 0) {
-      tmem_ld16(trow + c, v);
-      tmem_wait_ld();
-    }
-    if (m < g.M) {
-#pragma unroll
-      for (int q = 0; q < 16; q += 4) {
-        const int n = n0 + c + q;
-        if (n >= g.N) continue;  // N % 4 == 0
-        float4 o;
-        if (zero) {
-          o = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-          o = make_float4(__uint_as_float(v[q]), __uint_as_float(v[q + 1]), __uint_as_float(v[q + 2]), __uint_as_float(v[q + 3]));
-          if (g.deg_rowptr != nullptr) {
-            o.x = __fdiv_rn(o.x, den); o.y = __fdiv_rn(o.y, den); o.z = __fdiv_rn(o.z, den); o.w = __fdiv_rn(o.w, den);
-          }
-        }
-        *reinterpret_cast<float4*>(C + (size_t)m * g.ldc + n) = o;
+    for (int c = 0; c < TBN; c += 4) {
+      const int n = n0 + c;
+      if (n >= g.N) continue;  // N % 4 == 0
+      float4 o = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+      if (zero) {
+        o = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (g.deg_rowptr != nullptr) {
+        o.x = __fdiv_rn(o.x, den); o.y = __fdiv_rn(o.y, den); o.z = __fdiv_rn(o.z, den); o.w = __fdiv_rn(o.w, den);
       }
+      *reinterpret_cast<float4*>(C + (size_t)m * g.ldc + n) = o;
     }
   }
-  tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, TMEM_COLS);
 }
