@@ -1,9 +1,11 @@
 // tcgen05 / TMEM GEMM of the factored GNOConv evaluation (ngpde_gno.cuh): C[M][N] = op(A) op(B), FP32-accurate through
 // the 3xTF32 split (ngpde_umma.cuh), FP32 accumulation in tensor memory.
 //
-// One CTA of 128 threads owns a 128 x 64 output tile.  Per k-block of 32 floats both operand tiles are staged by all
-// four warps as K-major SWIZZLE_128B images (rows = m resp. n, 128-byte rows of 32 k-values; hi and lo image each):
-// global -> registers (prefetched one block ahead) -> TF32 split -> shared memory; one elected thread then issues
+// One CTA of 128 threads owns a 128 x 64 output tile.  Per k-block of 32 floats the A tile goes to TENSOR MEMORY (thread =
+// row = TMEM lane; hi and lo halves of the TF32 split side by side -- an SS-form first version was bound by shared-memory
+// bandwidth: 6 KB of operand reads per MMA plus the staging writes) and the B tile to shared memory as K-major
+// SWIZZLE_128B images (rows = n, 128-byte rows of 32 k-values; hi and lo image each):
+// global -> registers (prefetched two blocks ahead) -> TF32 split -> TMEM / shared memory; one elected thread then issues
 // 4 k-steps x 3 products  lo*hi, hi*lo, hi*hi  of tcgen05.mma kind::tf32 (M = 128, N = 64, K = 8) and commits them to the
 // stage's mbarrier; two stages, so the staging of block i+1 overlaps the MMAs of block i.  Sources stored with the
 // OTHER index contiguous (B = [K][N] of mbar = S B; both operands of dB = S' DM) are transposed on the way in with a lane
@@ -23,9 +25,10 @@ using namespace umma;
 constexpr int TBM = 128, TBN = 64, TBK = 32, TGT = 128;
 constexpr int A_IMG = TBM * TBK;                     // floats per A image (16 KB)
 constexpr int B_IMG = TBN * TBK;                     // floats per B image (8 KB)
-constexpr int STAGE_FLOATS = 2 * A_IMG + 2 * B_IMG;  // A hi | A lo | B hi | B lo   (48 KB)
+constexpr int STAGE_FLOATS = 2 * B_IMG;              // B hi | B lo   (16 KB); the A operand lives in tensor memory
 constexpr int TC_SMEM_BYTES = 2 * STAGE_FLOATS * 4 + 1024;
-constexpr int TMEM_COLS = 128;                      // two accumulators of 64 columns
+constexpr int TMEM_COLS = 256;                       // D0 | D1 (64 each) | stage 0: A hi, A lo (32 each) | stage 1: A hi, A lo
+constexpr int COL_A = 2 * TBN;
 constexpr int CHUNK = 8;                             // k-blocks (256 k-values) accumulated in TMEM before an FP32 flush
 
 struct TcGemmArgs {
@@ -97,6 +100,41 @@ __device__ __forceinline__ void tile_store(const float (&r)[ROWS / 4], float* __
   }
 }
 
+// ---- A operand: thread = tile row (= TMEM lane), 32 k-values per block.
+// SRC_T == false: source [M][K]: eight float4 of the thread's own row;  SRC_T == true: source [K][M]: 32 scalars, a warp's
+// lanes read 128 contiguous bytes per k.
+template <bool SRC_T>
+__device__ __forceinline__ void row_load(float (&r)[TBK], const float* __restrict__ P, int ld, long long m, long long M,
+                                         long long k0, long long kend) {
+  if (!SRC_T) {
+#pragma unroll
+    for (int q = 0; q < TBK / 4; ++q) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && k0 + 4 * q < kend) x = __ldg(reinterpret_cast<const float4*>(P + (size_t)m * ld + k0 + 4 * q));
+      r[4 * q + 0] = x.x; r[4 * q + 1] = x.y; r[4 * q + 2] = x.z; r[4 * q + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < TBK; ++k) r[k] = (m < M && k0 + k < kend) ? __ldg(P + (size_t)(k0 + k) * ld + m) : 0.f;
+  }
+}
+// TF32 split of the row into tensor memory: columns [col, col+32) = hi, [col+32, col+64) = lo
+__device__ __forceinline__ void row_store_tmem(const float (&r)[TBK], uint32_t taddr) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float x = r[16 * h + q];
+      const float xh = tf32_hi(x);
+      hi[q] = __float_as_uint(xh);
+      lo[q] = __float_as_uint(tf32_lo(x, xh));
+    }
+    tmem_st16(taddr + 16 * h, hi);
+    tmem_st16(taddr + TBK + 16 * h, lo);
+  }
+}
+
 template <bool A_T, bool B_T>
 __global__ void __launch_bounds__(TGT) gno_gemm_tc_kernel(const TcGemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -144,39 +182,40 @@ __global__ void __launch_bounds__(TGT) gno_gemm_tc_kernel(const TcGemmArgs g) {
   };
 
   // operand registers, prefetched two k-blocks ahead (the loop is unrolled by two so both sets are statically indexed)
-  float ra0[TBM / 4], rb0[TBN / 4], ra1[TBM / 4], rb1[TBN / 4];
-  auto fetch = [&](float (&ra)[TBM / 4], float (&rb)[TBN / 4], int kb) {
+  float ra0[TBK], rb0[TBN / 4], ra1[TBK], rb1[TBN / 4];
+  auto fetch = [&](float (&ra)[TBK], float (&rb)[TBN / 4], int kb) {
     if (kb < nkb) {
-      tile_load<TBM, A_T>(ra, g.A, g.lda, m0, g.M, kbeg + (long long)kb * TBK, kend, tid);
+      row_load<A_T>(ra, g.A, g.lda, m0 + tid, g.M, kbeg + (long long)kb * TBK, kend);
       tile_load<TBN, B_T>(rb, g.B, g.ldb, n0, g.N, kbeg + (long long)kb * TBK, kend, tid);
     }
   };
-  auto block = [&](float (&ra)[TBM / 4], float (&rb)[TBN / 4], int kb) {
+  auto block = [&](float (&ra)[TBK], float (&rb)[TBN / 4], int kb) {
     const int s = kb & 1;
     const int buf = (kb / CHUNK) & 1;
     const bool chunk_start = (kb % CHUNK) == 0;
     float* st = smem + s * STAGE_FLOATS;
-    if (kb >= 2) mbar_wait(&bar[s], (uint32_t)(((kb >> 1) - 1) & 1));  // the MMAs that read this stage have completed
-    tile_store<TBM, A_T>(ra, st, st + A_IMG, tid);
-    tile_store<TBN, B_T>(rb, st + 2 * A_IMG, st + 2 * A_IMG + B_IMG, tid);
+    if (kb >= 2) mbar_spin(&bar[s], (uint32_t)(((kb >> 1) - 1) & 1));  // the MMAs that read this stage have completed
+    row_store_tmem(ra, trow + COL_A + s * 2 * TBK);
+    tile_store<TBN, B_T>(rb, st, st + B_IMG, tid);
     fetch(ra, rb, kb + 2);
+    tmem_wait_st();
+    tc_fence_before();
     fence_async_smem();
     __syncthreads();
     if (warp == 0) {
       if (elect_one_sync()) {
         tc_fence_after();
-        const uint32_t a_hi = smem_base + (uint32_t)(s * STAGE_FLOATS) * 4u;
-        const uint32_t a_lo = a_hi + A_IMG * 4u;
-        const uint32_t b_hi = a_hi + 2u * A_IMG * 4u;
+        const uint32_t a_hi = tmem_d + (uint32_t)(COL_A + s * 2 * TBK);
+        const uint32_t a_lo = a_hi + TBK;
+        const uint32_t b_hi = smem_base + (uint32_t)(s * STAGE_FLOATS) * 4u;
         const uint32_t b_lo = b_hi + B_IMG * 4u;
         const uint32_t d = tmem_d + (uint32_t)(buf * TBN);
 #pragma unroll
         for (int ks = 0; ks < TBK / 8; ++ks) {
-          const uint64_t dah = make_sdesc(a_hi + ks * 32, 0, 1024, 2), dal = make_sdesc(a_lo + ks * 32, 0, 1024, 2);
           const uint64_t dbh = make_sdesc(b_hi + ks * 32, 0, 1024, 2), dbl = make_sdesc(b_lo + ks * 32, 0, 1024, 2);
-          mma_tf32_ss(d, dal, dbh, idesc, (!chunk_start || ks > 0) ? 1 : 0);  // small cross terms first
-          mma_tf32_ss(d, dah, dbl, idesc, 1);
-          mma_tf32_ss(d, dah, dbh, idesc, 1);
+          mma_tf32_ts(d, a_lo + ks * 8, dbh, idesc, (!chunk_start || ks > 0) ? 1 : 0);  // small cross terms first
+          mma_tf32_ts(d, a_hi + ks * 8, dbl, idesc, 1);
+          mma_tf32_ts(d, a_hi + ks * 8, dbh, idesc, 1);
         }
         mma_commit(&bar[s]);
       }
@@ -184,7 +223,7 @@ __global__ void __launch_bounds__(TGT) gno_gemm_tc_kernel(const TcGemmArgs g) {
     }
     if (chunk_start && kb > 0) {
       // the previous chunk ended with block kb-1: its commit covers every MMA of that chunk
-      mbar_wait(&bar[(kb - 1) & 1], (uint32_t)(((kb - 1) >> 1) & 1));
+      mbar_spin(&bar[(kb - 1) & 1], (uint32_t)(((kb - 1) >> 1) & 1));
       tc_fence_after();
       flush(buf ^ 1);
     }
@@ -208,7 +247,7 @@ __global__ void __launch_bounds__(TGT) gno_gemm_tc_kernel(const TcGemmArgs g) {
   }
   if (nkb > 0) {
     const int last = nkb - 1;
-    mbar_wait(&bar[last & 1], (uint32_t)((last >> 1) & 1));  // MMAs complete in issue order: the last commit covers all
+    mbar_spin(&bar[last & 1], (uint32_t)((last >> 1) & 1));  // MMAs complete in issue order: the last commit covers all
     tc_fence_after();
     flush((last / CHUNK) & 1);
   }
