@@ -26,7 +26,7 @@ constexpr int TBM = 128, TBN = 64, TBK = 32, TGT = 128;
 constexpr int A_IMG = TBM * TBK;                     // floats per A image (16 KB)
 constexpr int B_IMG = TBN * TBK;                     // floats per B image (8 KB)
 constexpr int STAGE_FLOATS = 2 * B_IMG;              // B hi | B lo   (16 KB); the A operand lives in tensor memory
-constexpr int TC_SMEM_BYTES = 2 * STAGE_FLOATS * 4 + 1024;
+constexpr int TC_SMEM_BYTES = 2 * STAGE_FLOATS * 4 + TBM * TBK * 4 + 1024;  // + the warps' transpose patches
 constexpr int TMEM_COLS = 256;                       // D0 | D1 (64 each) | stage 0: A hi, A lo (32 each) | stage 1: A hi, A lo
 constexpr int COL_A = 2 * TBN;
 constexpr int CHUNK = 8;                             // k-blocks (256 k-values) accumulated in TMEM before an FP32 flush
@@ -48,23 +48,38 @@ struct TcGemmArgs {
 template <int ROWS, bool SRC_T>
 __device__ __forceinline__ void tile_load(float (&r)[ROWS / 4], const float* __restrict__ P, int ld, long long row0,
                                           long long nrows, long long k0, long long kend, int tid) {
+  const bool full = k0 + TBK <= kend && row0 + ROWS <= nrows;
   if (!SRC_T) {
+    const float* p = P + (size_t)(row0 + (tid >> 3)) * ld + k0 + 4 * (tid & 7);
+    if (full) {
 #pragma unroll
-    for (int v = 0; v < ROWS / 16; ++v) {
-      const int row = (tid >> 3) + 16 * v, kq = tid & 7;
-      const long long gr = row0 + row, gk = k0 + 4 * kq;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gr < nrows && gk < kend) x = __ldg(reinterpret_cast<const float4*>(P + (size_t)gr * ld + gk));
-      r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+      for (int v = 0; v < ROWS / 16; ++v) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(p + (size_t)(16 * v) * ld));
+        r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < ROWS / 16; ++v) {
+        const long long gr = row0 + (tid >> 3) + 16 * v, gk = k0 + 4 * (tid & 7);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < nrows && gk < kend) x = __ldg(reinterpret_cast<const float4*>(p + (size_t)(16 * v) * ld));
+        r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+      }
     }
   } else {
     const int warp = tid >> 5, lane = tid & 31;
+    // combo = warp + 4 v: row = 8 (combo / 8) + lane / 4 = 8 (v / 2) + lane / 4, k = 4 (combo % 8) + lane % 4
+    const float* p = P + (size_t)(k0 + 4 * warp + (lane & 3)) * ld + row0 + (lane >> 2);
+    const float* p16 = p + (size_t)16 * ld;
+    if (full) {
 #pragma unroll
-    for (int v = 0; v < ROWS / 4; ++v) {
-      const int combo = warp + 4 * v;
-      const int row = 8 * (combo >> 3) + (lane >> 2), k = 4 * (combo & 7) + (lane & 3);
-      const long long gr = row0 + row, gk = k0 + k;
-      r[v] = (gr < nrows && gk < kend) ? __ldg(P + (size_t)gk * ld + gr) : 0.f;
+      for (int v = 0; v < ROWS / 4; ++v) r[v] = __ldg(((v & 1) ? p16 : p) + 8 * (v >> 1));
+    } else {
+#pragma unroll
+      for (int v = 0; v < ROWS / 4; ++v) {
+        const int row = 8 * (v >> 1) + (lane >> 2), k = 4 * (warp + 4 * (v & 1)) + (lane & 3);
+        r[v] = (row0 + row < nrows && k0 + k < kend) ? __ldg(((v & 1) ? p16 : p) + 8 * (v >> 1)) : 0.f;
+      }
     }
   }
 }
@@ -101,22 +116,62 @@ __device__ __forceinline__ void tile_store(const float (&r)[ROWS / 4], float* __
 }
 
 // ---- A operand: thread = tile row (= TMEM lane), 32 k-values per block.
-// SRC_T == false: source [M][K]: eight float4 of the thread's own row;  SRC_T == true: source [K][M]: 32 scalars, a warp's
-// lanes read 128 contiguous bytes per k.
+// SRC_T == true : source [K][M]: 32 scalars of the thread's own row; a warp's lanes read 128 contiguous bytes per k.
+// SRC_T == false: source [M][K]: read row-per-thread this would be 32 different 128-byte lines per warp instruction (ncu:
+//                 L1 85 % busy, tensor pipe 17 %), so each warp reads ITS 32 rows coalesced (8 lanes x float4 per row,
+//                 4 rows per instruction) and a_to_rows() turns the registers into row order through a warp-private,
+//                 XOR-swizzled 4 KB shared-memory patch.
 template <bool SRC_T>
-__device__ __forceinline__ void row_load(float (&r)[TBK], const float* __restrict__ P, int ld, long long m, long long M,
-                                         long long k0, long long kend) {
+__device__ __forceinline__ void a_load(float (&r)[TBK], const float* __restrict__ P, int ld, long long m0, long long M,
+                                       long long k0, long long kend, int tid) {
+  const bool full = k0 + TBK <= kend;
   if (!SRC_T) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const long long kq = k0 + 4 * (lane & 7);
+    const float* p = P + (size_t)(m0 + 32 * warp + (lane >> 3)) * ld + kq;
+    const long long mrow = m0 + 32 * warp + (lane >> 3);
+    if (full && m0 + TBM <= M) {
 #pragma unroll
-    for (int q = 0; q < TBK / 4; ++q) {
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M && k0 + 4 * q < kend) x = __ldg(reinterpret_cast<const float4*>(P + (size_t)m * ld + k0 + 4 * q));
-      r[4 * q + 0] = x.x; r[4 * q + 1] = x.y; r[4 * q + 2] = x.z; r[4 * q + 3] = x.w;
+      for (int v = 0; v < TBK / 4; ++v) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(p + (size_t)(4 * v) * ld));
+        r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < TBK / 4; ++v) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mrow + 4 * v < M && kq < kend) x = __ldg(reinterpret_cast<const float4*>(p + (size_t)(4 * v) * ld));
+        r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+      }
     }
   } else {
+    const long long m = m0 + tid;
+    const float* p = P + (size_t)k0 * ld + m;
+    if (m < M && full) {
 #pragma unroll
-    for (int k = 0; k < TBK; ++k) r[k] = (m < M && k0 + k < kend) ? __ldg(P + (size_t)(k0 + k) * ld + m) : 0.f;
+      for (int k = 0; k < TBK; ++k) r[k] = __ldg(p + (size_t)k * ld);
+    } else {
+#pragma unroll
+      for (int k = 0; k < TBK; ++k) r[k] = (m < M && k0 + k < kend) ? __ldg(p + (size_t)k * ld) : 0.f;
+    }
   }
+}
+// registers in a_load's coalesced order -> the thread's own row (no-op for SRC_T); tw = this warp's 32 x 32 float patch
+template <bool SRC_T>
+__device__ __forceinline__ void a_to_rows(float (&r)[TBK], float* __restrict__ tw, int lane) {
+  if (SRC_T) return;
+#pragma unroll
+  for (int v = 0; v < TBK / 4; ++v) {
+    const int row = 4 * v + (lane >> 3), kq = lane & 7;
+    *reinterpret_cast<float4*>(tw + row * 32 + ((kq ^ (row & 7)) << 2)) = make_float4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < TBK / 4; ++q) {
+    const float4 x = *reinterpret_cast<const float4*>(tw + lane * 32 + ((q ^ (lane & 7)) << 2));
+    r[4 * q + 0] = x.x; r[4 * q + 1] = x.y; r[4 * q + 2] = x.z; r[4 * q + 3] = x.w;
+  }
+  __syncwarp();
 }
 // TF32 split of the row into tensor memory: columns [col, col+32) = hi, [col+32, col+64) = lo
 __device__ __forceinline__ void row_store_tmem(const float (&r)[TBK], uint32_t taddr) {
@@ -185,7 +240,7 @@ __global__ void __launch_bounds__(TGT) gno_gemm_tc_kernel(const TcGemmArgs g) {
   float ra0[TBK], rb0[TBN / 4], ra1[TBK], rb1[TBN / 4];
   auto fetch = [&](float (&ra)[TBK], float (&rb)[TBN / 4], int kb) {
     if (kb < nkb) {
-      row_load<A_T>(ra, g.A, g.lda, m0 + tid, g.M, kbeg + (long long)kb * TBK, kend);
+      a_load<A_T>(ra, g.A, g.lda, m0, g.M, kbeg + (long long)kb * TBK, kend, tid);
       tile_load<TBN, B_T>(rb, g.B, g.ldb, n0, g.N, kbeg + (long long)kb * TBK, kend, tid);
     }
   };
@@ -195,6 +250,7 @@ __global__ void __launch_bounds__(TGT) gno_gemm_tc_kernel(const TcGemmArgs g) {
     const bool chunk_start = (kb % CHUNK) == 0;
     float* st = smem + s * STAGE_FLOATS;
     if (kb >= 2) mbar_spin(&bar[s], (uint32_t)(((kb >> 1) - 1) & 1));  // the MMAs that read this stage have completed
+    a_to_rows<A_T>(ra, smem + 2 * STAGE_FLOATS + (tid >> 5) * (32 * TBK), tid & 31);
     row_store_tmem(ra, trow + COL_A + s * 2 * TBK);
     tile_store<TBN, B_T>(rb, st, st + B_IMG, tid);
     fetch(ra, rb, kb + 2);
