@@ -168,9 +168,10 @@ __global__ void gno_dm_scale_kernel(const float* __restrict__ dmbar, const int* 
 
 int gno_gemm(const float* A, int lda, bool a_kmajor, const float* B, int ldb, bool b_kmajor, float* C, int ldc, int64_t M,
              int N, int64_t K, int splits, const int* deg_rowptr, cudaStream_t st) {
-  // short-K products (T = DM B': K = out_chs) are bound by the output write and per-tile overheads, where the
-  // tensor-core kernel has no edge over the FFMA one (measured at C4: 4.1 vs 3.9 ms)
-  if (tc_get_enabled() && K > 128 && gno_gemm_tc_supported(lda, a_kmajor, ldb, b_kmajor, ldc, N, K))
+  // short-K products are bound by the output write and per-tile overheads, where the generic tensor-core kernel has no
+  // edge over the FFMA one (measured at C4: 4.1 vs 3.9 ms); T = DM B' has its own variant that walks the n-tiles
+  const bool nloop = !a_kmajor && !b_kmajor && K <= 64 && splits <= 1 && deg_rowptr == nullptr && N > 64;  // T = DM B'
+  if (tc_get_enabled() && (K > 128 || nloop) && gno_gemm_tc_supported(lda, a_kmajor, ldb, b_kmajor, ldc, N, K))
     return gno_gemm_tc(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, splits, deg_rowptr, st);
   return gno_gemm_ffma(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, M, N, K, splits, deg_rowptr, st);
 }
