@@ -373,12 +373,17 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
         for (int item = tid; item < K * C::LD; item += NT) G[item] = 0.f;
         // pad rows of the staged T_n (read by the 4-row groups of gno_apply_T); Ts shares the weight staging buffer
         for (int i = tid + Ka * lds; i < ((Ka + 3) & ~3) * lds; i += NT) Ts[i] = 0.f;
+        if (a.debug_skip & 32) __syncthreads();
         for (int n = n0; n < n1; ++n) {
           const int r0 = a.tg.rowptr[n], r1 = a.tg.rowptr[n + 1];
           const int lo = max(r0, k0) - k0, hi = min(r1, k0 + ne) - k0;
           if (lo >= hi) continue;
-          __syncthreads();
           const float* __restrict__ Tn = a.gno_T + (size_t)n * R;
+          if (a.debug_skip & 32) {  // experiment: T_n read straight from global memory (L1), no staging, no barriers
+            gno_apply_T<TE, true>(Tn, a.gin, Zt, ldz, Ht, ldh, K, Ka, a.gin, lo, hi, k0, a.desrc, a.dx, G);
+            continue;
+          }
+          __syncthreads();
           const int q = a.gin >> 2;
           if (!(a.debug_skip & 8))
           for (int item = tid; item < Ka * q; item += NT) {

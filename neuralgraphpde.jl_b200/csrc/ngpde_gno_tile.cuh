@@ -115,13 +115,18 @@ __device__ __forceinline__ void gno_zero_isolated(const int* __restrict__ rowptr
 //     desrc[k0 + e][i] = sum_{j < Ka} Zt[e][j] * Ts[j][i]                 (cotangent of h_e = x[src(e)])
 //     G[j][e]          = sum_{i < gin} Ts[j][i] * Ht[e][i],   j < K        (cotangent of z_e, feature-major tile)
 // 16 edges per pass (lane te = tid & 15), 8 column groups of 8 (tc = tid >> 4); gin % 8 == 0.
-template <int TE>
+// TG: Ts is T_n itself in global memory (row stride gin, no pad rows: row reads are clamped to Ka-1, where za is 0).
+template <int TE, bool TG = false>
 __device__ __forceinline__ void gno_apply_T(const float* __restrict__ Ts, int lds, const float* __restrict__ Zt, int ldz,
                                             const float* __restrict__ Ht, int ldh, int K, int Ka, int gin, int lo, int hi,
                                             int k0, float* __restrict__ desrc, int dx, float* __restrict__ G) {
   using C = Cfg<TE>;
   const int te = threadIdx.x & 15, tc = threadIdx.x >> 4;
   const int Ka4 = (Ka + 3) & ~3;
+  const int jmax = TG ? Ka - 1 : Ka4 - 1;
+  auto ld4 = [](const float* p) {
+    return TG ? __ldg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
+  };
   for (int eg = lo; eg < hi; eg += 16) {
     const int e = eg + te;
     const bool valid = e < hi;
@@ -141,8 +146,9 @@ __device__ __forceinline__ void gno_apply_T(const float* __restrict__ Ts, int ld
         *reinterpret_cast<float4*>(&z[0]) = *reinterpret_cast<const float4*>(zrow + j4);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          const float4 t0 = *reinterpret_cast<const float4*>(tp + (j4 + jj) * lds);
-          const float4 t1 = *reinterpret_cast<const float4*>(tp + (j4 + jj) * lds + 4);
+          const int jr = TG ? min(j4 + jj, jmax) : j4 + jj;
+          const float4 t0 = ld4(tp + jr * lds);
+          const float4 t1 = ld4(tp + jr * lds + 4);
           acc[0] = fmaf(z[jj], t0.x, acc[0]); acc[1] = fmaf(z[jj], t0.y, acc[1]);
           acc[2] = fmaf(z[jj], t0.z, acc[2]); acc[3] = fmaf(z[jj], t0.w, acc[3]);
           acc[4] = fmaf(z[jj], t1.x, acc[4]); acc[5] = fmaf(z[jj], t1.y, acc[5]);
@@ -167,7 +173,7 @@ __device__ __forceinline__ void gno_apply_T(const float* __restrict__ Ts, int ld
         const float4 h = *reinterpret_cast<const float4*>(hrow + i4);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float4 t = *reinterpret_cast<const float4*>(tp + min(q, Ka4 - 1 - j0) * lds + i4);
+          const float4 t = ld4(tp + min(q, jmax - j0) * lds + i4);
           acc[q] = fmaf(h.x, t.x, acc[q]);
           acc[q] = fmaf(h.y, t.y, acc[q]);
           acc[q] = fmaf(h.z, t.z, acc[q]);
