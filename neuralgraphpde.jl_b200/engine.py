@@ -51,8 +51,9 @@ class RhsRunner:
         fam = ops._FAMILY_FN[self.desc.family]
         self._fwd = getattr(self.lib, f"ngpde_{fam}_forward")
         self._bwd = getattr(self.lib, f"ngpde_{fam}_backward")
-        self.launches_fwd = 2 if self.has_node else 1
-        self.launches_bwd = 8 if self.has_node else 5
+        factored = ops._factored(self.lib, self.handle, self.desc)  # GNOConv: + GEMMs, cotangent scale, split-K reduce
+        self.launches_fwd = (2 if self.has_node else 1) + (1 if factored else 0)
+        self.launches_bwd = (8 if self.has_node else 5) + (4 if factored else 0)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         if use_cuda_graph:
             self.capture()

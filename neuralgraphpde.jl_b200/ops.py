@@ -40,6 +40,20 @@ def _workspace(nbytes: int, device) -> Tensor:
 _FAMILY_FN = {0: "explicit_edge_conv", 1: "vmh_conv", 2: "mppde_conv", 3: "gno_conv"}
 
 
+def _factored(lib, handle, desc) -> bool:
+    """True when this layer call takes the factored GNOConv evaluation (extra GEMM / scale / reduce launches)."""
+    cached = getattr(desc, "_ngpde_factored", None)
+    if cached is None or cached[0] != handle:
+        out = (C.c_int32 * 4)()
+        _lib.check(lib.ngpde_conv_kernel_paths(handle, C.byref(desc), out))
+        cached = (handle, out[0] == 2)
+        try:
+            desc._ngpde_factored = cached
+        except AttributeError:
+            pass
+    return cached[1]
+
+
 class ConvFunction(torch.autograd.Function):
     """y = layer(x; phi_params, node_params) for the four MLP message-passing families."""
 
@@ -64,7 +78,7 @@ class ConvFunction(torch.autograd.Function):
             ws = _workspace(nbytes, dev)
             fn = getattr(lib, f"ngpde_{_FAMILY_FN[desc.family]}_forward")
             _lib.check(fn(handle, C.byref(desc), C.byref(io), ws.data_ptr(), ws.numel(), _stream(dev)))
-        LAUNCHES["count"] += 2 if has_node else 1
+        LAUNCHES["count"] += (2 if has_node else 1) + (1 if _factored(lib, handle, desc) else 0)
         ctx.save_for_backward(x, phi_params, node_params if node_params is not None else x.new_empty(0), mbar)
         ctx.handle, ctx.desc = handle, desc
         ctx.static = (snode, edata, theta)
@@ -93,7 +107,7 @@ class ConvFunction(torch.autograd.Function):
                              dphi_params=_ptr(dphi), dnode_params=_ptr(dnode))
             fn = getattr(lib, f"ngpde_{_FAMILY_FN[desc.family]}_backward")
             _lib.check(fn(handle, C.byref(desc), C.byref(io), ws.data_ptr(), ws.numel(), _stream(dev)))
-        LAUNCHES["count"] += 8 if ctx.has_node else 5
+        LAUNCHES["count"] += (8 if ctx.has_node else 5) + (4 if _factored(lib, handle, desc) else 0)
         return dx, dphi, dnode, None, None, None, None, None, None, None
 
 
