@@ -167,22 +167,45 @@ __device__ __forceinline__ void tile_outer(float* __restrict__ dW, int ldw, floa
       for (int r = 0; r < 8; ++r) ap[r] = A + (size_t)min(kb + kt + 8 * r, K - 1) * C::LD;
 #pragma unroll
       for (int c = 0; c < 4; ++c) bp[c] = B + (size_t)min(nb + nt + 16 * c, N - 1) * C::LD;
+      // rows this thread really owns in the block (a narrow first layer, K = 6, would otherwise cost a full 64-row block)
+      const int nr = min(8, max(0, (K - kb - kt + 7) >> 3));
+      if (nr == 8) {
 #pragma unroll 2
-      for (int e = 0; e < TE; e += 4) {
-        float4 a[8], b[4];
+        for (int e = 0; e < TE; e += 4) {
+          float4 a[8], b[4];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float4*>(ap[r] + e);
+          for (int r = 0; r < 8; ++r) a[r] = *reinterpret_cast<const float4*>(ap[r] + e);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4*>(bp[c] + e);
+          for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4*>(bp[c] + e);
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+          for (int r = 0; r < 8; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            acc[r][c] = fmaf(a[r].x, b[c].x, acc[r][c]);
-            acc[r][c] = fmaf(a[r].y, b[c].y, acc[r][c]);
-            acc[r][c] = fmaf(a[r].z, b[c].z, acc[r][c]);
-            acc[r][c] = fmaf(a[r].w, b[c].w, acc[r][c]);
+            for (int c = 0; c < 4; ++c) {
+              acc[r][c] = fmaf(a[r].x, b[c].x, acc[r][c]);
+              acc[r][c] = fmaf(a[r].y, b[c].y, acc[r][c]);
+              acc[r][c] = fmaf(a[r].z, b[c].z, acc[r][c]);
+              acc[r][c] = fmaf(a[r].w, b[c].w, acc[r][c]);
+            }
+        }
+      } else {
+        for (int e = 0; e < TE; e += 4) {
+          float4 b[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4*>(bp[c] + e);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (r < nr) {
+              const float4 a = *reinterpret_cast<const float4*>(ap[r] + e);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                acc[r][c] = fmaf(a.x, b[c].x, acc[r][c]);
+                acc[r][c] = fmaf(a.y, b[c].y, acc[r][c]);
+                acc[r][c] = fmaf(a.z, b[c].z, acc[r][c]);
+                acc[r][c] = fmaf(a.w, b[c].w, acc[r][c]);
+              }
+            }
           }
+        }
       }
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
