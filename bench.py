@@ -177,13 +177,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--partition", action="store_true",
                     help="N>1: split ONE graph over the ranks by nodes with a per-step halo exchange (strong scaling) "
                          "instead of one graph per rank (weak scaling)")
     ap.add_argument("--halo", default="nccl", choices=["nccl", "put"], help="halo transfer: NCCL all-to-all or peer stores")
     ap.add_argument("--nodes", type=int, default=0, help="override the node count of c4 (default 1,000,000)")
     ap.add_argument("--cuda-graph", action="store_true", help="replay fwd+bwd from a captured CUDA graph")
+    ap.add_argument("--graphs", type=int, default=0, help="c5: total number of 64x64 graphs in the ensemble (default 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (reported under config)")
     args = ap.parse_args()
@@ -210,6 +211,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     wkw = {"n_nodes": args.nodes} if (args.workload == "c4" and args.nodes) else {}
+    chain = args.workload == "c5"
+    if chain:
+        # the ensemble config: 512 graphs in total, whole graphs per rank (no data-path collective, dW all-reduce)
+        wkw = {"n_graphs": max(1, (args.graphs or 512) // world)}
     w = workloads.WORKLOADS[args.workload](dev, **wkw)
     K, W = args.steps, args.warmup
     gen = torch.Generator().manual_seed(1234)
@@ -222,6 +227,14 @@ def main():
         runner = prunner.runner
         prunner.dy_owned.copy_(torch.randn(tuple(prunner.dy_owned.shape), generator=gen).to(dev))
         one_step = prunner.step
+    elif chain:
+        runner = engine.ChainRhsRunner(w.layer, w.x, w.ps, w.st)
+        runner.dy.copy_(torch.randn(tuple(runner.dy.shape), generator=gen).to(dev))
+
+        def one_step():
+            runner.step()
+            if world > 1:
+                dist.all_reduce(runner.dparams)
     else:
         runner = engine.RhsRunner(w.layer, w.x, w.ps, w.st)
         runner.dy.copy_(torch.randn(tuple(runner.dy.shape), generator=gen).to(dev))
@@ -380,9 +393,12 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if chain else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_label(args.workload), "nodes_per_gpu": w.n_nodes, "edges_per_gpu": w.n_edges,
+                   **({"graphs_per_gpu": wkw["n_graphs"], "graphs_total": wkw["n_graphs"] * world,
+                       "chain": "GCNConv(2=>64,tanh) -> GCNConv(64=>64,tanh) -> VMHConv; the roofline block covers the "
+                                "VMHConv kernels only (the GCN aggregate is HBM-bound: DESIGN.md section 4)"} if chain else {}),
                    "step": "one RHS evaluation: layer forward + VJP w.r.t. (x, ps)", "aggr": "mean",
                    "l2": "warm (--no-flush)" if flush is None else "flushed between steps (256 MiB memset, untimed)",
                    "parallelism": "1 graph per GPU, dW all-reduce over NCCL" if world > 1 else "single GPU",

@@ -97,6 +97,42 @@ class RhsRunner:
             self.backward()
 
 
+class ChainRhsRunner:
+    """Forward + VJP of a Lux `Chain` of graph layers (C5: GCNConv -> GCNConv -> VMHConv) through the autograd bridge: every
+    layer call and every pullback goes through the C ABI (`ops.ConvFunction` / `ops.GcnFunction`), torch only links them.
+    Same surface as `RhsRunner` where `bench.py` needs it (`y`, `dy`, `step()`, `grads`, `handle`/`desc` of the last
+    message-passing layer for the kernel-path query)."""
+
+    def __init__(self, layer, x: Tensor, ps, st):
+        self.layer, self.st = layer, st
+        self.ca = ComponentArray(ps)
+        self.ca.data.requires_grad_(True)
+        self.x = x.detach().clone().requires_grad_(True)
+        # one eager pass: output shape, and the descriptor of the last layer that has a fused MLP
+        h = self.x.detach()
+        self.handle = self.desc = None
+        for i, l in enumerate(layer.layers):
+            k = f"layer_{i + 1}"
+            if hasattr(l, "prepare"):
+                pr = l.prepare(h, getattr(ps, k), st[k])
+                self.handle, self.desc = pr[3], pr[4]
+            h, _ = l(h, getattr(ps, k), st[k])
+        self.y = h.detach().T.contiguous()  # [N, d], the row-major image of Julia's (d, N)
+        self.dy = torch.zeros_like(self.y)
+        self.grads = [self.ca.data]
+
+    def step(self):
+        self.x.grad = None
+        self.ca.data.grad = None
+        y, _ = self.layer(self.x, self.ca, self.st)
+        y.backward(self.dy.T)
+        return y
+
+    @property
+    def dparams(self) -> Tensor:
+        return self.ca.data.grad
+
+
 class PartitionedRhsRunner:
     """RhsRunner over this rank's share of a node-partitioned graph (distributed.PartitionedLayer): every step exchanges
     the boundary rows of x, runs the local forward + VJP, sends the halo cotangents home and all-reduces the flat

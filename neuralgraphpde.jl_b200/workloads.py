@@ -246,7 +246,8 @@ def c5_gcn_vmh(device="cuda", n_graphs: int = 512, side: int = 64, hidden: int =
     fn = _mlp_flops([(2 * h, h), (h, 2)])
     bf, bb = _bytes(N, E, h, 2, 0, 2, layer.parameterlength())
     return Workload("C5 GCNConv+VMHConv %d x %dx%d grid-8 h%d" % (n_graphs, side, side, h), layer, ps, st,
-                    _x(rng, 2, N, device), g, N, E, float(f_gcn + E * fe + N * fn), bf, bb, rhs_per_step=4)
+                    _x(rng, 2, N, device), g, N, E, float(f_gcn + E * fe + N * fn), bf, bb, rhs_per_step=4,
+                    notes={"flops_edge_fwd": float(E * fe), "flops_node_fwd": float(N * fn)})
 
 
 WORKLOADS = {"c1": c1_edgeconv, "c2": c2_mppde, "c3": c3_vmh, "c4": c4_gno, "c5": c5_gcn_vmh}
