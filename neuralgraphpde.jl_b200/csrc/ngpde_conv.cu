@@ -719,8 +719,9 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   const float* gB = p.contract == 2 ? io->phi_params + p.phi.w_off[p.phi.L - 1] : nullptr;
 
   NGPDE_CUDA_TRY(cudaMemsetAsync(part_phi, 0, L.total - L.off_part_phi, st));
-  transpose_weights_kernel<<<64, 256, 0, st>>>(io->phi_params, wt_phi, p.phi);
-  if (p.has_node) transpose_weights_kernel<<<64, 256, 0, st>>>(io->node_params, wt_node, p.node);
+  // the transposed weights feed the FFMA kernels' input-gradient GEMMs only (the tensor-core kernels read their own image)
+  if (!L.tce.on) transpose_weights_kernel<<<64, 256, 0, st>>>(io->phi_params, wt_phi, p.phi);
+  if (p.has_node && !L.tcn.on) transpose_weights_kernel<<<64, 256, 0, st>>>(io->node_params, wt_node, p.node);
 
   // ---- node phase: dy -> (dx_direct, dmbar, dnode_params) ----
   if (p.has_node) {
