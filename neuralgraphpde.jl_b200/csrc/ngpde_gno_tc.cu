@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(TGT) gno_gemm_tc_nloop_kernel(const TcGemmArgs
   };
   // epilogue of tile t: TMEM -> registers (thread = row) -> warp-private swizzled patch -> coalesced stores (a row's 256
   // bytes by 16 lanes; written row-per-thread the stores are 32 half-filled sectors per instruction: 2.7 -> 1.9 ms at C4)
-  float* patch = smem + 2 * NSTAGE + TBM * TBK + (tid >> 5) * (32 * TBN);
+  float* patch = smem + 2 * NSTAGE + (tid >> 5) * (32 * TBN);  // shares its memory with the prologue's A patches
   const int lane = tid & 31;
   auto epilogue = [&](int t) {
     const int sb = t & 1;
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(TGT) gno_gemm_tc_nloop_kernel(const TcGemmArgs
 
 template <int KB>
 int launch_nloop(const TcGemmArgs& g, cudaStream_t st) {
-  constexpr int bytes = (2 * KB * 2 * B_IMG + TBM * TBK + TBM * TBN) * 4 + 1024;  // stages | A patch | epilogue patch
+  constexpr int bytes = (2 * KB * 2 * B_IMG + TBM * TBN) * 4 + 1024;  // stages | A patch (prologue) = epilogue patch: 97 KB, two CTAs per SM
   static bool configured = false;
   if (!configured) {
     NGPDE_CUDA_TRY(cudaFuncSetAttribute(gno_gemm_tc_nloop_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
