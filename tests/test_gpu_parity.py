@@ -588,6 +588,19 @@ def test_tensor_core_backward_is_deterministic():
     assert all(torch.equal(u, v) for u, v in zip(a, b))
 
 
+def test_chain_runner_matches_the_autograd_path():
+    """engine.ChainRhsRunner (what `bench.py --workload c5` times) is the same computation as a plain layer call + backward."""
+    from ngpde import engine
+    w = workloads.c5_gcn_vmh(DEV, n_graphs=2, side=10)
+    r = engine.ChainRhsRunner(w.layer, w.x, w.ps, w.st)
+    dy = torch.randn(tuple(r.dy.shape), generator=torch.Generator().manual_seed(3)).to(DEV)
+    r.dy.copy_(dy)
+    y = r.step()
+    y0, dx0, dp0 = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy.T)
+    assert torch.equal(y.detach(), y0) and torch.equal(r.x.grad, dx0) and torch.equal(r.dparams, dp0)
+    assert r.handle is not None and ngpde._lib.kernel_paths(r.handle, r.desc)["fwd_edge"] in (0, 1)
+
+
 def test_kernel_path_query_reports_the_engine_that_runs():
     """ngpde_conv_kernel_paths: C3 runs all four fused kernels on tcgen05; with the option off, or for GNOConv's bilinear
     contraction, the FP32-FFMA engine takes over (bench.py labels its roofline line with this)."""
