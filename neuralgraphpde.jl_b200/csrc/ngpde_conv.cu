@@ -5,11 +5,54 @@
 #include <utility>
 #include <vector>
 
-#include "ngpde_conv_kernels.cuh"
+#include "ngpde_conv_launch.cuh"
+#include "ngpde_gno_tile.cuh"
 #include "ngpde_tc_layout.cuh"
 #include "ngpde_gno.cuh"
 
 namespace ngpde {
+
+// ---- small epilogue kernels ----
+
+// wt[w_off + n*K + k] = params[w_off + k*N + n] for every layer
+__global__ void transpose_weights_kernel(const float* __restrict__ params, float* __restrict__ wt, MlpDev mlp) {
+  for (int l = 0; l < mlp.L; ++l) {
+    const int K = mlp.dims[l], N = mlp.dims[l + 1];
+    const float* W = params + mlp.w_off[l];
+    float* T = wt + mlp.w_off[l];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * N; i += gridDim.x * blockDim.x) {
+      const int n = i / K, k = i - n * K;
+      T[i] = W[(size_t)k * N + n];
+    }
+  }
+}
+
+// dparams[p] = sum over CTAs of partial[cta][p], in ascending CTA order (deterministic)
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int ncta, int P, float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float s = 0.f;
+  for (int c = 0; c < ncta; ++c) s += partial[(size_t)c * P + p];
+  out[p] = s;
+}
+
+// dx[i][c] = dx_direct[i][c] + dxdst[i][c] + sum over out-edges of i (src-sorted, stable) of desrc[edge][c]
+__global__ void dx_combine_kernel(const float* __restrict__ dx_direct, const float* __restrict__ dxdst,
+                                  const float* __restrict__ desrc, const int* __restrict__ tptr,
+                                  const int* __restrict__ tpos, int N, int dx, float* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * dx) return;
+  const int i = (int)(idx / dx), c = (int)(idx - (size_t)i * dx);
+  float s = 0.f;
+  if (dx_direct) s = dx_direct[idx];
+  if (dxdst) s += dxdst[idx];
+  if (desrc) {
+    for (int q = tptr[i]; q < tptr[i + 1]; ++q) s += desrc[(size_t)tpos[q] * dx + c];
+  }
+  out[idx] = s;
+}
+
+
 namespace {
 
 // ---- optional per-kernel timing (ngpde_profile_*): CUDA events recorded on the launching stream around the four
@@ -284,51 +327,6 @@ int pick_tile(F bytes_for, int* te_out, int* bytes_out) {
   return NGPDE_ERR_UNSUPPORTED;
 }
 
-template <class K>
-int launch_cfg(K kernel, int smem_bytes, int n_units, int num_sms, int* grid) {
-  NGPDE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  int occ = 0;
-  NGPDE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NT, smem_bytes));
-  if (occ < 1) {
-    set_error("kernel cannot be resident with %d bytes of shared memory", smem_bytes);
-    return NGPDE_ERR_UNSUPPORTED;
-  }
-  *grid = std::max(1, std::min(n_units, occ * num_sms));
-  return NGPDE_OK;
-}
-
-template <bool NODE>
-int launch_fwd(int te, const FwdArgs& a, int smem_bytes, int num_sms, cudaStream_t st) {
-  int grid = 0;
-  if (a.tg.n_units <= 0) return NGPDE_OK;
-#define NGPDE_LAUNCH_FWD(TE)                                                          \
-  {                                                                                   \
-    if (int rc = launch_cfg(mp_fwd_kernel<TE, NODE>, smem_bytes, a.tg.n_units, num_sms, &grid)) return rc; \
-    mp_fwd_kernel<TE, NODE><<<grid, NT, smem_bytes, st>>>(a);                         \
-  }
-  if (te == 128) NGPDE_LAUNCH_FWD(128) else if (te == 64) NGPDE_LAUNCH_FWD(64) else NGPDE_LAUNCH_FWD(32)
-#undef NGPDE_LAUNCH_FWD
-  NGPDE_CUDA_TRY(cudaGetLastError());
-  return NGPDE_OK;
-}
-
-template <bool NODE>
-int bwd_grid(int te, int smem_bytes, int n_units, int num_sms, int* grid) {
-  if (te == 128) return launch_cfg(mp_bwd_kernel<128, NODE>, smem_bytes, n_units, num_sms, grid);
-  if (te == 64) return launch_cfg(mp_bwd_kernel<64, NODE>, smem_bytes, n_units, num_sms, grid);
-  return launch_cfg(mp_bwd_kernel<32, NODE>, smem_bytes, n_units, num_sms, grid);
-}
-
-template <bool NODE>
-int launch_bwd(int te, const BwdArgs& a, int smem_bytes, int grid, cudaStream_t st) {
-  if (a.tg.n_units <= 0) return NGPDE_OK;
-  if (te == 128) mp_bwd_kernel<128, NODE><<<grid, NT, smem_bytes, st>>>(a);
-  else if (te == 64) mp_bwd_kernel<64, NODE><<<grid, NT, smem_bytes, st>>>(a);
-  else mp_bwd_kernel<32, NODE><<<grid, NT, smem_bytes, st>>>(a);
-  NGPDE_CUDA_TRY(cudaGetLastError());
-  return NGPDE_OK;
-}
-
 int tile_index(int te) { return te == 32 ? 0 : (te == 64 ? 1 : 2); }
 
 void fill_arrays(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, const ngpde_conv_io& io,
@@ -384,7 +382,7 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
             &L->te_e, &L->smem_e))
       return rc;
     L->se = bwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, d.aggr, false, p.edge_need_dz0, L->te_e, p.gno_Ka);
-    if (int rc = bwd_grid<false>(L->te_e, L->smem_e, std::max(1, g->n_units[tile_index(L->te_e)]), g->num_sms, &L->grid_e))
+    if (int rc = bwd_grid_edge(L->te_e, L->smem_e, std::max(1, g->n_units[tile_index(L->te_e)]), g->num_sms, &L->grid_e))
       return rc;
   }
   L->te_n = 0; L->smem_n = 0; L->grid_n = 0;
@@ -399,7 +397,7 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
         return rc;
       L->sn = bwd_smem(p.node, 0, 0, 0, d.aggr, true, true, L->te_n);
       const int nu = (int)((g->N + L->te_n - 1) / L->te_n);
-      if (int rc = bwd_grid<true>(L->te_n, L->smem_n, std::max(1, nu), g->num_sms, &L->grid_n)) return rc;
+      if (int rc = bwd_grid_node(L->te_n, L->smem_n, std::max(1, nu), g->num_sms, &L->grid_n)) return rc;
     }
   }
   size_t off = 0;
@@ -449,7 +447,7 @@ int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* param
   n.dout = mlp.dims[mlp.L];
   n.out = y;
   n.offA = fs.offA; n.offB = fs.offB; n.offW = fs.offW; n.offH = fs.offH;
-  return launch_fwd<true>(te, n, smem, g->num_sms, st);
+  return launch_fwd_node(te, n, smem, g->num_sms, st);
 }
 
 namespace {
@@ -463,7 +461,7 @@ int node_bwd_layout(const ngpde_graph* g, const MlpDev& mlp, NodeBwdLayout* L) {
     return rc;
   L->s = bwd_smem(mlp, 0, 0, 0, 0, true, true, L->te);
   const int nu = (int)((g->N + L->te - 1) / L->te);
-  if (int rc = bwd_grid<true>(L->te, L->smem, std::max(1, nu), g->num_sms, &L->grid)) return rc;
+  if (int rc = bwd_grid_node(L->te, L->smem, std::max(1, nu), g->num_sms, &L->grid)) return rc;
   size_t off = 0;
   L->off_wt = off;   off = align256(off + sizeof(float) * mlp.n_params);
   L->off_part = off; off = align256(off + sizeof(float) * (size_t)L->grid * mlp.n_params);
@@ -511,7 +509,7 @@ int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* para
   n.store_last = L.s.store_last;
   std::memcpy(n.zoff, L.s.zoff, sizeof(n.zoff));
   n.offG0 = L.s.offG0; n.offG1 = L.s.offG1; n.offW = L.s.offW;
-  if (int rc = launch_bwd<true>(L.te, n, L.smem, L.grid, st)) return rc;
+  if (int rc = launch_bwd_node(L.te, n, L.smem, L.grid, st)) return rc;
   reduce_partials_kernel<<<(mlp.n_params + 255) / 256, 256, 0, st>>>(part, L.grid, mlp.n_params, dparams);
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;
@@ -641,7 +639,7 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
       if (int rc = launch_fwd_tc(false, g->num_sms, fp.edge, p.phi, io->phi_params, a, reinterpret_cast<float*>(fws + fp.edge.ws_off), st))
         return rc;
     } else {
-      if (int rc = launch_fwd<false>(te, a, smem, g->num_sms, st)) return rc;
+      if (int rc = launch_fwd_edge(te, a, smem, g->num_sms, st)) return rc;
     }
     if (p.contract == 2) {
       // mbar = (S B) ./ deg,  B = [W3; b3] = the last layer's flat parameter segment viewed as [Ka*gin][gout]
@@ -676,7 +674,7 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
       if (int rc = launch_fwd_tc(true, g->num_sms, fp.node, p.node, io->node_params, n, reinterpret_cast<float*>(fws + fp.node.ws_off), st))
         return rc;
     } else {
-      if (int rc = launch_fwd<true>(te, n, smem, g->num_sms, st)) return rc;
+      if (int rc = launch_fwd_node(te, n, smem, g->num_sms, st)) return rc;
     }
   }
   return NGPDE_OK;
@@ -755,7 +753,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
         n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
         if (int rc = launch_bwd_tc(true, L.tcn, p.node, n, reinterpret_cast<float*>(ws + L.tcn.ws_off), st)) return rc;
       } else {
-        if (int rc = launch_bwd<true>(te, n, L.smem_n, L.grid_n, st)) return rc;
+        if (int rc = launch_bwd_node(te, n, L.smem_n, L.grid_n, st)) return rc;
       }
     }
     const int P = p.node.n_params;
@@ -809,7 +807,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
         a.tg.n_units = g->n_units[2];
         if (int rc = launch_bwd_tc(false, L.tce, p.phi, a, reinterpret_cast<float*>(ws + L.tce.ws_off), st)) return rc;
       } else {
-        if (int rc = launch_bwd<false>(te, a, L.smem_e, L.grid_e, st)) return rc;
+        if (int rc = launch_bwd_edge(te, a, L.smem_e, L.grid_e, st)) return rc;
       }
       if (p.contract == 2) {
         // dB = S' DM over the nodes, split-K slices reduced in fixed order

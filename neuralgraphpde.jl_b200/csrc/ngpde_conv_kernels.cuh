@@ -631,44 +631,4 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
   }
 }
 
-// ---- small epilogue kernels ----
-
-// wt[w_off + n*K + k] = params[w_off + k*N + n] for every layer
-__global__ void transpose_weights_kernel(const float* __restrict__ params, float* __restrict__ wt, MlpDev mlp) {
-  for (int l = 0; l < mlp.L; ++l) {
-    const int K = mlp.dims[l], N = mlp.dims[l + 1];
-    const float* W = params + mlp.w_off[l];
-    float* T = wt + mlp.w_off[l];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * N; i += gridDim.x * blockDim.x) {
-      const int n = i / K, k = i - n * K;
-      T[i] = W[(size_t)k * N + n];
-    }
-  }
-}
-
-// dparams[p] = sum over CTAs of partial[cta][p], in ascending CTA order (deterministic)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int ncta, int P, float* __restrict__ out) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  float s = 0.f;
-  for (int c = 0; c < ncta; ++c) s += partial[(size_t)c * P + p];
-  out[p] = s;
-}
-
-// dx[i][c] = dx_direct[i][c] + dxdst[i][c] + sum over out-edges of i (src-sorted, stable) of desrc[edge][c]
-__global__ void dx_combine_kernel(const float* __restrict__ dx_direct, const float* __restrict__ dxdst,
-                                  const float* __restrict__ desrc, const int* __restrict__ tptr,
-                                  const int* __restrict__ tpos, int N, int dx, float* __restrict__ out) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)N * dx) return;
-  const int i = (int)(idx / dx), c = (int)(idx - (size_t)i * dx);
-  float s = 0.f;
-  if (dx_direct) s = dx_direct[idx];
-  if (dxdst) s += dxdst[idx];
-  if (desrc) {
-    for (int q = tptr[i]; q < tptr[i + 1]; ++q) s += desrc[(size_t)tpos[q] * dx + c];
-  }
-  out[idx] = s;
-}
-
 }  // namespace ngpde
