@@ -357,6 +357,7 @@ int check_io(const ngpde_conv_desc& d, const Plan& p, const ngpde_conv_io& io, b
 }
 
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 struct BwdLayout {
   int te_e, smem_e, grid_e;
@@ -365,7 +366,7 @@ struct BwdLayout {
   TcBwdPhase tce, tcn;  // tensor-core variants of the two phases (when eligible)
   size_t off_wt_phi, off_wt_node, off_dmbar, off_dxdirect, off_dxdst, off_desrc, off_part_phi, off_part_node, total;
   // factored GNO
-  size_t off_S = 0, off_T = 0, off_DM = 0, off_dBpart = 0;
+  size_t off_S = 0, off_T = 0, off_DM = 0, off_dBpart = 0, off_B = 0;
   int part_stride = 0, gno_splits = 1;
 };
 
@@ -418,6 +419,7 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
     L->off_T = off;      off = align256(off + sizeof(float) * (size_t)g->N * R);
     L->off_DM = off;     off = align256(off + sizeof(float) * (size_t)g->N * d.gno_out);
     L->off_dBpart = off; off = align256(off + sizeof(float) * (size_t)L->gno_splits * R * d.gno_out);
+    L->off_B = off;      off = align256(off + sizeof(float) * R * d.gno_out);
   }
   L->off_part_phi = off;  off = align256(off + sizeof(float) * (size_t)L->grid_e * L->part_stride);
   L->off_part_node = off; off = align256(off + sizeof(float) * (size_t)L->grid_n * p.node.n_params);
@@ -524,7 +526,7 @@ namespace {
 struct FwdPlan {
   TcPhase edge, node;
   size_t ws_bytes = 0;
-  size_t off_S = 0;
+  size_t off_S = 0, off_B = 0;
 };
 
 FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin) {
@@ -550,6 +552,8 @@ FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin) {
   if (p.contract == 2) {
     f.off_S = off;
     off = align256(off + sizeof(float) * (size_t)N * p.gno_Ka * gin);
+    f.off_B = off;  // 16-byte aligned copy of B = [W3; b3] for when the flat parameter segment is not
+    off = align256(off + sizeof(float) * (size_t)p.gno_Ka * gin * p.dm);
   }
   f.ws_bytes = off;
   return f;
@@ -644,7 +648,15 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
     if (p.contract == 2) {
       // mbar = (S B) ./ deg,  B = [W3; b3] = the last layer's flat parameter segment viewed as [Ka*gin][gout]
       const int R = p.gno_Ka * desc->gno_in;
-      if (int rc = gno_gemm(a.gno_S, R, false, io->phi_params + p.phi.w_off[p.phi.L - 1], desc->gno_out, true, io->mbar,
+      NGPDE_REQUIRE(aligned16(io->x) && aligned16(io->mbar),
+                    "GNOConv (factored evaluation): x and mbar must be 16-byte aligned (or set NGPDE_OPT_GNO_FACTORED = 0)");
+      const float* gB = io->phi_params + p.phi.w_off[p.phi.L - 1];
+      if (!aligned16(gB)) {
+        float* cp = reinterpret_cast<float*>(fws + fp.off_B);
+        NGPDE_CUDA_TRY(cudaMemcpyAsync(cp, gB, sizeof(float) * (size_t)R * desc->gno_out, cudaMemcpyDeviceToDevice, st));
+        gB = cp;
+      }
+      if (int rc = gno_gemm(a.gno_S, R, false, gB, desc->gno_out, true, io->mbar,
                             desc->gno_out, g->N, desc->gno_out, R, 1,
                             desc->aggr == NGPDE_AGGR_MEAN ? g->rowptr : nullptr, st))
         return rc;
@@ -715,6 +727,14 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   float* gdB = reinterpret_cast<float*>(ws + L.off_dBpart);
   const int gR = p.gno_Ka * desc->gno_in;
   const float* gB = p.contract == 2 ? io->phi_params + p.phi.w_off[p.phi.L - 1] : nullptr;
+  if (p.contract == 2) {
+    NGPDE_REQUIRE(aligned16(io->x), "GNOConv (factored evaluation): x must be 16-byte aligned (or set NGPDE_OPT_GNO_FACTORED = 0)");
+    if (!aligned16(gB)) {  // the flat parameter segment may start anywhere: the GEMMs read B with 128-bit loads
+      float* cp = reinterpret_cast<float*>(ws + L.off_B);
+      NGPDE_CUDA_TRY(cudaMemcpyAsync(cp, gB, sizeof(float) * (size_t)gR * desc->gno_out, cudaMemcpyDeviceToDevice, st));
+      gB = cp;
+    }
+  }
 
   NGPDE_CUDA_TRY(cudaMemsetAsync(part_phi, 0, L.total - L.off_part_phi, st));
   // the transposed weights feed the FFMA kernels' input-gradient GEMMs only (the tensor-core kernels read their own image)

@@ -320,6 +320,41 @@ def test_gno_conv_factored_and_per_edge_paths(factored, aggr, phi_bias, depth, c
         ngpde._lib.set_option(ngpde._lib.OPT_GNO_FACTORED, 1)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_gno_conv_factored_vs_per_edge_random_shapes(seed):
+    """Random widths / depths / degree distributions (hubs, isolated nodes, duplicate edges): the factored evaluation and the
+    per-edge contraction are two routes to the same numbers."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(5, 400))
+    e = int(rng.integers(1, 6 * n))
+    cin = int(rng.choice([8, 16, 24, 40, 64, 72]))
+    cout = int(rng.choice([4, 8, 12, 36, 64, 68]))
+    hid = int(rng.integers(1, 70))
+    depth = int(rng.integers(1, 4))
+    s, t = rng.integers(0, n, e), rng.integers(0, n, e)
+    if seed % 3 == 0:
+        t[: e // 2] = int(rng.integers(0, n))  # a hub: one row spanning several tiles
+    de = int(rng.integers(0, 3))
+    g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"x": jl_rand(rng, 2, n)},
+                 edata={"e": jl_rand(rng, de, e)} if de else None).to(DEV)
+    dims = [4 + de] + [hid] * (depth - 1) + [cin * cout]
+    layers = [Dense(dims[i], dims[i + 1], ["tanh", "relu", "swish"][seed % 3] if i < depth - 1 else "identity",
+                    bias=bool((seed + i) % 2) or i < depth - 1) for i in range(depth)]
+    layer = GNOConv((cin, cout), layers[0] if depth == 1 else Chain(*layers), "tanh", initialgraph=g,
+                    aggr="mean" if seed % 2 else "+", bias=bool(seed % 4))
+    ps, st = setup(rng, layer, DEV)
+    x = jl_rand(rng, cin, n, DEV)
+    dy = torch.from_numpy(rng.standard_normal((cout, n)).astype(np.float32)).to(DEV)
+    a = product_fwd_bwd(layer, x, ps, st, dy)
+    ngpde._lib.set_option(ngpde._lib.OPT_GNO_FACTORED, 0)
+    try:
+        b = product_fwd_bwd(layer, x, ps, st, dy)
+    finally:
+        ngpde._lib.set_option(ngpde._lib.OPT_GNO_FACTORED, 1)
+    for u, v in zip(a, b):
+        assert torch.isfinite(u).all() and relerr(u, v) <= TOL
+
+
 def test_gno_conv_factored_matches_per_edge_at_c4_widths():
     w = workloads.c4_gno(DEV, n_nodes=6000)
     dy = torch.randn(64, w.n_nodes, generator=torch.Generator().manual_seed(2)).to(DEV)
