@@ -414,7 +414,20 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
   if (p.contract == 2) {
     const size_t R = (size_t)p.gno_Ka * d.gno_in;
     L->part_stride = p.phi.w_off[p.phi.L - 1];  // the last layer's gradient comes from the GEMM dB = S' DM
-    L->gno_splits = (int)std::min<int64_t>(32, std::max<int64_t>(1, g->N / 1024));
+    // split-K slices of dB = S' DM: m-tiles x slices should fill whole waves of 2 CTAs per SM
+    {
+      const int mt = (int)((R + 127) / 128);
+      const int per_wave = 2 * g->num_sms;
+      int best = 1;
+      double best_cost = 1e30;
+      for (int sp = 1; sp <= 48; ++sp) {
+        if ((int64_t)sp * 1024 > g->N && sp > 1) break;
+        const int waves = (mt * sp + per_wave - 1) / per_wave;
+        const double cost = (double)waves / sp;  // time ~ waves x (K / slices)
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = sp; }
+      }
+      L->gno_splits = best;
+    }
     L->off_S = off;      off = align256(off + sizeof(float) * (size_t)g->N * R);
     L->off_T = off;      off = align256(off + sizeof(float) * (size_t)g->N * R);
     L->off_DM = off;     off = align256(off + sizeof(float) * (size_t)g->N * d.gno_out);

@@ -142,7 +142,7 @@ __device__ __forceinline__ void gno_apply_T(const float* __restrict__ Ts, int ld
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] = 0.f;
       const float* tp = Ts + i0;
-#pragma unroll 2
+#pragma unroll 4
       for (int j4 = 0; j4 < Ka4; j4 += 4) {
         float z[4];
         *reinterpret_cast<float4*>(&z[0]) = *reinterpret_cast<const float4*>(zrow + j4);
@@ -171,7 +171,7 @@ __device__ __forceinline__ void gno_apply_T(const float* __restrict__ Ts, int ld
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] = 0.f;
       const float* tp = Ts + j0 * lds;  // rows j0..j0+7 exist up to Ka4 >= K; rows >= K are never written out
-#pragma unroll 2
+#pragma unroll 4
       for (int i4 = 0; i4 < gin; i4 += 4) {
         const float4 h = *reinterpret_cast<const float4*>(hrow + i4);
 #pragma unroll
