@@ -46,6 +46,30 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def lib_sha256() -> str:
+    import hashlib
+    path = os.path.join(ROOT, "neuralgraphpde.jl_b200", "libngpde.so")
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 20), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
+def committed_traffic(workload: str, kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), valid only for
+    the build it was captured on: the file records the sha256 of libngpde.so and a stale capture is reported as null."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tpath):
+        return None, "no capture committed"
+    with open(tpath) as f:
+        t = json.load(f)
+    sha = lib_sha256()
+    if t.get("lib_sha256") != sha:
+        return None, f"capture is of another build (captured {str(t.get('lib_sha256'))[:12]}, benched {sha[:12]})"
+    return t.get(workload, {}).get(kernel), f"profiles/traffic.json (ncu --set full, build {sha[:12]})"
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -130,7 +154,8 @@ def cpu_reference_step_fn(workload_name: str, sample_kw: dict):
     return step, w
 
 
-CPU_SAMPLE = {"c1": {}, "c2": {}, "c3": {"side": 128}, "c4": {"n_nodes": 15625}, "c5": {"n_graphs": 8}}
+# bounded CPU samples of each workload ({} = the workload itself, at full size: C3 is 0.2-0.3 s per fwd+bwd on 16 cores)
+CPU_SAMPLE = {"c1": {}, "c2": {}, "c3": {}, "c4": {"n_nodes": 15625}, "c5": {"n_graphs": 8}}
 
 
 def run_reference(args, rank: int):
@@ -146,7 +171,8 @@ def run_reference(args, rank: int):
         step()
     dt = time.perf_counter() - t0
     val = w.n_edges * args.steps / dt
-    sample = f"{w.name}: {w.n_nodes} nodes / {w.n_edges} edges per step (kwargs {sample_kw})"
+    sample = (f"{w.name}: {w.n_nodes} nodes / {w.n_edges} edges per step "
+              f"({'the full workload' if not sample_kw else 'reduced: ' + str(sample_kw)})")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -171,6 +197,175 @@ def workload_label(name: str) -> str:
     }[name]
 
 
+class Timer:
+    """K steps bracketed by barrier + synchronize on both sides, every step timed with CUDA events on the launching
+    stream, L2 flushed (untimed) between steps; the result is the MAX over ranks of the summed step times."""
+
+    def __init__(self, dev, world, flush):
+        self.dev, self.world, self.flush = dev, world, flush
+
+    def sync_all(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def __call__(self, fn, k):
+        evs = []
+        self.sync_all()
+        for _ in range(k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+            if self.flush is not None:
+                self.flush.zero_()
+        self.sync_all()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+
+def roofline_block(workload, w, prof, K, paths, step_ms, peaks, edges_launch, nodes_launch):
+    """`roofline` object for the dominant fused kernel.  `edges_launch` / `nodes_launch` are the units ONE launch on THIS
+    rank processes (a node-partitioned rank holds 1/world of the graph: its flops, not the global graph's)."""
+    dom = max(prof, key=lambda k: prof[k][0])
+    dom_ms = prof[dom][0] / max(prof[dom][1], 1)
+    phase_e = dom.endswith("edge")
+    fe, fn = w.notes["flops_edge_fwd"] / max(w.n_edges, 1), w.notes["flops_node_fwd"] / max(w.n_nodes, 1)
+    f_phase = fe * edges_launch if phase_e else fn * nodes_launch
+    # algorithmic flops of that launch (SURVEY.md 8d): forward F; backward 2F (dgrad + wgrad); recompute not counted
+    alg_flops = f_phase * (1.0 if dom.startswith("fwd") else 2.0)
+    ach_tflops = alg_flops / (dom_ms * 1e-3) / 1e12
+    step_kernel_ms = sum(v[0] for v in prof.values()) / K
+    on_tc = paths.get(dom, 0) == 1
+    factored = paths.get(dom, 0) == 2
+    kname = {"fwd_edge": "mp_fwd{}_kernel<edge>", "fwd_node": "mp_fwd{}_kernel<node>", "bwd_node": "mp_bwd{}_kernel<node>",
+             "bwd_edge": "mp_bwd{}_kernel<edge>"}[dom].format("_tc" if on_tc else "")
+    if factored:
+        kname = {"fwd_edge": "gno factored edge phase: mp_fwd_kernel<edge> (S builder) + gno_gemm (mbar = S B)",
+                 "bwd_edge": "gno factored edge phase: gno_gemm (T = DM B') + mp_bwd_kernel<edge> + gno_gemm (dB = S' DM)"}[dom]
+    # the pipe that can hold the 1e-5 tolerance: 3xTF32 on tcgen05 = a third of the TF32 rate = a sixth of the dense BF16
+    # peak; the FP32-FFMA engine: 148 SMs x 128 lanes x 2 flop x 1.965 GHz = 74.4 TFLOP/s
+    pipe_peak = peaks["bf16_tflops"] / 6.0 if on_tc else 74.4
+    traffic, traffic_src = committed_traffic(workload, kname)
+    scale = edges_launch / max(w.n_edges, 1)
+    ex = w.notes.get("flops_executed_" + dom)
+    out = {
+        "kernel": kname,
+        "bound": "tensor", "achieved": ach_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": ach_tflops / peaks["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": peaks["source"] + " bf16 cuBLAS burst (MEASURED_PEAKS.json)",
+        "pipe": ("tcgen05 3xTF32 (fp32-accurate split: 3 TF32 MMAs per product; peak = bf16 peak / 6)" if on_tc else
+                 "fp32 FFMA (fp32-accurate; tolerance 1e-5 excludes plain TF32/BF16)"),
+        "pipe_peak_tflops": pipe_peak, "pipe_frac": ach_tflops / pipe_peak,
+        "kernel_paths": {k: {1: "tcgen05", 0: "ffma", 2: "factored (ffma + fp32 gemm)", -1: "none"}[v] for k, v in paths.items()},
+        "avg_launch_ms": dom_ms, "algorithmic_flops_per_launch": alg_flops,
+        "units_per_launch": {"edges": int(edges_launch), "nodes": int(nodes_launch)},
+        "share_of_step_kernel_time": (prof[dom][0] / K) / step_kernel_ms if step_kernel_ms else None,
+        "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items()},
+        "hbm": {"algorithmic_bytes_per_step": w.bytes_fwdbwd * scale,
+                "achieved_gbs": w.bytes_fwdbwd * scale / (step_ms * 1e-3) / 1e9,
+                "frac_of_measured": w.bytes_fwdbwd * scale / (step_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+    }
+    if factored and ex is not None:
+        # the factored evaluation does fewer flops than SURVEY 8d's count: lead with what is executed
+        ex = ex * scale
+        out.update({
+            "executed_flops_per_launch": ex, "executed_tflops": ex / (dom_ms * 1e-3) / 1e12,
+            "executed_pipe_frac": ex / (dom_ms * 1e-3) / 1e12 / pipe_peak,
+            "note": "factored GNOConv (csrc/ngpde_gno.cuh): the contraction with phi's affine last layer is done once per "
+                    "destination node on per-node outer-product sums instead of once per edge, so the flops EXECUTED are "
+                    "fewer than SURVEY 8d's algorithmic count. `executed_*` is the honest pipe utilisation; `achieved` / "
+                    "`pipe_frac` use the algorithmic count as the contract asks (and can exceed the pipe: work not done, "
+                    "not work done faster)"})
+    return out
+
+
+def strong_c4(args, rank, world, dev, peaks):
+    """The north-star scaling configuration: ONE GNOConv graph of 1M nodes / ~16M radius edges, node-partitioned over
+    the `world` ranks with a halo exchange per RHS, fwd + VJP per step, strong scaling; with a parity
+    record computed on the spot: this rank's owned rows against the same call on the unpartitioned graph."""
+    import torch.distributed as dist
+    from ngpde import _lib, distributed as D, engine, ops, workloads
+    n_nodes = args.c4_nodes
+    K = max(3, min(args.steps, args.c4_steps))
+    t_build = time.perf_counter()
+    w = workloads.c4_gno(dev, n_nodes=n_nodes)
+    gen = torch.Generator().manual_seed(4321)
+    dy_full = torch.randn((w.layer.out_chs, w.n_nodes), generator=gen).to(dev)
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    timer = Timer(dev, world, flush)
+    out = {"workload": workload_label("c4"), "nodes_total": w.n_nodes, "edges_total": w.n_edges, "steps": K,
+           "scaling": "strong", "unit": UNIT}
+    if world == 1:
+        runner = engine.RhsRunner(w.layer, w.x, w.ps, w.st)
+        runner.dy.copy_(dy_full.T)
+        step = runner.step
+        edges_launch, nodes_launch = w.n_edges, w.n_nodes
+        out["parallelism"] = "single GPU (the 1-GPU point of the strong-scaling series)"
+    else:
+        pl = D.PartitionedLayer(w.layer, w.graph, rank, world, dev, mode=args.halo)
+        pr = engine.PartitionedRhsRunner(pl, pl.owned(w.x), w.ps, w.st)
+        pr.dy_owned.copy_(pl.owned(dy_full).T)
+        runner, step = pr.runner, pr.step
+        p = pl.part
+        edges_launch, nodes_launch = int(p.edge_ids.size), int(p.n_local)
+        halo = torch.tensor([p.n_halo, p.n_owned, p.edge_ids.size], dtype=torch.float64, device=dev)
+        hmax = halo.clone()
+        dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(halo, op=dist.ReduceOp.SUM)
+        out.update({"parallelism": f"node-partitioned over {world} GPUs (contiguous ranges balanced by in-edges), halo via {args.halo}",
+                    "halo_rows_max": int(hmax[0].item()), "halo_rows_total": int(halo[0].item()),
+                    "owned_rows_max": int(hmax[1].item()), "edges_max_over_mean": float(hmax[2].item() / (halo[2].item() / world)),
+                    "step": "halo exchange + layer forward + VJP + reverse halo + dW all-reduce"})
+    out["build_s"] = time.perf_counter() - t_build
+    for _ in range(3):
+        step()
+        if flush is not None:
+            flush.zero_()
+    l0 = ops.LAUNCHES["count"]
+    ms = timer(step, K)
+    out.update({"ms_per_step": ms / K, "value": w.n_edges * K / (ms * 1e-3), "rhs_evals_per_sec": K / (ms * 1e-3),
+                "gpu_launches": ops.LAUNCHES["count"] - l0})
+    _lib.profile_enable(True)
+    timer(step, K)
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    out["roofline"] = roofline_block("c4", w, prof, K, _lib.kernel_paths(runner.handle, runner.desc), ms / K, peaks,
+                                     edges_launch, nodes_launch)
+    # ---- parity, at this world size, on the spot ----
+    if world > 1:
+        step()
+        y_p, dx_p = pr.y_owned.clone(), pr.dx_owned.clone()
+        dp_p = runner.dparams.clone()
+        del pr, runner
+        torch.cuda.empty_cache()
+        full = engine.RhsRunner(w.layer, w.x, w.ps, w.st)   # the same call on the whole graph, on this rank's GPU
+        full.dy.copy_(dy_full.T)
+        full.step()
+        own = pl.owned_global.to(dev)
+        den = lambda t: max(float(t.abs().max().item()), 1e-30)
+        mism = float((y_p != full.y[own]).sum().item())
+        e_dx = float((dx_p - full.dx[own]).abs().max().item()) / den(full.dx)
+        e_dp = float((dp_p - full.dparams).abs().max().item()) / den(full.dparams)
+        stats = torch.tensor([mism, e_dx, e_dp], dtype=torch.float64, device=dev)
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        out["dist_parity"] = {"ranks": world, "forward_mismatched_values": int(stats[0].item()),
+                              "dx_rel_err": float(stats[1].item()), "dparams_rel_err": float(stats[2].item()),
+                              "against": "the unpartitioned layer call (forward + VJP) on the same 1M-node graph, run on every "
+                                         "rank's own GPU; forward must be bit-identical, gradients within 1e-5 (max over ranks)",
+                              "ok": bool(stats[0].item() == 0 and stats[1].item() <= 1e-5 and stats[2].item() <= 1e-5)}
+        del full
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,7 +376,8 @@ def main():
     ap.add_argument("--partition", action="store_true",
                     help="N>1: split ONE graph over the ranks by nodes with a per-step halo exchange (strong scaling) "
                          "instead of one graph per rank (weak scaling)")
-    ap.add_argument("--halo", default="nccl", choices=["nccl", "put"], help="halo transfer: NCCL all-to-all or peer stores")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "put", "native"],
+                    help="halo transfer: NCCL all-to-all (torch), peer stores, or the C ABI's own NCCL communicator")
     ap.add_argument("--nodes", type=int, default=0, help="override the node count of c4 (default 1,000,000)")
     ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=True,
                     help="replay the step's forward+backward launches from a captured CUDA graph (default)")
@@ -189,6 +385,10 @@ def main():
     ap.add_argument("--graphs", type=int, default=0, help="c5: total number of 64x64 graphs in the ensemble (default 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (reported under config)")
+    ap.add_argument("--no-strong-c4", action="store_true",
+                    help="skip the node-partitioned C4 (1M-node GNOConv) strong-scaling block that the default C3 line carries")
+    ap.add_argument("--c4-nodes", type=int, default=1_000_000)
+    ap.add_argument("--c4-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -211,6 +411,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    peaks = measured_peaks()
 
     wkw = {"n_nodes": args.nodes} if (args.workload == "c4" and args.nodes) else {}
     chain = args.workload == "c5"
@@ -222,6 +423,8 @@ def main():
     gen = torch.Generator().manual_seed(1234)
     partitioned = args.partition and world > 1
     flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    timed = Timer(dev, world, flush)
+    allreduce_in_graph = False
     if partitioned:
         from ngpde import distributed as D
         pl = D.PartitionedLayer(w.layer, w.graph, rank, world, dev, mode=args.halo)
@@ -240,45 +443,32 @@ def main():
     else:
         runner = engine.RhsRunner(w.layer, w.x, w.ps, w.st)
         runner.dy.copy_(torch.randn(tuple(runner.dy.shape), generator=gen).to(dev))
+
+        # data-parallel: ONE collective over the flat [dphi | dnode] buffer (NCCL over NVLink), captured into the same CUDA
+        # graph as the kernels when the capture accepts it, so that no host launch gap separates it from the last kernel
+        def grad_allreduce():
+            dist.all_reduce(runner.dparams)
+
         if args.cuda_graph:
             try:
-                runner.capture()
-            except Exception as exc:  # keep measuring with direct launches rather than lose the line
-                sys.stderr.write(f"bench.py: CUDA graph capture failed ({exc}); launching kernels directly\n")
-                runner.graph = None
-                args.cuda_graph = False
+                runner.capture(extra=grad_allreduce if world > 1 else None)
+                allreduce_in_graph = world > 1
+            except Exception as exc:  # noqa: BLE001
                 torch.cuda.synchronize(dev)
-        grads = [t for t in (runner.dphi, runner.dnode) if t is not None]
+                try:
+                    runner.capture()
+                except Exception as exc2:  # keep measuring with direct launches rather than lose the line
+                    sys.stderr.write(f"bench.py: CUDA graph capture failed ({exc2}); launching kernels directly\n")
+                    runner.graph = None
+                    args.cuda_graph = False
+                    torch.cuda.synchronize(dev)
+                else:
+                    sys.stderr.write(f"bench.py: all-reduce not capturable ({exc}); it is issued after the graph replay\n")
 
         def one_step():
             runner.step()
-            if world > 1:
-                for t in grads:  # data-parallel: sum the flat parameter gradients over ranks (NCCL over NVLink)
-                    dist.all_reduce(t)
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(fn, k):
-        evs = []
-        sync_all()
-        for _ in range(k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            evs.append((e0, e1))
-            if flush is not None:
-                flush.zero_()
-        sync_all()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+            if world > 1 and not allreduce_in_graph:
+                grad_allreduce()
 
     for _ in range(W):
         one_step()
@@ -306,56 +496,12 @@ def main():
         timed(one_step, K)
     prof = _lib.profile_read()
     _lib.profile_enable(False)
-    peaks = measured_peaks()
-    dom = max(prof, key=lambda k: prof[k][0])
-    dom_ms = prof[dom][0] / max(prof[dom][1], 1)
-    phase_e = dom.endswith("edge")
-    # algorithmic flops of that launch: forward F; backward 2F (dgrad + wgrad); recompute not counted
-    f_edge = w.notes.get("flops_edge_fwd")
-    f_node = w.notes.get("flops_node_fwd")
-    f_phase = (f_edge if phase_e else f_node) if f_edge is not None else w.flops_fwd
-    alg_flops = f_phase * (1.0 if dom.startswith("fwd") else 2.0)
-    ach_tflops = alg_flops / (dom_ms * 1e-3) / 1e12
-    step_kernel_ms = sum(v[0] for v in prof.values()) / K
     paths = _lib.kernel_paths(runner.handle, runner.desc)
-    on_tc = paths.get(dom, 0) == 1
-    factored = paths.get(dom, 0) == 2
-    kname = {"fwd_edge": "mp_fwd{}_kernel<edge>", "fwd_node": "mp_fwd{}_kernel<node>", "bwd_node": "mp_bwd{}_kernel<node>",
-             "bwd_edge": "mp_bwd{}_kernel<edge>"}[dom].format("_tc" if on_tc else "")
-    if factored:
-        kname = {"fwd_edge": "gno factored edge phase: mp_fwd_kernel<edge> (S builder) + gno_gemm (mbar = S B)",
-                 "bwd_edge": "gno factored edge phase: gno_gemm (T = DM B') + mp_bwd_kernel<edge> + gno_gemm (dB = S' DM)"}[dom]
-    # the pipe that can hold the 1e-5 tolerance: 3xTF32 on tcgen05 = a third of the TF32 rate = a sixth of the dense BF16
-    # peak; the FP32-FFMA engine: 148 SMs x 128 lanes x 2 flop x 1.965 GHz = 74.4 TFLOP/s
-    pipe_peak = peaks["bf16_tflops"] / 6.0 if on_tc else 74.4
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get(kname)
-    roofline = {
-        "kernel": kname,
-        "bound": "tensor", "achieved": ach_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": ach_tflops / peaks["bf16_tflops"], "traffic": traffic,
-        "peak_source": peaks["source"] + " bf16 cuBLAS burst (MEASURED_PEAKS.json)",
-        "pipe": ("tcgen05 3xTF32 (fp32-accurate split: 3 TF32 MMAs per product; peak = bf16 peak / 6)" if on_tc else
-                 "fp32 FFMA (fp32-accurate; tolerance 1e-5 excludes plain TF32/BF16)"),
-        **({"executed_flops_per_launch": w.notes.get("flops_executed_" + dom),
-            "executed_tflops": w.notes.get("flops_executed_" + dom, 0.0) / (dom_ms * 1e-3) / 1e12,
-            "executed_pipe_frac": w.notes.get("flops_executed_" + dom, 0.0) / (dom_ms * 1e-3) / 1e12 / pipe_peak,
-            "note": "factored GNOConv (csrc/ngpde_gno.cuh): the contraction with phi's affine last layer is done once per "
-                    "destination node on per-node outer-product sums instead of once per edge, so the flops EXECUTED are "
-                    "fewer than SURVEY 8d's algorithmic count; `achieved`/`pipe_frac` use the algorithmic count (and can "
-                    "exceed the pipe), `executed_*` the flops actually issued"} if factored else {}),
-        "pipe_peak_tflops": pipe_peak, "pipe_frac": ach_tflops / pipe_peak,
-        "kernel_paths": {k: {1: "tcgen05", 0: "ffma", 2: "factored (ffma + fp32 gemm)", -1: "none"}[v] for k, v in paths.items()},
-        "avg_launch_ms": dom_ms, "algorithmic_flops_per_launch": alg_flops,
-        "share_of_step_kernel_time": (prof[dom][0] / K) / step_kernel_ms if step_kernel_ms else None,
-        "kernels_ms_per_step": {k: v[0] / K for k, v in prof.items()},
-        "hbm": {"algorithmic_bytes_per_step": w.bytes_fwdbwd,
-                "achieved_gbs": w.bytes_fwdbwd / (total_ms / K * 1e-3) / 1e9,
-                "frac_of_measured": w.bytes_fwdbwd / (total_ms / K * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-    }
+    if partitioned:
+        edges_launch, nodes_launch = int(pl.part.edge_ids.size), int(pl.part.n_local)
+    else:
+        edges_launch, nodes_launch = w.n_edges, w.n_nodes
+    roofline = roofline_block(args.workload, w, prof, K, paths, total_ms / K, peaks, edges_launch, nodes_launch)
 
     if partitioned:
         p = pl.part
@@ -416,11 +562,16 @@ def main():
                                 "VMHConv kernels only (the GCN aggregate is HBM-bound: DESIGN.md section 4)"} if chain else {}),
                    "step": "one RHS evaluation: layer forward + VJP w.r.t. (x, ps)", "aggr": "mean",
                    "l2": "warm (--no-flush)" if flush is None else "flushed between steps (256 MiB memset, untimed)",
-                   "parallelism": "1 graph per GPU, dW all-reduce over NCCL" if world > 1 else "single GPU",
+                   "parallelism": ("1 graph per GPU, one coalesced dW all-reduce over NCCL"
+                                   + (" captured in the step's CUDA graph" if allreduce_in_graph else "")) if world > 1 else "single GPU",
                    "cuda_graph": bool(args.cuda_graph) and not chain},
         "rhs_evals_per_sec": K * world / (total_ms * 1e-3),
         "algorithmic_tflops": 3.0 * w.flops_fwd * world / (total_ms / K * 1e-3) / 1e12,
         "gpu_launches": launches,
+        "gpu_launches_how": ("kernel nodes of the captured CUDA graph x replays (ngpde_cuda_graph_kernel_nodes)"
+                             if getattr(runner, "graph_kernels", None) is not None and args.cuda_graph and not chain
+                             else "per-call table in ops.py"),
+        "lib_sha256": lib_sha256(),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K, "api": "layer(x, ps, st) + backward via the C ABI (torch.autograd bridge)"},
@@ -439,8 +590,23 @@ def main():
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {
             "value": ws.n_edges * n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{ws.name}: {ws.n_nodes} nodes / {ws.n_edges} edges, {n} fwd+bwd steps in {dt:.1f} s "
+            "sample": f"{ws.name}: {ws.n_nodes} nodes / {ws.n_edges} edges "
+                      f"({'the full workload' if not sample_kw else 'reduced: ' + str(sample_kw)}), {n} fwd+bwd steps in {dt:.1f} s "
                       "(oracle: torch-CPU restatement of the unfused reference algorithm; Julia is not installed)"}
+
+    # ---- the north-star scaling configuration rides on the default line: C4, 1M nodes, node-partitioned, with parity ----
+    if args.workload == "c3" and not args.no_strong_c4:
+        del runner, w
+        flush = None
+        timed.flush = None
+        torch.cuda.empty_cache()
+        try:
+            line["strong_c4"] = strong_c4(args, rank, world, dev, peaks)
+        except Exception as exc:  # noqa: BLE001 -- never lose the headline line over the extra block
+            import traceback
+            line["strong_c4"] = {"error": repr(exc), "trace": traceback.format_exc()[-1500:]}
+            if world > 1:
+                raise
 
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NGPDE_VERSION 100
+#define NGPDE_VERSION 200
 
 /* status codes */
 #define NGPDE_OK 0
@@ -181,7 +181,10 @@ int ngpde_gno_conv_backward(ngpde_graph_t, const ngpde_conv_desc*, const ngpde_c
  * ascending-source accumulation order, multiply and add rounded separately.
  *   y = act(W (c .* A^T (c .* x)) + b),   c = 1/sqrt(in-degree),   W applied first when out < in.
  * edge_weight: NULL or [E] (original order; self-loop weights of 1 are appended internally, layers.jl:215).
- * graph_weight: NULL or the graph's own stored weights [E], used when use_edge_weight != 0 (w_mul_xj).
+ * graph_weight: NULL or the graph's own stored weights [E].  They scale the messages only when use_edge_weight != 0
+ *   (w_mul_xj, layers.jl:230), but whenever present (and no explicit edge_weight is given) they weight the in-degree of
+ *   the normaliser: `degree(g, T; dir=:in, edge_weight)` with edge_weight === nothing resolves to the stored weights in
+ *   GNN.jl (layers.jl:224).
  * agg_buf: [N][min(in,out)] scratch kept for the backward; lin_buf: [N][min(in,out)] scratch. ---- */
 typedef struct {
   int32_t in_chs, out_chs;
@@ -221,6 +224,87 @@ int ngpde_rows_put(const float* x, const int32_t* rows, const int64_t* peer_ptr,
                    int64_t n_rows, int32_t d, void* stream);
 int ngpde_rows_segment_add(float* dst, const float* src, const int32_t* seg_rows, const int32_t* seg_ptr,
                            const int32_t* seg_pos, int64_t n_segs, int32_t d, void* stream);
+
+/* ---- multi-GPU, host side: the node partitioner.  Owner-computes by destination over contiguous
+ * node ranges: rank r owns [bounds[r], bounds[r+1]) and every edge whose target it owns, in the original relative order
+ * (so each owned row reduces the same messages in the same order as on one GPU: the forward is bit-identical); sources
+ * owned elsewhere form the halo, appended after the owned rows in ascending global id.  `src`/`dst` are HOST arrays of
+ * the full COO lists (every rank holds them at build time; nothing is communicated here).  bounds == NULL: balanced by
+ * in-edge count + 1 per node (by_edges != 0) or by node count.  All arrays a plan exposes are int64 host arrays owned by
+ * the plan; together with the graph handle's arrays they are the bit-exact index contract of the partitioned path. ---- */
+typedef struct ngpde_partition* ngpde_partition_t;
+enum {
+  NGPDE_PA_BOUNDS = 0,       /* [world+1] global node ranges                                                      */
+  NGPDE_PA_HALO_GLOBAL = 1,  /* [n_halo]  global ids of imported sources, ascending (= grouped by owner)          */
+  NGPDE_PA_RECV_COUNTS = 2,  /* [world]   halo rows received from each peer                                       */
+  NGPDE_PA_SEND_COUNTS = 3,  /* [world]   owned rows sent to each peer                                            */
+  NGPDE_PA_SEND_LOCAL = 4,   /* [n_send]  owned-local row ids, grouped by peer, each group ascending              */
+  NGPDE_PA_S_LOCAL = 5,      /* [E_local] local source ids (owned: id - lo; halo: n_owned + rank in HALO_GLOBAL)  */
+  NGPDE_PA_T_LOCAL = 6,      /* [E_local] local target ids (always owned)                                         */
+  NGPDE_PA_EDGE_IDS = 7,     /* [E_local] original COO positions, ascending                                       */
+  NGPDE_PA_SEG_ROWS = 8,     /* [U]       distinct owned-local rows with at least one remote reader, ascending    */
+  NGPDE_PA_SEG_PTR = 9,      /* [U+1]                                                                             */
+  NGPDE_PA_SEG_POS = 10,     /* [n_send]  positions in the peer-major buffer of returned halo cotangents          */
+  NGPDE_PA_PEER_RECV_OFFSET = 11 /* [world] row offset of my rows inside peer p's halo block (direct peer stores) */
+};
+int ngpde_partition_create(ngpde_partition_t* out, int64_t num_nodes, int64_t num_edges, const void* src, const void* dst,
+                           int32_t index_dtype, int32_t index_base, int32_t world, int32_t rank, int32_t by_edges,
+                           const int64_t* bounds);
+int ngpde_partition_destroy(ngpde_partition_t p);
+int ngpde_partition_array(ngpde_partition_t p, int32_t which, const int64_t** host_ptr, int64_t* len);
+/* Morton (Z-order) permutation of the nodes from their coordinates pos [N][dim] (HOST, float32, dim = 1..3): order[k] = id of
+ * the k-th node along the curve.  Relabelling the graph with it before ngpde_partition_create turns contiguous id ranges
+ * into compact spatial blocks, so an arbitrarily numbered geometric graph gets an O(sqrt(N)) halo instead of O(N). */
+int ngpde_morton_order(const float* pos, int64_t num_nodes, int32_t dim, int64_t* order);
+
+/* ---- multi-GPU, device side: communicator + per-RHS halo exchange.  NCCL is bound at run time (dlopen of
+ * `libnccl_path`, NULL = "libnccl.so.2": the copy the host framework already loaded -- torch's bundled one, NCCL.jl's
+ * artifact), so libngpde itself has no link-time dependency on it.
+ *   comm_unique_id     rank 0 creates the 128-byte id; the host layer ships it to the other ranks (any side channel)
+ *   comm_init          ncclCommInitRank on the CURRENT device
+ *   comm_adopt         wrap an existing ncclComm_t (not destroyed by comm_destroy)
+ *   halo_create        uploads the plan's send / segment lists; owns a send buffer and a receive buffer sized on demand
+ *   halo_forward       x_local[0:n_owned] = x_owned; boundary rows packed (ngpde_rows_gather) and exchanged with grouped
+ *                      ncclSend/ncclRecv straight into x_local[n_owned:]            (forward of propagate's gather)
+ *   halo_backward      dx_owned = dx_local[0:n_owned] + returned halo cotangents added per row in fixed peer order
+ *                      (ngpde_rows_segment_add): deterministic                      (its pullback)
+ *   allreduce_sum      in-place sum of the flat parameter gradient over ranks. ---- */
+typedef struct ngpde_comm* ngpde_comm_t;
+typedef struct ngpde_halo* ngpde_halo_t;
+#define NGPDE_UNIQUE_ID_BYTES 128
+int ngpde_comm_unique_id(void* id_out, const char* libnccl_path);
+int ngpde_comm_init(ngpde_comm_t* out, const void* unique_id, int32_t world, int32_t rank, const char* libnccl_path);
+int ngpde_comm_adopt(ngpde_comm_t* out, void* nccl_comm, int32_t world, int32_t rank, const char* libnccl_path);
+int ngpde_comm_destroy(ngpde_comm_t c);
+int ngpde_halo_create(ngpde_halo_t* out, ngpde_partition_t plan, ngpde_comm_t comm, void* stream);
+int ngpde_halo_destroy(ngpde_halo_t h);
+int ngpde_halo_forward(ngpde_halo_t h, const float* x_owned, int32_t d, float* x_local, void* stream);
+int ngpde_halo_backward(ngpde_halo_t h, const float* dx_local, int32_t d, float* dx_owned, void* stream);
+int ngpde_allreduce_sum(ngpde_comm_t c, float* buf, int64_t n, void* stream);
+
+/* ---- the training step either side of the adjoint (docs/src/tutorials/graph_node.md:100-129,
+ * VMH.md:97-109,140-143): loss value + cotangent, and the optimiser update over the flat parameter vector.
+ *   adam_step   Optimisers.Adam:  m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; x -= m/(1-b1^t) / (sqrt(v/(1-b2^t)) + eps) * eta
+ *               (beta1_t = b1^t, beta2_t = b2^t are carried by the host as Optimisers.jl does)
+ *   rprop_step  Optimisers.Rprop: eta_i *= l+ (<= gamma_max) while g keeps its sign, *= l- (>= gamma_min) and g_prev = 0 when
+ *               it flips; x -= eta_i sign(g_prev')
+ *   mse_loss    loss = mean((yhat - y)^2) over n floats; dyhat (may be NULL) = 2 (yhat - y) / n
+ *   logit_cross_entropy   yhat [n_rows][C]; mask_idx [n_masked] row ids (NULL: all rows); y [n_masked][C];
+ *               loss = mean_j( -sum_c y[j][c] logsoftmax(yhat[mask[j]])[c] ); dyhat [n_rows][C] (may be NULL; zero outside the mask)
+ * `loss` is a DEVICE scalar; reductions are two-stage in fixed order (deterministic). ---- */
+int ngpde_adam_step(float* params, const float* grad, float* m, float* v, int64_t n, float eta, float beta1, float beta2,
+                    float eps, float beta1_t, float beta2_t, void* stream);
+int ngpde_rprop_step(float* params, const float* grad, float* g_prev, float* eta, int64_t n, float ell_minus, float ell_plus,
+                     float gamma_min, float gamma_max, void* stream);
+size_t ngpde_loss_workspace_bytes(void);
+int ngpde_mse_loss(const float* yhat, const float* y, int64_t n, float* loss, float* dyhat, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int ngpde_logit_cross_entropy(const float* yhat, int64_t n_rows, int32_t n_classes, const float* y, const int32_t* mask_idx,
+                              int64_t n_masked, float* loss, float* dyhat, void* workspace, size_t workspace_bytes,
+                              void* stream);
+
+/* number of kernel nodes / of all nodes of a captured cudaGraph_t (benchmarks count a replayed step's launches with it) */
+int ngpde_cuda_graph_kernel_nodes(void* cuda_graph, int64_t* n_kernels, int64_t* n_nodes);
 
 /* ---- optional kernel timing: while enabled, the four fused kernels of the conv layers (edge/node phase, forward/
  * backward) are bracketed by CUDA events on the launching stream.  ngpde_profile_read synchronises those events, returns

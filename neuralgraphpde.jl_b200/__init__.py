@@ -12,7 +12,7 @@ from .layers import (AbstractGNNContainerLayer, AbstractGNNLayer, ExplicitEdgeCo
 from .lux import (NT, Chain, ComponentArray, Dense, flat_params, glorot_normal, glorot_uniform, julia_array, merge,
                   ones32, setup, zeros32)
 from .utils import drop, updategraph
-from . import distributed, partition
+from . import distributed, losses, optim, partition
 
 __all__ = [
     "AbstractGNNLayer", "AbstractGNNContainerLayer", "ExplicitEdgeConv", "GCNConv", "VMHConv", "MPPDEConv", "GNOConv",

@@ -30,7 +30,15 @@ EXPORTS = [
     "ngpde_gcn_workspace_bytes", "ngpde_gcn_conv_forward", "ngpde_gcn_conv_backward", "ngpde_axpy_stages",
     "ngpde_profile_enable", "ngpde_profile_read", "ngpde_set_option", "ngpde_rows_gather", "ngpde_rows_put",
     "ngpde_rows_segment_add", "ngpde_debug_buffer", "ngpde_conv_kernel_paths", "ngpde_debug_gemm",
+    "ngpde_partition_create", "ngpde_partition_destroy", "ngpde_partition_array", "ngpde_morton_order",
+    "ngpde_comm_unique_id", "ngpde_comm_init", "ngpde_comm_adopt", "ngpde_comm_destroy", "ngpde_halo_create",
+    "ngpde_halo_destroy", "ngpde_halo_forward", "ngpde_halo_backward", "ngpde_allreduce_sum", "ngpde_adam_step",
+    "ngpde_rprop_step", "ngpde_loss_workspace_bytes", "ngpde_mse_loss", "ngpde_logit_cross_entropy",
+    "ngpde_cuda_graph_kernel_nodes",
 ]
+PA = {"bounds": 0, "halo_global": 1, "recv_counts": 2, "send_counts": 3, "send_local": 4, "s_local": 5, "t_local": 6,
+      "edge_ids": 7, "seg_rows": 8, "seg_ptr": 9, "seg_pos": 10, "peer_recv_offset": 11}
+UNIQUE_ID_BYTES = 128
 
 
 class Mlp(C.Structure):
@@ -103,6 +111,27 @@ def load() -> C.CDLL:
     lib.ngpde_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]
     lib.ngpde_conv_kernel_paths.argtypes = [vp, C.POINTER(ConvDesc), C.POINTER(i32)]
     lib.ngpde_debug_gemm.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i64, i32, i64, i32, vp, i32, vp]
+    f32, cp = C.c_float, C.c_char_p
+    lib.ngpde_partition_create.argtypes = [C.POINTER(vp), i64, i64, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.ngpde_partition_destroy.argtypes = [vp]
+    lib.ngpde_partition_array.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64)]
+    lib.ngpde_morton_order.argtypes = [vp, i64, i32, vp]
+    lib.ngpde_comm_unique_id.argtypes = [vp, cp]
+    lib.ngpde_comm_init.argtypes = [C.POINTER(vp), vp, i32, i32, cp]
+    lib.ngpde_comm_adopt.argtypes = [C.POINTER(vp), vp, i32, i32, cp]
+    lib.ngpde_comm_destroy.argtypes = [vp]
+    lib.ngpde_halo_create.argtypes = [C.POINTER(vp), vp, vp, vp]
+    lib.ngpde_halo_destroy.argtypes = [vp]
+    lib.ngpde_halo_forward.argtypes = [vp, vp, i32, vp, vp]
+    lib.ngpde_halo_backward.argtypes = [vp, vp, i32, vp, vp]
+    lib.ngpde_allreduce_sum.argtypes = [vp, vp, i64, vp]
+    lib.ngpde_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp]
+    lib.ngpde_rprop_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp]
+    lib.ngpde_loss_workspace_bytes.argtypes = []
+    lib.ngpde_loss_workspace_bytes.restype = sz
+    lib.ngpde_mse_loss.argtypes = [vp, vp, i64, vp, vp, vp, sz, vp]
+    lib.ngpde_logit_cross_entropy.argtypes = [vp, i64, i32, vp, vp, i64, vp, vp, vp, sz, vp]
+    lib.ngpde_cuda_graph_kernel_nodes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     _lib = lib
     return lib
 
@@ -136,6 +165,13 @@ def kernel_paths(graph_handle, desc) -> dict:
     out = (C.c_int32 * 4)()
     check(load().ngpde_conv_kernel_paths(graph_handle, C.byref(desc), out))
     return {k: int(out[i]) for i, k in enumerate(PROF_SLOTS)}
+
+
+def cuda_graph_kernel_nodes(raw_cuda_graph) -> tuple:
+    """(kernel nodes, all nodes) of a captured cudaGraph_t (torch.cuda.CUDAGraph(keep_graph=True).raw_cuda_graph())."""
+    nk, nn = C.c_int64(), C.c_int64()
+    check(load().ngpde_cuda_graph_kernel_nodes(C.c_void_p(int(raw_cuda_graph)), C.byref(nk), C.byref(nn)))
+    return int(nk.value), int(nn.value)
 
 
 def check(rc: int) -> None:

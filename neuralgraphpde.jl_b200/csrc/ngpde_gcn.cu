@@ -12,13 +12,15 @@ namespace ngpde {
 namespace {
 
 // Per-call edge quantities: merged-entry weights `val` and the normaliser c = 1/sqrt(in-degree).
-//   w_ext : explicit edge_weight (original order) or NULL;  w_g : the graph's own weights or NULL.
+//   w     : what scales the messages -- the explicit edge_weight, else the graph's own weights when use_edge_weight, else NULL;
+//   w_deg : what weights the in-degree -- the explicit edge_weight, else the graph's own stored weights whenever it has
+//           any (`degree(g, T; dir=:in, edge_weight)` with edge_weight === nothing resolves to get_edge_weight(g) in
+//           GNN.jl's _get_edge_weight, independently of use_edge_weight), else NULL = plain count.
 __global__ void gcn_prepare_kernel(int N, int E, int nnz, const int* __restrict__ runptr, const int* __restrict__ order,
                                    const int* __restrict__ rowptr, const int* __restrict__ perm,
-                                   const float* __restrict__ w_ext, const float* __restrict__ w_g, int with_loops,
+                                   const float* __restrict__ w, const float* __restrict__ w_deg, int with_loops,
                                    float* __restrict__ val, float* __restrict__ c) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const float* w = w_ext ? w_ext : w_g;
   if (i < nnz) {
     const int a = runptr[i], b = runptr[i + 1];
     float v;
@@ -35,11 +37,11 @@ __global__ void gcn_prepare_kernel(int N, int E, int nnz, const int* __restrict_
   }
   if (i < N) {
     float d;
-    if (w_ext == nullptr) {
-      d = (float)(rowptr[i + 1] - rowptr[i] + (with_loops ? 1 : 0));  // degree(g, T; dir=:in), unweighted (layers.jl:224)
+    if (w_deg == nullptr) {
+      d = (float)(rowptr[i + 1] - rowptr[i] + (with_loops ? 1 : 0));  // degree(g, T; dir=:in) of an unweighted graph (layers.jl:224)
     } else {
       d = 0.f;
-      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) d = __fadd_rn(d, w_ext[perm[k]]);
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) d = __fadd_rn(d, w_deg[perm[k]]);
       if (with_loops) d = __fadd_rn(d, 1.f);
     }
     c[i] = __fdiv_rn(1.f, __fsqrt_rn(d));
@@ -251,9 +253,10 @@ extern "C" int ngpde_gcn_conv_forward(ngpde_graph_t g, const ngpde_gcn_desc* des
   float* agg = reinterpret_cast<float*>(ws + w.off_agg);
   float* lin = reinterpret_cast<float*>(ws + w.off_lin);
   const int N = (int)g->N, E = (int)g->E;
-  const float* wg = desc->use_edge_weight ? graph_weight : nullptr;
+  const float* wmsg = edge_weight ? edge_weight : (desc->use_edge_weight ? graph_weight : nullptr);
+  const float* wdeg = edge_weight ? edge_weight : graph_weight;
   gcn_prepare_kernel<<<(std::max(N, L.nnz) + 255) / 256, 256, 0, st>>>(N, E, L.nnz, L.runptr, L.order, g->rowptr, g->perm,
-                                                                     edge_weight, wg, desc->add_self_loops, val, c);
+                                                                     wmsg, wdeg, desc->add_self_loops, val, c);
   const bool first = desc->out_chs < desc->in_chs;
   MlpDev m;
   if (int rc = gcn_mlp(*desc, first, &m)) return rc;
@@ -303,10 +306,11 @@ extern "C" int ngpde_gcn_conv_backward(ngpde_graph_t g, const ngpde_gcn_desc* de
   void* mlp_ws = ws + w.off_mlp;
   const size_t mlp_ws_bytes = w.total - w.off_mlp;
   const int N = (int)g->N, E = (int)g->E;
-  const float* wg = desc->use_edge_weight ? graph_weight : nullptr;
+  const float* wmsg = edge_weight ? edge_weight : (desc->use_edge_weight ? graph_weight : nullptr);
+  const float* wdeg = edge_weight ? edge_weight : graph_weight;
   // recompute the forward intermediates (val, c, aggregate): cheaper than keeping them alive between calls
   gcn_prepare_kernel<<<(std::max(N, L.nnz) + 255) / 256, 256, 0, st>>>(N, E, L.nnz, L.runptr, L.order, g->rowptr, g->perm,
-                                                                     edge_weight, wg, desc->add_self_loops, val, c);
+                                                                     wmsg, wdeg, desc->add_self_loops, val, c);
   const bool first = desc->out_chs < desc->in_chs;
   MlpDev m;
   if (int rc = gcn_mlp(*desc, first, &m)) return rc;

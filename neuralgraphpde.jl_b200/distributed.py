@@ -12,7 +12,9 @@ Two ways the path shards (index lists come from partition.
 
 Transfers: `mode="nccl"` packs with `ngpde_rows_gather` and calls `all_to_all_single`; `mode="put"` writes the rows
 straight into the peers' halo buffers from inside the pack kernel (`ngpde_rows_put`, peer-mapped symmetric memory over
-NVLink/NVSwitch), followed by a device-side barrier -- no send buffer, no NCCL call on the per-RHS path.
+NVLink/NVSwitch), followed by a device-side barrier -- no send buffer, no NCCL call on the per-RHS path; `mode="native"`
+runs the whole exchange inside the C ABI (`ngpde_halo_forward/backward`: pack kernel + grouped ncclSend/ncclRecv on a
+communicator the library created from a unique id, csrc/ngpde_dist.cu) -- the path a Julia binder gets.
 """
 from __future__ import annotations
 
@@ -26,7 +28,8 @@ import torch.distributed as dist
 from . import _lib, ops
 from .graph import GNNGraph, from_rowmajor, rowmajor
 from .lux import NT
-from .partition import BatchShard, NodePartition, partition_nodes, shard_batch
+from .partition import (BatchShard, NodePartition, morton_order, partition_nodes, partition_nodes_native, relabel,
+                        shard_batch)
 
 Tensor = torch.Tensor
 
@@ -35,13 +38,51 @@ def _i32(a: np.ndarray, device) -> Tensor:
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
 
 
+class NativeComm:
+    """An NCCL communicator owned by libngpde (`ngpde_comm_init`): rank 0 draws the unique id through the C ABI, the id
+    travels over the existing torch.distributed group (any side channel would do), every rank initialises on its current
+    device.  From here on the data path needs no torch collective."""
+
+    def __init__(self, device, group=None):
+        self.lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device)
+        idbuf = (C.c_ubyte * _lib.UNIQUE_ID_BYTES)()
+        if self.rank == 0:
+            _lib.check(self.lib.ngpde_comm_unique_id(idbuf, None))
+        backend = dist.get_backend(group)
+        t = torch.tensor(list(idbuf), dtype=torch.uint8, device=self.device if backend == "nccl" else "cpu")
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(t, src=src, group=group)
+        raw = bytes(t.cpu().tolist())
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ngpde_comm_init(C.byref(h), raw, self.world, self.rank, None))
+        self.handle = h
+
+    def allreduce_sum(self, t: Tensor) -> Tensor:
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        with torch.cuda.device(t.device):
+            _lib.check(self.lib.ngpde_allreduce_sum(self.handle, t.data_ptr(), t.numel(), ops._stream(t.device)))
+        return t
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h is not None and h.value:
+            try:
+                self.lib.ngpde_comm_destroy(h)
+            except Exception:
+                pass
+
+
 class HaloExchange:
     """Per-RHS boundary exchange of one NodePartition.  `forward(x_owned [n_owned, d]) -> x_local [n_local, d]` and
     `backward(dx_local) -> dx_owned` are each other's transposes."""
 
     def __init__(self, part: NodePartition, device, group=None, mode: str = "nccl"):
-        if mode not in ("nccl", "put"):
-            raise ValueError("mode must be 'nccl' or 'put'")
+        if mode not in ("nccl", "put", "native"):
+            raise ValueError("mode must be 'nccl', 'put' or 'native'")
         self.part, self.device, self.group, self.mode = part, torch.device(device), group, mode
         self.send_rows = _i32(part.send_local, device)
         self.seg_rows, self.seg_ptr, self.seg_pos = (_i32(part.seg_rows, device), _i32(part.seg_ptr, device),
@@ -50,6 +91,35 @@ class HaloExchange:
         self.recv_splits = [int(c) for c in part.recv_counts]
         self.n_send = int(part.send_counts.sum())
         self._symm: Dict[int, tuple] = {}
+        self._native = None
+
+    # ---- native mode: plan + communicator + exchange all inside the C ABI ----
+    def attach_native_plan(self, s: np.ndarray, t: np.ndarray, num_nodes: int, by: str = "edges"):
+        """Build the native plan + communicator + halo object (mode='native'); called by PartitionedLayer."""
+        lib, p = _lib.load(), self.part
+        s = np.ascontiguousarray(s, dtype=np.int64)
+        t = np.ascontiguousarray(t, dtype=np.int64)
+        b = np.ascontiguousarray(p.bounds, dtype=np.int64)
+        plan = C.c_void_p()
+        _lib.check(lib.ngpde_partition_create(C.byref(plan), int(num_nodes), int(s.size), s.ctypes.data, t.ctypes.data,
+                                              _lib.IDX_I64, 0, p.world, p.rank, 1 if by == "edges" else 0, b.ctypes.data))
+        try:
+            self.comm = NativeComm(self.device, self.group) if p.world > 1 else None
+            h = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(lib.ngpde_halo_create(C.byref(h), plan, None if self.comm is None else self.comm.handle,
+                                                 ops._stream(self.device)))
+            self._native = h
+        finally:
+            lib.ngpde_partition_destroy(plan)
+
+    def __del__(self):
+        h, self._native = getattr(self, "_native", None), None
+        if h is not None and h.value:
+            try:
+                _lib.load().ngpde_halo_destroy(h)
+            except Exception:
+                pass
 
     # ---- device primitives (CUDA only: the product path has no CPU fallback) ----
     def _pack(self, x: Tensor, rows: Tensor) -> Tensor:
@@ -99,6 +169,14 @@ class HaloExchange:
         p = self.part
         d = x_owned.shape[1]
         x_local = torch.empty((p.n_local, d), dtype=torch.float32, device=x_owned.device)
+        if self.mode == "native":
+            if self._native is None:
+                raise _lib.NgpdeError("mode='native': no native plan attached (build the exchange through PartitionedLayer)")
+            with torch.cuda.device(x_owned.device):
+                _lib.check(_lib.load().ngpde_halo_forward(self._native, x_owned.data_ptr(), d, x_local.data_ptr(),
+                                                          ops._stream(x_owned.device)))
+            ops.LAUNCHES["count"] += 1
+            return x_local
         x_local[:p.n_owned].copy_(x_owned)
         if p.world == 1:
             return x_local
@@ -119,6 +197,13 @@ class HaloExchange:
 
     def backward(self, dx_local: Tensor) -> Tensor:
         p = self.part
+        if self.mode == "native":
+            dx_owned = torch.empty((p.n_owned, dx_local.shape[1]), dtype=torch.float32, device=dx_local.device)
+            with torch.cuda.device(dx_local.device):
+                _lib.check(_lib.load().ngpde_halo_backward(self._native, dx_local.data_ptr(), dx_local.shape[1],
+                                                           dx_owned.data_ptr(), ops._stream(dx_local.device)))
+            ops.LAUNCHES["count"] += 1
+            return dx_owned
         dx_owned = dx_local[:p.n_owned].clone()
         if p.world == 1:
             return dx_owned
@@ -141,7 +226,7 @@ class _HaloFunction(torch.autograd.Function):
 
 def exchange_static(ex: HaloExchange, a_owned: Tensor) -> Tensor:
     """One-time exchange of static node data (graph `ndata`): [n_owned, d] -> [n_local, d], no gradient."""
-    saved, ex.mode = ex.mode, "nccl"
+    saved, ex.mode = ex.mode, ("native" if ex.mode == "native" else "nccl")
     try:
         with torch.no_grad():
             return ex.forward(a_owned.contiguous())
@@ -159,14 +244,36 @@ class PartitionedLayer:
     """
 
     def __init__(self, layer, g_full: GNNGraph, rank: int, world: int, device, group=None, mode: str = "nccl",
-                 by: str = "edges", exchange_cls=HaloExchange):
+                 by: str = "edges", exchange_cls=HaloExchange, order=None):
+        if not hasattr(layer, "prepare"):
+            # GCNConv (alone or inside a Chain) normalises by the in-degree of the SOURCE as well: halo rows have no local
+            # in-edges, so their 1/sqrt(deg) factor would be wrong and the owned outputs silently incorrect
+            raise TypeError("PartitionedLayer shards ExplicitEdgeConv / VMHConv / MPPDEConv / GNOConv; GCNConv needs the halo's "
+                            "global in-degrees and is sharded by whole graphs instead (shard_ensemble)")
         self.layer, self.rank, self.world = layer, rank, world
         self.device = torch.device(device)
         s, t = g_full.s.cpu().numpy(), g_full.t.cpu().numpy()
-        self.part = partition_nodes(s, t, g_full.num_nodes, world, rank, by=by)
+        # optional spatial renumbering: contiguous id ranges become compact blocks of the Morton curve, so a graph whose
+        # node numbering has no locality still gets an O(sqrt(N)) halo
+        self.order: Optional[np.ndarray] = None
+        if isinstance(order, str):
+            if order != "morton":
+                raise ValueError("order must be 'morton', a permutation, or None")
+            if "x" not in g_full.ndata:
+                raise KeyError("order='morton' needs the node coordinates in g.ndata.x")
+            order = morton_order(g_full.ndata["x"].cpu().numpy())
+        if order is not None:
+            self.order = np.asarray(order, dtype=np.int64)
+            s, t, _ = relabel(s, t, self.order)
+        self.part = partition_nodes_native(s, t, g_full.num_nodes, world, rank, by=by)
         p = self.part
         self.exchange = exchange_cls(p, self.device, group, mode)
-        l2g = torch.from_numpy(p.local_to_global())
+        if mode == "native":
+            self.exchange.attach_native_plan(s, t, g_full.num_nodes, by)
+        l2g = p.local_to_global()
+        if self.order is not None:
+            l2g = self.order[l2g]
+        l2g = torch.from_numpy(l2g)
         eid = torch.from_numpy(p.edge_ids)
         # rank-local copies of the static data: owned + halo node rows (a slice of the host copy every rank built from the
         # same seed; `exchange_static` does the same over the wire when only owned rows are at hand), local edge rows
@@ -174,14 +281,17 @@ class PartitionedLayer:
         ed = {k: v.cpu()[:, eid].to(self.device) for k, v in g_full.edata.items()}
         self.graph = GNNGraph(torch.from_numpy(p.s_local), torch.from_numpy(p.t_local), num_nodes=p.n_local, ndata=nd,
                               edata=ed, gdata=g_full.gdata).to(self.device)
+        self.owned_global = l2g[:p.n_owned]  # ids (in the caller's numbering) of the rows this rank owns, in local order
 
     def local_state(self, st: NT) -> NT:
         from .utils import updategraph
         return updategraph(st, self.graph)
 
     def owned(self, x_full: Tensor) -> Tensor:
-        """Columns of a full (d, N) array owned by this rank."""
-        return x_full[:, self.part.lo:self.part.hi]
+        """Columns of a full (d, N) array owned by this rank (in local row order)."""
+        if self.order is None:
+            return x_full[:, self.part.lo:self.part.hi]
+        return x_full[:, self.owned_global.to(x_full.device)]
 
     def __call__(self, x_owned: Tensor, ps, st_local: NT):
         x_rm = rowmajor(x_owned)
@@ -208,6 +318,9 @@ def allreduce_gradients(grads: Sequence[Optional[Tensor]], group=None) -> None:
     latency-bound, so they are coalesced into one buffer)."""
     gs = [g for g in grads if g is not None]
     if not gs or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    if len(gs) == 1 and gs[0].is_contiguous():
+        dist.all_reduce(gs[0], group=group)
         return
     flat = torch.cat([g.reshape(-1) for g in gs])
     dist.all_reduce(flat, group=group)

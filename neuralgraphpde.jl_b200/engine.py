@@ -21,6 +21,7 @@ class RhsRunner:
         if not hasattr(layer, "prepare"):
             raise TypeError("RhsRunner binds one of ExplicitEdgeConv / VMHConv / MPPDEConv / GNOConv")
         self.lib = _lib.load()
+        self._layer, self._st = layer, st
         (x_rm, phi, node, self.handle, self.desc, self.snode, self.edata, self.theta, dm, dy) = layer.prepare(x, ps, st)
         dev = x_rm.device
         self.dev = dev
@@ -33,8 +34,14 @@ class RhsRunner:
         self.y = torch.empty((N, dy), dtype=torch.float32, device=dev) if self.has_node else self.mbar
         self.dy = torch.zeros_like(self.y)
         self.dx = torch.empty_like(self.x)
-        self.dphi = torch.empty_like(self.phi)
-        self.dnode = None if self.node is None else torch.empty_like(self.node)
+        # one flat gradient buffer [dphi | dnode] (phi padded to a 16-byte boundary): a data-parallel step all-reduces it
+        # with ONE collective, no staging copy
+        nphi = self.phi.numel()
+        pad = (-nphi) % 4
+        self.dparams = torch.zeros(nphi + pad + (0 if self.node is None else self.node.numel()), dtype=torch.float32,
+                                   device=dev)
+        self.dphi = self.dparams[:nphi]
+        self.dnode = None if self.node is None else self.dparams[nphi + pad:]
         with torch.cuda.device(dev):
             nbytes = self.lib.ngpde_conv_workspace_bytes(self.handle, C.byref(self.desc), 1)
             if nbytes == 0:
@@ -55,6 +62,11 @@ class RhsRunner:
         self.launches_fwd = (2 if self.has_node else 1) + (1 if factored else 0)
         self.launches_bwd = (8 if self.has_node else 5) + (4 if factored else 0)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_kernels: Optional[int] = None  # kernel nodes of the captured step (exact launch count per replay)
+        # Everything a captured graph points at is owned by this object (x / parameters are private copies, the packed
+        # static data and the native graph layout are referenced from here), so replaying stays valid whatever happens
+        # to the caller's ps / st afterwards; new values come in through `set_params` / `x.copy_`.
+        self._keep = (self.snode, self.edata, self.theta, self.handle)
         if use_cuda_graph:
             self.capture()
 
@@ -73,25 +85,44 @@ class RhsRunner:
         ops.LAUNCHES["count"] += self.launches_bwd
         return self.dx, self.dphi, self.dnode
 
-    def capture(self):
-        """Capture forward+backward into one CUDA graph (launch-latency-bound configs such as C1)."""
+    def set_params(self, ps) -> None:
+        """Copy new parameter values (same tree) into the bound buffers, e.g. after an optimiser step."""
+        pr = self._layer.prepare(self.x.T, ps, self._st)
+        self.phi.copy_(pr[1].detach())
+        if self.node is not None:
+            self.node.copy_(pr[2].detach())
+
+    def capture(self, extra=None):
+        """Capture forward+backward (and `extra()`, e.g. the gradient all-reduce) into one CUDA graph."""
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
             self.forward()
             self.backward()
+            if extra is not None:
+                extra()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
-        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.LAUNCHES["count"]
+        self.graph = torch.cuda.CUDAGraph(keep_graph=True)
         with torch.cuda.graph(self.graph):
             self.forward()
             self.backward()
+            if extra is not None:
+                extra()
+        ops.LAUNCHES["count"] = l0  # a capture launches nothing
+        try:
+            self.graph_kernels, _ = _lib.cuda_graph_kernel_nodes(self.graph.raw_cuda_graph())
+        except Exception:  # noqa: BLE001 -- counting is a diagnostic; the table below stays as the estimate
+            self.graph_kernels = None
+        self.graph.instantiate()
 
     def step(self):
         """One RHS evaluation, forward + VJP."""
         if self.graph is not None:
             self.graph.replay()
-            ops.LAUNCHES["count"] += self.launches_fwd + self.launches_bwd
+            ops.LAUNCHES["count"] += (self.graph_kernels if self.graph_kernels is not None
+                                      else self.launches_fwd + self.launches_bwd)
         else:
             self.forward()
             self.backward()
@@ -162,4 +193,8 @@ class PartitionedRhsRunner:
         r.dy[:self.n_owned].copy_(self.dy_owned)
         r.backward()
         self.dx_owned = self.pl.exchange.backward(r.dx)
-        self._allreduce([r.dphi, r.dnode], self.pl.exchange.group)
+        ex = self.pl.exchange
+        if ex.mode == "native" and getattr(ex, "comm", None) is not None:
+            ex.comm.allreduce_sum(r.dparams)      # NCCL through the C ABI's own communicator
+        else:
+            self._allreduce([r.dparams], ex.group)  # one collective over the flat [dphi | dnode] buffer

@@ -39,21 +39,47 @@ def rowmajor(x: Tensor, dtype=torch.float32) -> Tensor:
     return r.contiguous()
 
 
+class GraphHandle:
+    """Owner of one native `ngpde_graph_t` (the device CSR layout of one topology on one device).  It is what the layers
+    pass to the C ABI (`_as_parameter_` makes ctypes take the raw pointer) and what autograd contexts and runners keep a
+    reference to: the native layout lives exactly as long as somebody can still call into it -- a graph that is garbage
+    collected, or asked for a layout on another device, between a forward and its backward cannot free the arrays the
+    backward kernels read."""
+
+    def __init__(self, ptr: C.c_void_p, device: torch.device):
+        self._as_parameter_ = ptr
+        self.device = device
+
+    @property
+    def value(self):
+        return self._as_parameter_.value
+
+    def __del__(self):
+        ptr, self._as_parameter_ = getattr(self, "_as_parameter_", None), None
+        if ptr is not None and ptr.value:
+            try:
+                _lib.load().ngpde_graph_destroy(ptr)
+            except Exception:
+                pass
+
+
 class _Topology:
-    """Edge lists + the lazily built libngpde handle; shared between shallow copies of a graph."""
+    """Edge lists + the lazily built libngpde handles (one per device); shared between shallow copies of a graph."""
 
     def __init__(self, s: Tensor, t: Tensor, num_nodes: int, num_graphs: int):
         self.s, self.t = s, t
         self.num_nodes, self.num_graphs = int(num_nodes), int(num_graphs)
-        self._handle: Optional[C.c_void_p] = None
-        self._handle_device = None
+        self._handles: Dict[torch.device, GraphHandle] = {}
 
-    def handle(self, device: torch.device) -> C.c_void_p:
-        if self._handle is not None and self._handle_device == device:
-            return self._handle
+    def handle(self, device: torch.device) -> GraphHandle:
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        hit = self._handles.get(device)
+        if hit is not None:
+            return hit
         if device.type != "cuda":
             raise _lib.NgpdeError("the message-passing path runs on CUDA only (no CPU fallback); move x/ps/st to a GPU")
-        self._release()
         lib = _lib.load()
         s = self.s.to(device=device, dtype=torch.int64).contiguous()
         t = self.t.to(device=device, dtype=torch.int64).contiguous()
@@ -62,8 +88,8 @@ class _Topology:
             stream = torch.cuda.current_stream(device).cuda_stream
             _lib.check(lib.ngpde_graph_create(C.byref(h), self.num_nodes, s.numel(), s.data_ptr(), t.data_ptr(),
                                               _lib.IDX_I64, 0, 1, self.num_graphs, stream))
-        self._handle, self._handle_device = h, device
-        return h
+        self._handles[device] = GraphHandle(h, device)
+        return self._handles[device]
 
     def array(self, name: str, device: torch.device, with_self_loops: bool = False) -> Tensor:
         """Copy of one of the handle's integer arrays (bit-exact index contract; used by tests)."""
@@ -77,17 +103,6 @@ class _Topology:
             _lib.check(lib.ngpde_graph_array_copy(h, _lib.GA[name], int(with_self_loops), out.data_ptr(), n.value,
                                                   stream))
         return out
-
-    def _release(self):
-        if self._handle is not None:
-            try:
-                _lib.load().ngpde_graph_destroy(self._handle)
-            except Exception:
-                pass
-            self._handle = None
-
-    def __del__(self):
-        self._release()
 
 
 def _as_index(a, base: int) -> Tensor:
@@ -198,19 +213,38 @@ class GNNGraph:
         return self._topo.array(name, device, with_self_loops)
 
     def _packed(self, kind: str, keys: Sequence[str], source: Dict[str, Tensor], device, width_axis0: bool = True):
-        """[items, sum D] float32 row-major concatenation of the named fields, cached on their identity/version."""
-        sig = (kind, tuple(keys), tuple((source[k].data_ptr(), source[k]._version, tuple(source[k].shape)) for k in keys),
-               str(device))
+        """[items, sum D] float32 row-major concatenation of the named fields.  Cached per `kind`; the entry keeps the
+        SOURCE tensors alive and is valid only while the very same tensor objects, at the same in-place version, are
+        still installed (identity, not address: a freed block handed out again by the caching allocator cannot alias)."""
+        srcs = tuple(source[k] for k in keys)
+        vers = tuple(t._version for t in srcs)
         hit = self._cache.get(kind)
-        if hit is not None and hit[0] == sig:
-            return hit[1]
+        if (hit is not None and hit[0] == (tuple(keys), str(device)) and len(hit[1]) == len(srcs)
+                and all(a is b for a, b in zip(hit[1], srcs)) and hit[2] == vers):
+            return hit[3]
         if not keys:
             packed = None
         else:
-            parts = [rowmajor(source[k].to(device)) for k in keys]
+            for k, t in zip(keys, srcs):
+                _warn_float64(k, t)
+            parts = [rowmajor(t.to(device)) for t in srcs]
             packed = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1).contiguous()
-        self._cache[kind] = (sig, packed)
+        self._cache[kind] = ((tuple(keys), str(device)), srcs, vers, packed)
         return packed
+
+
+_F64_WARNED = set()
+
+
+def _warn_float64(name: str, t: Tensor) -> None:
+    """Float64 side data (the reference's tests build `rand(2, n)` arrays: test/runtests.jl:58-61,126-128).  Julia promotes
+    the whole layer call to Float64 there; this path computes in float32 only, so the data is converted -- once per
+    field name, loudly."""
+    if t.dtype == torch.float64 and name not in _F64_WARNED:
+        import warnings
+        _F64_WARNED.add(name)
+        warnings.warn(f"graph data field {name!r} is float64: converted to float32 (the B200 path computes in float32; the "
+                      "reference would promote the layer call to Float64)", stacklevel=3)
 
 
 def copy(g: GNNGraph, **kwargs) -> GNNGraph:

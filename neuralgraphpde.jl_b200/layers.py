@@ -104,6 +104,17 @@ def _nparams(spec) -> int:
     return sum(i * o + (o if b else 0) for i, o, _, b in spec)
 
 
+def _reject_collisions(xs: Dict[str, Tensor], g: GNNGraph, who: str):
+    """`xs = merge(x, g.ndata)` (layers.jl:110,324): on a key present in both, Julia's merge keeps x's position but takes
+    the ndata VALUE, i.e. the trainable input would be silently replaced by static data (and, in VMHConv, gamma would
+    still see the input's value).  The fused kernels keep trainable and static columns apart, so this corner is refused
+    loudly instead of being computed differently from the reference."""
+    both = [k for k in xs if k in g.ndata]
+    if both:
+        raise _lib.NgpdeError(f"{who}: field(s) {both} appear both in the input NamedTuple and in st.graph.ndata; "
+                              "merge(x, ndata) would replace the input by the static data (layers.jl:110,324) -- rename one")
+
+
 def _check_nodes(x_rm: Tensor, g: GNNGraph):
     if x_rm.shape[0] != g.num_nodes:
         raise ValueError(f"DimensionMismatch: x has {x_rm.shape[0]} columns but the graph has {g.num_nodes} nodes")
@@ -126,9 +137,10 @@ class ExplicitEdgeConv(AbstractGNNContainerLayer):
         if "x" not in g.ndata:
             raise KeyError("ExplicitEdgeConv needs the spatial coordinates in st.graph.ndata.x (layers.jl:98-105)")
         dev = next(iter(xs.values())).device
+        _reject_collisions(xs, g, "ExplicitEdgeConv")
         x_rm = _concat_rm([v for k, v in xs.items() if k != "x"])
         _check_nodes(x_rm, g)
-        hs_keys = [k for k in g.ndata if k != "x" and k not in xs]
+        hs_keys = [k for k in g.ndata if k != "x"]
         snode = g._packed("edgeconv_s", hs_keys + ["x"], g.ndata, dev)
         dhs = snode.shape[1] - g.ndata["x"].shape[0]
         phi = mlp_spec(self.ϕ)
@@ -155,9 +167,10 @@ class VMHConv(AbstractGNNContainerLayer):
         if "x" not in g.ndata:
             raise KeyError("VMHConv needs the spatial coordinates in st.graph.ndata.x (layers.jl:313-321)")
         dev = next(iter(xs.values())).device
+        _reject_collisions(xs, g, "VMHConv")
         x_rm = _concat_rm([v for k, v in xs.items() if k != "x"])
         _check_nodes(x_rm, g)
-        hs_keys = [k for k in g.ndata if k != "x" and k not in xs]
+        hs_keys = [k for k in g.ndata if k != "x"]
         snode = g._packed("vmh_s", hs_keys + ["x"], g.ndata, dev)
         dpos = g.ndata["x"].shape[0]
         phi, gamma = mlp_spec(self.ϕ), mlp_spec(self.γ)
@@ -282,7 +295,9 @@ class GCNConv(AbstractGNNLayer):
         desc = _lib.GcnDesc(self.in_chs, self.out_chs, _lib.ACT[self.activation], 1, int(self.add_self_loops),
                             int(self.use_edge_weight))
         params = flat_params(ps, self.parameterlength())
-        gw = g.w.to(dev) if (self.use_edge_weight and g.w is not None) else None
+        # the graph's own stored weights always go down: `degree(g, T; dir=:in, edge_weight)` with edge_weight === nothing
+        # resolves to them (GNN.jl `_get_edge_weight`), whether or not use_edge_weight lets them scale the messages
+        gw = g.w.to(dev) if g.w is not None else None
         ew = None if edge_weight is None else edge_weight.to(dev)
         y = ops.GcnFunction.apply(x_rm, params, g.handle(dev), desc, ew, gw)
         return from_rowmajor(y), st

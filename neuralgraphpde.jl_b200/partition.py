@@ -160,6 +160,85 @@ def shard_batch(s: np.ndarray, t: np.ndarray, num_nodes: int, num_graphs: int, w
     return BatchShard(rank, world, g0, g1, lo, hi, src - lo, t[eid] - lo, eid)
 
 
+def partition_nodes_native(s: np.ndarray, t: np.ndarray, num_nodes: int, world: int, rank: int,
+                           bounds: Optional[np.ndarray] = None, by: str = "edges") -> NodePartition:
+    """The same plan built by the C ABI (`ngpde_partition_create`, csrc/ngpde_dist.cu) -- what `PartitionedLayer` uses and
+    what a Julia binder calls; `partition_nodes` above is its numpy statement, kept as the checker of the CPU tests."""
+    import ctypes as C
+    from . import _lib
+    if by not in ("edges", "nodes"):
+        raise ValueError(f"unknown balancing criterion {by!r}")
+    lib = _lib.load()
+    s = np.ascontiguousarray(s, dtype=np.int64)
+    t = np.ascontiguousarray(t, dtype=np.int64)
+    b = None if bounds is None else np.ascontiguousarray(bounds, dtype=np.int64)
+    if b is not None and b.shape != (world + 1,):
+        raise ValueError("bounds must be a non-decreasing [world+1] vector from 0 to num_nodes")
+    h = C.c_void_p()
+    rc = lib.ngpde_partition_create(C.byref(h), int(num_nodes), int(s.size), s.ctypes.data, t.ctypes.data, _lib.IDX_I64, 0,
+                                    int(world), int(rank), 1 if by == "edges" else 0, None if b is None else b.ctypes.data)
+    if rc != 0:
+        msg = lib.ngpde_last_error().decode("utf-8", "replace")
+        raise ValueError(msg) if rc == -1 else _lib.NgpdeError(f"libngpde error {rc}: {msg}")
+    try:
+        def arr(name):
+            ptr, n = C.c_void_p(), C.c_int64()
+            _lib.check(lib.ngpde_partition_array(h, _lib.PA[name], C.byref(ptr), C.byref(n)))
+            if n.value == 0:
+                return np.zeros(0, dtype=np.int64)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int64)), shape=(n.value,)).copy()
+        a = {k: arr(k) for k in _lib.PA}
+    finally:
+        lib.ngpde_partition_destroy(h)
+    bd = a["bounds"]
+    return NodePartition(rank, world, bd, int(bd[rank]), int(bd[rank + 1]), a["halo_global"], a["recv_counts"],
+                         a["send_counts"], a["send_local"], a["s_local"], a["t_local"], a["edge_ids"], a["seg_rows"],
+                         a["seg_ptr"], a["seg_pos"], a["peer_recv_offset"])
+
+
+def morton_order(pos: np.ndarray) -> np.ndarray:
+    """Z-order permutation of the nodes from coordinates `pos` (dim, N) Julia-shaped or (N, dim): order[k] = id of the k-th
+    node along the curve (C ABI `ngpde_morton_order`)."""
+    from . import _lib
+    p = np.asarray(pos, dtype=np.float32)
+    if p.ndim == 1:
+        p = p[None, :]
+    if p.shape[0] <= 3 and p.shape[1] > 3:
+        p = p.T
+    p = np.ascontiguousarray(p)
+    order = np.empty(p.shape[0], dtype=np.int64)
+    _lib.check(_lib.load().ngpde_morton_order(p.ctypes.data, p.shape[0], p.shape[1], order.ctypes.data))
+    return order
+
+
+def morton_order_numpy(pos: np.ndarray) -> np.ndarray:
+    """numpy statement of `morton_order` (test checker)."""
+    p = np.asarray(pos, dtype=np.float32)
+    if p.ndim == 1:
+        p = p[None, :]
+    if p.shape[0] <= 3 and p.shape[1] > 3:
+        p = p.T
+    n, dim = p.shape
+    mn, mx = p.min(axis=0).astype(np.float64), p.max(axis=0).astype(np.float64)
+    span = mx - mn
+    u = np.where(span > 0, (p.astype(np.float64) - mn) / np.where(span > 0, span, 1.0), 0.0)
+    q = np.minimum(np.floor(u * float(1 << 21)), float((1 << 21) - 1)).astype(np.uint64)
+    code = np.zeros(n, dtype=np.uint64)
+    for bit in range(20, -1, -1):
+        for a in range(dim):
+            code = (code << np.uint64(1)) | ((q[:, a] >> np.uint64(bit)) & np.uint64(1))
+    return np.argsort(code, kind="stable").astype(np.int64)
+
+
+def relabel(s: np.ndarray, t: np.ndarray, order: np.ndarray):
+    """Edge lists under the renumbering new_id = rank of the node in `order` (edges keep their stored order, so every
+    destination still reduces the same messages in the same order).  Returns (s_new, t_new, inverse) with
+    inverse[old_id] = new_id; node-indexed arrays move as `a[..., order]`."""
+    inv = np.empty(order.size, dtype=np.int64)
+    inv[order] = np.arange(order.size, dtype=np.int64)
+    return inv[np.asarray(s, dtype=np.int64)], inv[np.asarray(t, dtype=np.int64)], inv
+
+
 def partition_summary(parts: List[NodePartition]) -> Dict[str, float]:
     """Balance and halo statistics over all ranks (for logs and DESIGN.md tables)."""
     e = np.array([p.edge_ids.size for p in parts], dtype=np.float64)

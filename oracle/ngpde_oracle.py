@@ -484,9 +484,13 @@ def gcn_conv(x: Tensor, ps: Dict, g: OGraph, in_chs: int, out_chs: int, act: str
     n = g.num_nodes
     if out_chs < in_chs:
         x = ps["weight"] @ x  # :220-223
-    # degree(g, T; dir=:in, edge_weight): weighted only when an explicit vector was passed (:224)
+    # degree(g, T; dir=:in, edge_weight) (:224): the explicit vector when one was passed; with edge_weight === nothing
+    # GNN.jl's `_get_edge_weight(g, nothing)` resolves to the graph's own stored weights (self-loops padded with ones by
+    # add_self_loops), whatever use_edge_weight says; a graph without weights gives the plain in-degree
     if edge_weight is not None:
         d = scatter("+", edge_weight.reshape(1, -1).to(x.dtype), g.t, n).reshape(-1)
+    elif g.w is not None:
+        d = scatter("+", g.w.reshape(1, -1).to(x.dtype), g.t, n).reshape(-1)
     else:
         d = torch.from_numpy(in_degree(g.t, n).astype(np.float64)).to(x.dtype)
     c = 1.0 / torch.sqrt(d)  # :225
@@ -636,3 +640,54 @@ def integrate_fixed(rhs: Callable[[Tensor], Tensor], u0: Tensor, t0: float, t1: 
         for w, k in zip(b, ks):
             u = u + (dt * w) * k
     return u
+
+
+# --------------------------------------------------------------------------------------
+# the training step either side of the adjoint.  The reference reaches these through un-vendored
+# packages (Optimisers.jl, Flux.Losses / its own one-liner); their published rules are restated here in float32 numpy with
+# one rounding per operation, in the operation order of the Julia source.
+# --------------------------------------------------------------------------------------
+
+
+def adam_init(x: np.ndarray, beta=(0.9, 0.999)):
+    """Optimisers.jl `init(o::Adam, x) = (zero(x), zero(x), o.beta)` (call site: graph_node.md:122-123)."""
+    return np.zeros_like(x), np.zeros_like(x), (np.float32(beta[0]), np.float32(beta[1]))
+
+
+def adam_step(x: np.ndarray, g: np.ndarray, state, eta=0.001, beta=(0.9, 0.999), eps=1e-8):
+    """Optimisers.jl `apply!(o::Adam, state, x, dx)` followed by `x .- dx'`:
+        mt = b1 mt + (1 - b1) dx;  vt = b2 vt + (1 - b2) dx^2;  dx' = mt / (1 - b1^t) / (sqrt(vt / (1 - b2^t)) + eps) * eta."""
+    f = np.float32
+    m, v, bt = state
+    b1, b2, eta, eps = f(beta[0]), f(beta[1]), f(eta), f(eps)
+    m = b1 * m + (f(1) - b1) * g
+    v = b2 * v + (f(1) - b2) * (g * g)
+    step = m / (f(1) - bt[0]) / (np.sqrt(v / (f(1) - bt[1])) + eps) * eta
+    return (x - step).astype(np.float32), (m.astype(np.float32), v.astype(np.float32), (f(bt[0] * b1), f(bt[1] * b2)))
+
+
+def rprop_init(x: np.ndarray, eta=1e-3):
+    """Optimisers.jl `init(o::Rprop, x) = (zero(x), onevalue(o.eta, x))` (call site: VMH.md:97)."""
+    return np.zeros_like(x), np.full_like(x, np.float32(eta))
+
+
+def rprop_step(x: np.ndarray, dx: np.ndarray, state, ell=(0.5, 1.2), gamma=(1e-6, 50.0)):
+    """Optimisers.jl `apply!(o::Rprop, state, x, dx)`: eta grows by ell[2] (capped at gamma[2]) while g*dx > 0, shrinks by
+    ell[1] (floored at gamma[1]) when g*dx < 0, in which case the stored gradient is zeroed; x -= eta * sign(g)."""
+    f = np.float32
+    g, eta = state
+    prod = g * dx
+    eta = np.where(prod > 0, np.minimum(eta * f(ell[1]), f(gamma[1])),
+                   np.where(prod < 0, np.maximum(eta * f(ell[0]), f(gamma[0])), eta)).astype(np.float32)
+    g = np.where(prod < 0, f(0), dx).astype(np.float32)
+    return (x - eta * np.sign(g)).astype(np.float32), (g, eta)
+
+
+def mse(yhat: Tensor, y: Tensor) -> Tensor:
+    """Flux.Losses.mse (VMH.md:105-109): mean(abs2, yhat - y)."""
+    return ((yhat - y) ** 2).mean()
+
+
+def logitcrossentropy(yhat: Tensor, y: Tensor) -> Tensor:
+    """graph_node.md:100: `mean(-sum(y .* logsoftmax(yhat); dims=1))` on Julia-shaped (classes, items) arrays."""
+    return (-(y * torch.log_softmax(yhat, dim=0)).sum(dim=0)).mean()

@@ -20,6 +20,42 @@ def relerr(a: torch.Tensor, b: torch.Tensor) -> float:
     return (a - b).abs().max().item() / den
 
 
+def block_relerrs(a: torch.Tensor, b: torch.Tensor, blocks) -> dict:
+    """Max-norm relative error per named block: blocks = [(name, index-or-slice into the leading axis / flat vector)].
+    A block whose reference is identically zero must be matched to 1e-30 absolute (den = max|b| of the WHOLE array
+    there, so that e.g. the zero gradient of an unused bias does not divide by zero)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    whole = max(b.abs().max().item(), 1e-30) if b.numel() else 1.0
+    out = {}
+    for name, sel in blocks:
+        aa, bb = a[sel], b[sel]
+        if bb.numel() == 0:
+            continue
+        den = bb.abs().max().item()
+        if den == 0.0:
+            den = whole
+        out[name] = (aa - bb).abs().max().item() / den
+    return out
+
+
+def param_blocks(tree, prefix=""):
+    """[(name, slice)] of the leaves of a Julia-shaped parameter tree in ComponentArray (flat) order."""
+    out, off = [], 0
+
+    def walk(t, pre):
+        nonlocal off
+        for k, v in t.items():
+            if isinstance(v, torch.Tensor):
+                out.append((pre + k, slice(off, off + v.numel())))
+                off += v.numel()
+            else:
+                walk(v, pre + k + ".")
+
+    walk(tree, prefix)
+    return out
+
+
 def tree_to_cpu(ps, dtype=torch.float32):
     """ngpde NT / ComponentArray tree -> nested dict of CPU tensors (Julia shapes) for the oracle."""
     if isinstance(ps, ngpde.ComponentArray):

@@ -1,7 +1,7 @@
 """Real multi-rank check of the node-partitioned path (run under torchrun on >= 2 GPUs; not collected by pytest):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tests/dist_check.py [--mode nccl|put]
+        tests/dist_check.py [--mode nccl|put|native] [--order morton]
 
 Every rank builds the same synthetic GNOConv / VMHConv workload, runs its share through PartitionedLayer (halo exchange
 over NCCL or direct peer stores), and rank 0 compares the gathered result with the unpartitioned single-GPU call:
@@ -21,7 +21,8 @@ import torch.distributed as dist
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="nccl", choices=["nccl", "put"])
+    ap.add_argument("--mode", default="nccl", choices=["nccl", "put", "native"])
+    ap.add_argument("--order", default=None, choices=[None, "morton"])
     args = ap.parse_args()
     import ngpde
     from ngpde import distributed as D, workloads
@@ -37,8 +38,9 @@ def main():
         y_full, _ = w.layer(w.x, w.ps, w.st)
         dy = torch.randn(tuple(y_full.shape), generator=gen).to(dev)
         y0, dx0, dp0 = product_fwd_bwd(w.layer, w.x, w.ps, w.st, dy)
-        pl = D.PartitionedLayer(w.layer, w.graph, rank, world, dev, mode=args.mode)
+        pl = D.PartitionedLayer(w.layer, w.graph, rank, world, dev, mode=args.mode, order=args.order)
         p = pl.part
+        own = pl.owned_global.to(dev)
         x_owned = pl.owned(w.x).detach().clone().requires_grad_(True)
         ca = ngpde.ComponentArray(w.ps)
         ca.data.requires_grad_(True)
@@ -46,15 +48,18 @@ def main():
             x_owned.grad = None
             ca.data.grad = None
             y, _ = pl(x_owned, ca, pl.local_state(w.st))
-            y.backward(dy[:, p.lo:p.hi])
-            D.allreduce_gradients([ca.data.grad])
-        e_y = float((y.detach() != y0[:, p.lo:p.hi]).sum().item())
-        e_dx = relerr(x_owned.grad, dx0[:, p.lo:p.hi])
+            y.backward(dy[:, own])
+            if args.mode == "native":
+                pl.exchange.comm.allreduce_sum(ca.data.grad)  # NCCL through the C ABI's own communicator
+            else:
+                D.allreduce_gradients([ca.data.grad])
+        e_y = float((y.detach() != y0[:, own]).sum().item())
+        e_dx = relerr(x_owned.grad, dx0[:, own])
         e_dp = relerr(ca.data.grad, dp0)
         stats = torch.tensor([e_y, e_dx, e_dp], dtype=torch.float64, device=dev)
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"{w.name} world={world} mode={args.mode}: halo rows {p.n_halo} of {p.n_owned} owned; "
+            print(f"{w.name} world={world} mode={args.mode} order={args.order}: halo rows {p.n_halo} of {p.n_owned} owned; "
                   f"forward mismatches {int(stats[0])}, dx rel err {stats[1]:.2e}, dps rel err {stats[2]:.2e}", flush=True)
         ok = ok and stats[0].item() == 0 and stats[1].item() <= 1e-5 and stats[2].item() <= 1e-5
     dist.barrier()

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libngpde.so does not export {name}"
     assert set(ngpde._lib.EXPORTS) == declared
-    assert lib.ngpde_version() == 100
+    assert lib.ngpde_version() == 200
 
 
 def test_gcn_state_and_params():  # runtests.jl:16-25

@@ -168,3 +168,68 @@ def test_halo_exchange_two_ranks_gloo(tmp_path):
     world, port = 2, _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+# ---- the C ABI's partitioner (csrc/ngpde_dist.cu) against the numpy statement: every array, element by element ----
+
+@pytest.mark.parametrize("world", [1, 2, 5, 8])
+@pytest.mark.parametrize("by", ["edges", "nodes"])
+def test_native_partition_plan_matches_numpy(world, by):
+    rng = np.random.default_rng(11 + world)
+    cases = [(40, 300), (1, 0), (7, 1), (500, 6000), (64, 64)]
+    for n, e in cases:
+        s, t = rng.integers(0, n, e), rng.integers(0, n, e)
+        for r in range(world):
+            a = P.partition_nodes(s, t, n, world, r, by=by)
+            b = P.partition_nodes_native(s, t, n, world, r, by=by)
+            for f in a.__dataclass_fields__:
+                va, vb = getattr(a, f), getattr(b, f)
+                same = np.array_equal(va, vb) if isinstance(va, np.ndarray) else va == vb
+                assert same, (n, e, world, r, by, f)
+    # explicit bounds, including an empty rank
+    n, e = 30, 200
+    s, t = rng.integers(0, n, e), rng.integers(0, n, e)
+    bounds = np.linspace(0, n, world + 1).astype(np.int64)
+    if world > 2:
+        bounds[2] = bounds[1]
+    for r in range(world):
+        a = P.partition_nodes(s, t, n, world, r, bounds=bounds)
+        b = P.partition_nodes_native(s, t, n, world, r, bounds=bounds)
+        assert all(np.array_equal(getattr(a, f), getattr(b, f)) for f in a.__dataclass_fields__)
+
+
+def test_native_partition_rejects_bad_input():
+    s, t = np.array([0, 5]), np.array([1, 1])
+    with pytest.raises(ValueError):
+        P.partition_nodes_native(s, t, 3, 2, 0)  # source 5 out of range
+    with pytest.raises(ValueError):
+        P.partition_nodes_native(np.array([0]), np.array([1]), 3, 2, 0, bounds=np.array([0, 4, 3]))
+
+
+def test_morton_order_and_halo_locality():
+    """An unsorted geometric graph: contiguous id ranges are random node sets (halo ~ everything); after the Morton
+    renumbering they are compact blocks (halo ~ perimeter).  The C implementation equals the numpy statement."""
+    rng = np.random.default_rng(5)
+    n = 20000
+    s, t, pos = workloads.radius_edges(n, 12.0, rng)
+    scr = rng.permutation(n)
+    s, t, _ = P.relabel(s, t, scr)
+    pos = pos[:, scr]
+    order = P.morton_order(pos)
+    assert np.array_equal(np.sort(order), np.arange(n))
+    assert np.array_equal(order, P.morton_order_numpy(pos))
+    for dim in (1, 3):
+        q = rng.uniform(-3, 5, size=(dim, 1000)).astype(np.float32)
+        assert np.array_equal(P.morton_order(q), P.morton_order_numpy(q))
+    halo_before = max(P.partition_nodes_native(s, t, n, 4, r).n_halo for r in range(4))
+    s2, t2, inv = P.relabel(s, t, order)
+    assert np.array_equal(order[s2], s) and np.array_equal(inv[order], np.arange(n))
+    halo_after = max(P.partition_nodes_native(s2, t2, n, 4, r).n_halo for r in range(4))
+    assert halo_before > 0.5 * n * 3 / 4 * 0.9 and halo_after < 0.06 * n, (halo_before, halo_after)
+
+
+def test_partitioned_layer_refuses_gcnconv():
+    from ngpde import distributed as D
+    g = ngpde.GNNGraph([0, 1], [1, 0], num_nodes=2)
+    with pytest.raises(TypeError):
+        D.PartitionedLayer(ngpde.GCNConv((2, 2), initialgraph=g), g, 0, 1, "cpu")
