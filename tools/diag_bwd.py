@@ -9,8 +9,11 @@ from ngpde import Chain, Dense, GNNGraph, VMHConv, setup
 from common import jl_rand, oracle_fwd_bwd, product_fwd_bwd, relerr
 
 DEV = "cuda:0"
-dims, gdims, aggr = [6, 16, 48, 5], [7, 40, 3], sys.argv[1] if len(sys.argv) > 1 else "+"
+import json
+aggr = sys.argv[1] if len(sys.argv) > 1 else "+"
 long_row = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+dims = json.loads(sys.argv[3]) if len(sys.argv) > 3 else [6, 16, 48, 5]
+gdims = json.loads(sys.argv[4]) if len(sys.argv) > 4 else [7, 40, 3]
 rng = np.random.default_rng(77)
 n = 900
 s, t = rng.integers(0, n, 7000), rng.integers(0, n, 7000)
@@ -39,6 +42,8 @@ for name, tc in (("TC", 1), ("FFMA", 0)):
     print(name, "y", relerr(y, y64), "dx", relerr(dxx, dx64), "dp", relerr(dp, dp64), "| oracle32: dx", relerr(dx32, dx64), "dp", relerr(dp32, dp64))
     for nm, a, b in blocks:
         print(f"   {nm:8s} rel {relerr(dp[a:b], dp64[a:b]):.2e}  max|ref| {dp64[a:b].abs().max().item():.3e}")
+    for r in range(dxx.shape[0]):
+        print(f"   dx[{r}] rel {relerr(dxx[r], dx64[r]):.2e} (oracle32 {relerr(dx32[r], dx64[r]):.2e})  max|ref| {dx64[r].abs().max().item():.3e}")
     e = (dxx.cpu().double() - dx64).abs()
     i = int(e.max(dim=0).values.argmax())
     print("   dx worst node", i, "err", e[:, i].tolist(), "ref", dx64[:, i].tolist(), "indeg", int((t == i).sum()), "outdeg", int((s == i).sum()))
