@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libngpde.so")
+LIB_PATH = os.environ.get("NGPDE_LIB_PATH") or os.path.join(HERE, "libngpde.so")  # override: developer builds (tools/)
 
 MAX_LAYERS = 8
 
