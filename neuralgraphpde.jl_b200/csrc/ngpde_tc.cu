@@ -91,16 +91,46 @@ bool tc_bwd_make_impl(const MlpDev& m, bool contract, bool addend, bool node, in
   int cols = 32;
   while (cols < total) cols *= 2;
   t->tmem_cols = cols;
-  // shared memory: weight block | column tables | staging (Z hi, Z lo: nzh groups each; G hi, G lo: 2 groups each) | dZ_0
+  // shared memory: weight images | column tables | staging (Z hi, Z lo: nzh groups each; G hi, G lo: 2 groups each) | dZ_0.
+  // Preferred: stage the weight-gradient operands for the whole 128-row tile at once (all 16 warps work, one MMA batch
+  // per layer).  That needs (2 nzh + 4) x 16 KB of staging; when the weight images do not fit beside it, the images of
+  // layer 1 (used by the recompute and, late, by its own input gradient) and of the last layer (used once, first thing in
+  // the backward sweep) share one slot and are swapped by TMA twice per tile.  Otherwise: two 64-row halves, all resident.
   t->nzh = (kdmax + 31) / 32;
   t->nzl = t->nzh;
-  t->off_cols = 4 * lay.block_floats;
-  t->off_stage = (t->off_cols + (int)(sizeof(TcCol) + sizeof(TcDst)) * lay.Kd[0] + 1023) & ~1023;
-  t->off_dz = t->off_stage + (2 * t->nzh + 4) * TCB_HALF * 128;
   const int dz_bytes = (!node && need_dz0) ? TC_TILE * (lay.Kd[0] + 1) * 4 : 0;
-  const int totalb = 1024 + t->off_dz + dz_bytes;
-  if (totalb > kSmemMaxTc) return false;
-  t->smem = std::max(totalb, 116 * 1024);  // one CTA per SM: its TMEM allocation must not wait for a neighbour's
+  const int cols_bytes = (int)(sizeof(TcCol) + sizeof(TcDst)) * lay.Kd[0];
+  auto place = [&](bool full, bool stream) -> bool {
+    int off = 0;  // floats
+    const int sa = stream ? 1 : -1, sb = stream ? L - 1 : -1;
+    int slot = 0;
+    for (int l = 0; l < L; ++l) {
+      if (l == sb) {
+        t->woff[l] = t->woff[sa];
+        continue;
+      }
+      t->woff[l] = off;
+      int fl = 2 * lay.img_floats[l];
+      if (l == sa) fl = slot = std::max(fl, 2 * lay.img_floats[sb]);
+      off += fl;
+    }
+    (void)slot;
+    t->stream_a = sa;
+    t->stream_b = sb;
+    t->full = full;
+    t->off_cols = 4 * off;
+    t->off_stage = (t->off_cols + cols_bytes + 1023) & ~1023;
+    t->off_dz = t->off_stage + (2 * t->nzh + 4) * (full ? TC_TILE : TCB_HALF) * 128;
+    const int totalb = 1024 + t->off_dz + dz_bytes;
+    t->smem = std::max(totalb, 116 * 1024);  // one CTA per SM: its TMEM allocation must not wait for a neighbour's
+    return totalb <= kSmemMaxTc;
+  };
+  const char* force = getenv("NGPDE_TCB_STAGING");  // developer switch: "half" forces the two-pass staging
+  const bool allow_full = !(force && force[0] == 'h') && kdmax <= 64;
+  bool ok = allow_full && place(true, false);
+  if (!ok && allow_full && L >= 4) ok = place(true, true);
+  if (!ok) ok = place(false, false);
+  if (!ok) return false;
   t->on = true;
   return true;
 }
@@ -184,10 +214,17 @@ int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base,
   std::memcpy(a.c_zs, t.c_zs, sizeof(a.c_zs));
   a.c_a = t.c_a; a.a_width = t.a_width; a.c_d = t.c_d; a.c_dw = t.c_dw; a.c_d0 = t.c_d0; a.c_dw0 = t.c_dw0; a.tmem_cols = t.tmem_cols; a.dw_alt = t.dw_alt;
   a.off_cols = t.off_cols; a.off_stage = t.off_stage; a.off_dz = t.off_dz; a.nzh = t.nzh; a.nzl = t.nzl;
+  std::memcpy(a.woff, t.woff, sizeof(a.woff));
+  a.stream_a = t.stream_a; a.stream_b = t.stream_b;
   a.dbg = NODE ? nullptr : g_tcb_dbg;
   { const char* e = getenv("NGPDE_TCB_OPT"); a.opt = e ? atoi(e) : 0; }
-  NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_bwd_tc_kernel<NODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
-  mp_bwd_tc_kernel<NODE><<<t.grid, TCB_THREADS, t.smem, st>>>(a);
+  if (t.full) {
+    NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_bwd_tc_kernel<NODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
+    mp_bwd_tc_kernel<NODE, true><<<t.grid, TCB_THREADS, t.smem, st>>>(a);
+  } else {
+    NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_bwd_tc_kernel<NODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
+    mp_bwd_tc_kernel<NODE, false><<<t.grid, TCB_THREADS, t.smem, st>>>(a);
+  }
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;
 }

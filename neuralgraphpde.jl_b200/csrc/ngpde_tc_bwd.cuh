@@ -53,24 +53,31 @@ struct TcBwdArgs {
   // shared memory byte offsets
   int off_cols, off_stage, off_dz;
   int nzh, nzl;            // 32-column groups of the staged Z hi / lo images
+  // weight images in shared memory: layer l's hi image starts at float offset woff[l] (its lo image follows).  When the
+  // block does not fit next to a FULL-tile staging buffer, layers stream_a and stream_b share one slot (same woff) and
+  // are swapped in by TMA bulk copies twice per tile (see the kernel); -1 = everything resident.
+  int woff[NGPDE_MAX_LAYERS];
+  int stream_a, stream_b;
   int opt;                 // experiment switches (NGPDE_TCB_OPT)
   long long* dbg;          // optional phase timestamps (clock64) of CTA 0, thread 64: [tile][64]; nullptr = off
 };
 
-// float offset inside a staged image of TCB_HALF rows: element (r, c)
+// float offset inside a staged image of ROWS rows: element (r, c)
+template <int ROWS>
 __device__ __forceinline__ uint32_t stage_off(int r, int c) {
-  return umma::sw128b32_offset(c >> 5, TCB_HALF, r, c & 31);
+  return umma::sw128b32_offset(c >> 5, ROWS, r, c & 31);
 }
 
 // write 16 consecutive columns [c0, c0+16) of row r into a staged hi image and lo image (c0 % 16 == 0).
 // A quarter warp holds 8 consecutive rows; rows r and r + 4 share the swizzled 32-byte chunk position, so the two 16-byte
 // halves of a chunk are written in opposite order by the rows with bit 2 set: every 128-bit store instruction then
 // covers 8 distinct 16-byte bank groups (conflict-free instead of 2-way conflicted).
+template <int ROWS>
 __device__ __forceinline__ void stage_chunk(float* img_hi, float* img_lo, int r, int c0, const float (&f)[16]) {
   const bool swp = (r & 4) != 0;
 #pragma unroll
   for (int b = 0; b < 2; ++b) {  // two 32-byte blocks
-    const uint32_t o = stage_off(r, c0 + 8 * b);
+    const uint32_t o = stage_off<ROWS>(r, c0 + 8 * b);
     const uint32_t o1 = o + (swp ? 4u : 0u), o2 = o + (swp ? 0u : 4u);
     float x[8];
 #pragma unroll
@@ -95,10 +102,10 @@ __device__ __forceinline__ void stage_chunk(float* img_hi, float* img_lo, int r,
 // MMAs [i0, i1) of the 3 * (Kd/8) that make up one recomputed Dense layer (pass = i / nks: lo*hi, hi*lo, hi*hi), into the
 // accumulator tDpart.  Two issuing warps take one half each, into separate accumulators (one thread sustains only one MMA
 // per ~65 cycles, tools/tmem_bench.cu); the bias is added by the epilogue, so no "ones" column is involved.
-__device__ __forceinline__ void tcb_issue_fwd_part(const TcLayout& lay, int l, uint32_t wblk_smem, uint32_t tDpart, uint32_t tAhi,
+__device__ __forceinline__ void tcb_issue_fwd_part(const TcLayout& lay, int l, uint32_t wimg_smem, uint32_t tDpart, uint32_t tAhi,
                                                    uint32_t tAlo, int i0, int i1) {
   const uint32_t idesc = umma::make_idesc(TC_TILE, lay.Np[l], /*a_mn=*/0, /*b_mn=*/1);
-  const uint32_t hi = wblk_smem + 4u * lay.img_off[l], lo = hi + 4u * lay.img_floats[l];
+  const uint32_t hi = wimg_smem, lo = hi + 4u * lay.img_floats[l];
   const uint32_t lbo = 128u * lay.Kp[l];
   const uint64_t dhi = umma::make_sdesc(hi, lbo, 512, 1), dlo = umma::make_sdesc(lo, lbo, 512, 1);
   const int nks = lay.Kd[l] / 8;
@@ -114,10 +121,10 @@ __device__ __forceinline__ void tcb_issue_fwd_part(const TcLayout& lay, int l, u
 
 // dZ_l = G W_l^T: A = G hi/lo in TMEM [128 x Np_l], B = forward weight image of layer l read K-major, N = Kd_l columns.
 // K-step ks covers columns [8 ks, 8 ks + 8) of the image rows: group ks / 4 (gstride bytes apart), 32-byte block ks % 4.
-__device__ __forceinline__ void tcb_issue_dgrad(const TcLayout& lay, int l, uint32_t wblk_smem, uint32_t tD, uint32_t tAhi,
+__device__ __forceinline__ void tcb_issue_dgrad(const TcLayout& lay, int l, uint32_t wimg_smem, uint32_t tD, uint32_t tAhi,
                                                 uint32_t tAlo) {
   const uint32_t idesc = umma::make_idesc(TC_TILE, lay.Kd[l], 0, 0);
-  const uint32_t hi = wblk_smem + 4u * lay.img_off[l];
+  const uint32_t hi = wimg_smem;
   const uint64_t dhi = umma::make_sdesc(hi, 0, 512, 1);
   const uint64_t dlo = dhi + (uint64_t)(lay.img_floats[l] >> 2);  // image sizes are multiples of 1 KB: no field overflow
   const uint32_t g16 = 8u * lay.Kp[l];                             // group stride in 16-byte units
@@ -132,16 +139,17 @@ __device__ __forceinline__ void tcb_issue_dgrad(const TcLayout& lay, int l, uint
   }
 }
 
-// dW_l^T += G^T Z over one staged half tile: M = 64, K = TCB_HALF rows, N = Kd_l;
+// dW_l^T += G^T Z over one staged image of ROWS rows (a half tile or the full tile): M = 64, K = ROWS, N = Kd_l;
 // one K-step = 8 staged rows = 1024 bytes = 64 descriptor address units
+template <int ROWS>
 __device__ __forceinline__ void tcb_issue_wgrad(const TcLayout& lay, int l, uint32_t ghi, uint32_t glo, uint32_t zhi,
                                                 uint32_t zlo, uint32_t tDw, int accumulate) {
   const uint32_t id_full = umma::make_idesc(64, lay.Kd[l], 1, 1);
   const uint32_t id_data = id_full;
-  const uint32_t lbo = 128u * TCB_HALF;
+  const uint32_t lbo = 128u * ROWS;
   const uint64_t dgh = umma::make_sdesc(ghi, lbo, 512, 1), dgl = umma::make_sdesc(glo, lbo, 512, 1);
   const uint64_t dzh = umma::make_sdesc(zhi, lbo, 512, 1), dzl = umma::make_sdesc(zlo, lbo, 512, 1);
-  constexpr int nks = TCB_HALF / 8;
+  constexpr int nks = ROWS / 8;
 #pragma unroll
   for (int ks = 0; ks < nks; ++ks)
     umma::mma_tf32_ss(tDw, dgl + (uint64_t)(ks * 64), dzh + (uint64_t)(ks * 64), id_full, accumulate | (ks > 0));
@@ -212,11 +220,23 @@ __device__ __forceinline__ float tcb_colsum16(const float (&g)[16], int lane) {
   return z;
 }
 
-template <bool NODE>
+// Warp roles: 16 WORKER warps (thread = (row, 16-column chunk) of the tile) and one dedicated ISSUER warp.  tcgen05.mma issue
+// is back-pressured at the rate the tensor pipe executes (measured, tools/mma_order.cu: the issuing lane is held for the
+// whole batch), so an issuing worker would stall its own share of the epilogues and, through the next barrier, everybody
+// else's.  The issuer only waits for "operands ready" mbarriers (bar_fg: A operand in TMEM; bar_fs: staged images in shared
+// memory; 16 arrivals = one per worker warp) and issues; the workers never wait for the issuer, only for MMA completion
+// (bar_d / bar_w, armed by tcgen05.commit).
+// FULL: the weight-gradient operands of a layer are staged for the whole 128-row tile at once (all 16 warps, all four
+// schedulers busy, one MMA batch of K = 128 per layer) instead of in two 64-row halves.  The 128 KB staging buffer only
+// fits next to the weight images when two of them share a slot (stream_a / stream_b).
+template <bool NODE, bool FULL>
 __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_constant__ TcBwdArgs a) {
+  constexpr int NW = TCB_WORKERS;  // worker threads
+  constexpr int ROWS = FULL ? TC_TILE : TCB_HALF;  // rows of one staged image
+  constexpr int NH = TC_TILE / ROWS;               // staging passes per layer
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ __align__(8) uint64_t bar_d, bar_w, wbar;
+  __shared__ __align__(8) uint64_t bar_d, bar_w, wbar, bar_ring, bar_fg, bar_fs;
   __shared__ uint32_t tmem_slot;
   const TcLayout& lay = a.lay;
   const int tid = threadIdx.x, warp = umma::uniform_i32(threadIdx.x >> 5), lane = tid & 31;
@@ -228,8 +248,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   TcCol* cols = reinterpret_cast<TcCol*>(smem + a.off_cols);
   TcDst* dcols = reinterpret_cast<TcDst*>(cols + lay.Kd[0]);
   float* st_base = reinterpret_cast<float*>(smem + a.off_stage);  // Z hi | Z lo | G hi | G lo, each nz (2 for G) groups
-  float* st_ghi = st_base + 2 * a.nzh * TCB_HALF * 32;
-  float* st_glo = st_ghi + 2 * TCB_HALF * 32;
+  float* st_ghi = st_base + 2 * a.nzh * ROWS * 32;
+  float* st_glo = st_ghi + 2 * ROWS * 32;
   float* DZ = reinterpret_cast<float*>(smem + a.off_dz);  // edge phase: [128][Kd0 + 1]; later reused for the db exchange
   const int L = lay.L, Kd0 = lay.Kd[0];
   // edge phase: the gathered layer-0 input is parked in the (not yet used) dZ_0 tile instead of being gathered twice
@@ -240,6 +260,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
     umma::mbar_init(&wbar, 1);
     umma::mbar_init(&bar_d, 1);
     umma::mbar_init(&bar_w, 1);
+    umma::mbar_init(&bar_ring, 1);
+    umma::mbar_init(&bar_fg, NW / 32);
+    umma::mbar_init(&bar_fs, NW / 32);
     umma::fence_mbar_init();
   }
   tc_build_cols(a, cols, Kd0, tid, TCB_THREADS);
@@ -259,11 +282,26 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
+  // one layer's (hi, lo) image pair: global prepared block -> its shared-memory slot, completion on `bar`
+  auto load_layer = [&](int l, uint64_t* bar) {
+    const uint32_t bytes = 8u * lay.img_floats[l];
+    mbar_arrive_expect_tx(bar, bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wblock + lay.img_off[l]);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(wblk + a.woff[l]);
+    for (uint32_t off = 0; off < bytes; off += 16384) bulk_g2s(dst + off, src + off, min(16384u, bytes - off), bar);
+  };
   if (tid == 0) {
-    const uint32_t bytes = 4u * lay.block_floats;
+    uint32_t bytes = 0;
+    for (int l = 0; l < L; ++l)
+      if (l != a.stream_b) bytes += 8u * lay.img_floats[l];
     mbar_arrive_expect_tx(&wbar, bytes);
-    for (uint32_t off = 0; off < bytes; off += 16384)
-      bulk_g2s(smem + off, reinterpret_cast<const uint8_t*>(a.wblock) + off, min(16384u, bytes - off), &wbar);
+    for (int l = 0; l < L; ++l) {
+      if (l == a.stream_b) continue;  // shares stream_a's slot: swapped in during the tile
+      const uint32_t lb = 8u * lay.img_floats[l];
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wblock + lay.img_off[l]);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(wblk + a.woff[l]);
+      for (uint32_t off = 0; off < lb; off += 16384) bulk_g2s(dst + off, src + off, min(16384u, lb - off), &wbar);
+    }
   }
   umma::mbar_wait(&wbar, 0);
 
@@ -274,6 +312,82 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   const uint32_t s_ghi = umma::smem_u32(st_ghi), s_glo = umma::smem_u32(st_glo);
   uint32_t ph_d = 0, ph_w = 0;
   const int gdiv = a.tg.gdiv, aggr = a.aggr, dout = a.dout;
+  const bool streaming = a.stream_a >= 0;
+  int dbg_tile = 0;
+
+  auto worker_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(TCB_WORKERS) : "memory"); };
+  // this warp's part of a hand-off to the issuer: everything each lane wrote (TMEM stores waited for, shared-memory stores
+  // fenced towards the async proxy by the caller) is ordered before lane 0's arrival
+  auto arrive = [&](uint64_t* bar) {
+    umma::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) umma::mbar_arrive(bar);
+  };
+
+  if (warp == NW / 32) {
+    // ================= ISSUER: one elected lane walks the same tile / layer sequence and issues every MMA batch =================
+    if (umma::elect_one_sync()) {
+      uint32_t pf = 0, ps = 0, pr = 0, pd = 0;  // pd: parity of bar_d's next completion (diagnosis only)
+      for (int unit = blockIdx.x; unit < a.tg.n_units; unit += gridDim.x) {
+        int kbeg, kend;
+        if (NODE) {
+          kbeg = unit * TC_TILE;
+          kend = min(a.tg.N, kbeg + TC_TILE);
+        } else {
+          kbeg = a.tg.rowptr[a.tg.unit_ptr[unit]];
+          kend = a.tg.rowptr[a.tg.unit_ptr[unit + 1]];
+        }
+        for (int k0 = kbeg; k0 < kend; k0 += TC_TILE) {
+          for (int l = 0; l < L - 1; ++l) {  // recompute: two accumulators (tD, tDw), summed by the epilogue
+            const int nmma = 3 * (lay.Kd[l] / 8), isplit = (nmma + 1) / 2;
+            umma::mbar_wait(&bar_fg, pf);
+            pf ^= 1;
+            umma::tc_fence_after();
+            tcb_issue_fwd_part(lay, l, wblk_smem + 4u * a.woff[l], tD, tAhi, tAlo, 0, isplit);
+            tcb_issue_fwd_part(lay, l, wblk_smem + 4u * a.woff[l], tDw, tAhi, tAlo, isplit, nmma);
+            umma::mma_commit(&bar_d);
+            pd ^= 1;
+          }
+          for (int l = L - 1; l >= 0; --l) {
+            const bool do_dgrad = l > 0 || a.need_dz0;
+            const uint32_t tDl = (l == 0) ? tmem + a.c_d0 : tD;
+            const uint32_t tDwl = (l == 0) ? tmem + a.c_dw0 : tDw + ((l & 1) ? a.dw_alt : 0);
+            const bool swapped = streaming && (l == a.stream_a || l == a.stream_b);
+            if (do_dgrad) {
+              umma::mbar_wait(&bar_fg, pf);
+              pf ^= 1;
+              umma::tc_fence_after();
+              if (swapped) umma::mbar_wait(&bar_ring, pr);
+              TCB_STAMP_ANY(32 + 4 * l);
+              tcb_issue_dgrad(lay, l, wblk_smem + 4u * a.woff[l], tDl, tAhi, tAlo);
+              umma::mma_commit(&bar_d);
+              TCB_STAMP_ANY(33 + 4 * l);
+              if (a.opt & 4) {  // diagnosis: when does this batch really complete?  (bar_d parity as the workers track it)
+                umma::mbar_spin(&bar_d, pd);
+                TCB_STAMP_ANY(48 + l);
+              }
+              pd ^= 1;
+            }
+            if (swapped) pr ^= 1;
+            const int gz = (lay.Kd[l] + 31) >> 5;
+            const uint32_t s_zhi = umma::smem_u32(st_base), s_zlo = s_zhi + 4u * gz * ROWS * 32;
+            for (int h = 0; h < NH; ++h) {
+              umma::mbar_wait(&bar_fs, ps);
+              ps ^= 1;
+              umma::tc_fence_after();
+              TCB_STAMP_ANY(34 + 4 * l);
+              tcb_issue_wgrad<ROWS>(lay, l, s_ghi, s_glo, s_zhi, s_zlo, tDwl, h);
+              umma::mma_commit(&bar_w);
+              TCB_STAMP_ANY(35 + 4 * l);
+            }
+          }
+          ++dbg_tile;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+  // ================= WORKERS =================
 
   // register accumulators of dW^T: per layer 8 values of the 16-column chunk (k = c0 + 8*(lane>=16) + j, n = 16*lq +
   // lane%16) plus up to 2 values of the columns beyond 64 (k = 64 + 8*t + 2*q + (lane>=16)), and one bias-gradient value
@@ -287,7 +401,6 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   }
   const bool upper = lane >= 16;
   const int n_items = NODE ? a.tg.N : a.tg.rowptr[a.tg.N];  // edges in the edge phase
-  int dbg_tile = 0;
 
   for (int unit = blockIdx.x; unit < a.tg.n_units; unit += gridDim.x) {
     int n0, n1, kbeg, kend;
@@ -302,7 +415,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       kbeg = a.tg.rowptr[n0];
       kend = a.tg.rowptr[n1];
       if (a.has_dst_side) {
-        for (int item = tid; item < (n1 - n0) * a.dx; item += TCB_THREADS) {
+        for (int item = tid; item < (n1 - n0) * a.dx; item += NW) {
           const int jj = item / a.dx;
           if (a.tg.rowptr[n0 + jj] == a.tg.rowptr[n0 + jj + 1]) a.dxdst[(size_t)n0 * a.dx + item] = 0.f;
         }
@@ -355,32 +468,11 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           umma::tmem_st16(tAlo + lane_addr + cc, lo);
         }
         umma::tmem_wait_st();
-        umma::tc_fence_before();
-        __syncthreads();
+        arrive(&bar_fg);
 #pragma unroll 1
         for (int l = 0; l < L - 1; ++l) {
-          const int nmma = 3 * (lay.Kd[l] / 8), isplit = (nmma + 1) / 2;
-          // the other 31 lanes of an issuing warp park on __syncwarp: lanes spinning on an mbarrier would keep the
-          // issuing lane from being scheduled for > 1000 cycles (measured)
-          if (warp == 0) {
-            if (umma::elect_one_sync()) {
-              umma::tc_fence_after();
-              tcb_issue_fwd_part(lay, l, wblk_smem, tD, tAhi, tAlo, 0, isplit);
-              umma::mma_commit(&bar_d);
-            }
-            __syncwarp();
-          } else if (warp == 1) {
-            if (umma::elect_one_sync()) {
-              umma::tc_fence_after();
-              tcb_issue_fwd_part(lay, l, wblk_smem, tDw, tAhi, tAlo, isplit, nmma);
-              umma::mma_commit(&bar_w);
-            }
-            __syncwarp();
-          }
           mbar_wait_warp(&bar_d, ph_d, a.opt);
-          mbar_wait_warp(&bar_w, ph_w, a.opt);
           ph_d ^= 1;
-          ph_w ^= 1;
           umma::tc_fence_after();
           const int Np = lay.Np[l];
           if (c0 < Np) {
@@ -388,7 +480,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             umma::tmem_ld16(tD + lane_addr + c0, v);
             umma::tmem_ld16(tDw + lane_addr + c0, w);
             // bias row of the weight image (row Kd, unswizzled because Kd % 4 == 0): hi + lo
-            const float* bh = wblk + lay.img_off[l] + (c0 >> 5) * lay.Kp[l] * 32 + lay.Kd[l] * 32 + (c0 & 31);
+            const float* bh = wblk + a.woff[l] + (c0 >> 5) * lay.Kp[l] * 32 + lay.Kd[l] * 32 + (c0 & 31);
             const float* bl = bh + lay.img_floats[l];
             float f[16];
 #pragma unroll
@@ -411,8 +503,16 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             }
           }
           umma::tmem_wait_st();
-          umma::tc_fence_before();
-          __syncthreads();
+          if (l < L - 2) arrive(&bar_fg);  // the next recomputed layer's A operand is in place
+          // layer stream_a's image (MMAs done, bias row read by every worker) makes room for stream_b's, first needed by
+          // the input-gradient MMAs of the last layer -- at least one recomputed layer away
+          if (streaming && l == a.stream_a) {
+            worker_sync();
+            if (tid == 0) {
+              umma::fence_async_smem();
+              load_layer(a.stream_b, &bar_ring);
+            }
+          }
         }
       }
 
@@ -490,62 +590,47 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         const bool active = c0 < Np;
         const bool do_dgrad = l > 0 || a.need_dz0;
         const uint32_t tDl = (l == 0) ? tmem + a.c_d0 : tD;
-        // with two dW^T accumulators (dw_alt) layer l + 1's block is collected while layer l is being staged, by the
-        // warps that are idle in that half; with one it has to be collected before this layer's first MMA batch
+        // with two dW^T accumulators (dw_alt) a layer's block is collected two layers later, off the critical path; with one
+        // it has to be collected before the next layer's weight-gradient batch is issued
         const bool defer = a.dw_alt > 0;
-        const uint32_t tDwl = (l == 0) ? tmem + a.c_dw0 : tDw + ((l & 1) ? a.dw_alt : 0);
-        const uint32_t tDwp = tDw + (((l + 1) & 1) ? a.dw_alt : 0);  // layer l + 1's accumulator (l + 1 >= 1)
         const int gz = (Kd + 31) >> 5;  // 32-column groups of this layer's staged Z images
         float* st_zhi = st_base;
-        float* st_zlo = st_base + gz * TCB_HALF * 32;
-        // the previous layer's dW^T block (its second MMA batch also frees the staging buffer)
-        if (l < L - 1) {
-          mbar_wait_warp(&bar_w, ph_w, a.opt);
-          ph_w ^= 1;
-          umma::tc_fence_after();
-          if (!defer) collect_dw(l + 1, tDwp);
-        }
+        float* st_zlo = st_base + gz * ROWS * 32;
         TCB_STAMP(3 + 6 * l);
-        if (active) {
-          if (do_dgrad) {
+        // (A) G_{l+1} -> TMEM A operand; the issuer queues the input-gradient MMAs dZ_l = G W_l^T behind the previous layer's
+        // weight-gradient batch
+        if (do_dgrad) {
+          if (active) {
             uint32_t hi[16], lo[16];
             tc_split16(g, hi, lo);
             umma::tmem_st16(tAhi + lane_addr + c0, hi);
             umma::tmem_st16(tAlo + lane_addr + c0, lo);
           }
-        }
-        const bool early = (a.opt & 1) == 0;
-        if (do_dgrad && early) {
           umma::tmem_wait_st();
-          umma::tc_fence_before();
-          __syncthreads();
-          if (warp == 2) {
-            if (umma::elect_one_sync()) {
-              umma::tc_fence_after();
-              tcb_issue_dgrad(lay, l, wblk_smem, tDl, tAhi, tAlo);
-              umma::mma_commit(&bar_d);
-            }
-            __syncwarp();
-          }
+          arrive(&bar_fg);
         }
+        // (B) deferred: the dW^T block of layer l + 2 (complete since the previous iteration's (C); its accumulator is the
+        // one this layer's weight-gradient batch will overwrite)
+        if (defer && l + 2 <= L - 1) collect_dw(l + 2, tDw + (((l + 2) & 1) ? a.dw_alt : 0));
+        // (C) the previous layer's weight-gradient batch has drained the staging buffer
+        if (l < L - 1) {
+          mbar_wait_warp(&bar_w, ph_w, a.opt);
+          ph_w ^= 1;
+          umma::tc_fence_after();
+          if (!defer) collect_dw(l + 1, tDw);
+        }
+        TCB_STAMP(4 + 6 * l);
+        // (D) stage G_{l+1} and Z_l as MN-major hi/lo images -- the whole tile at once (FULL), or rows 0..63 and then, once
+        // that batch has drained the buffer, rows 64..127 -- while the input-gradient MMAs run
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NH; ++h) {
           if (h == 1) {
             mbar_wait_warp(&bar_w, ph_w, a.opt);  // the first half has been consumed
             ph_w ^= 1;
           }
-          if ((lq >> 1) != h) {
-            // idle in this half: bias gradient (column sums of G over this warp's 32 rows) and the deferred dW^T block
-            if (active) {
-              const float cs = tcb_colsum16(g, lane);
-#pragma unroll
-              for (int ll = 0; ll < TCB_MAXL; ++ll)
-                if (ll == l) dbacc[ll] += cs;
-            }
-            if (defer && l < L - 1) collect_dw(l + 1, tDwp);
-          } else {
-            const int r = row - TCB_HALF * h;
-            if (active) stage_chunk(st_ghi, st_glo, r, c0, g);
+          if (FULL || (lq >> 1) == h) {
+            const int r = row - ROWS * h;
+            if (active) stage_chunk<ROWS>(st_ghi, st_glo, r, c0, g);
             // Z_l: the gathered input for l == 0, else the FP32 copy kept in TMEM by the recompute
             for (int cc = c0; cc < Kd; cc += 64) {
               float z[16];
@@ -564,33 +649,36 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) z[j] = __uint_as_float(v[j]);
               }
-              stage_chunk(st_zhi, st_zlo, r, cc, z);
+              stage_chunk<ROWS>(st_zhi, st_zlo, r, cc, z);
             }
           }
           umma::fence_async_smem();
-          if (!early) umma::tmem_wait_st();
-          umma::tc_fence_before();
-          __syncthreads();
-          if (!early && do_dgrad && h == 0 && warp == 2) {
-            if (umma::elect_one_sync()) {
-              umma::tc_fence_after();
-              tcb_issue_dgrad(lay, l, wblk_smem, tDl, tAhi, tAlo);
-              umma::mma_commit(&bar_d);
+          if (h == 0) {
+            TCB_STAMP(5 + 6 * l);
+            // (E) bias gradient: column sums of G over this warp's 32 rows
+            if (active) {
+              const float cs = tcb_colsum16(g, lane);
+#pragma unroll
+              for (int ll = 0; ll < TCB_MAXL; ++ll)
+                if (ll == l) dbacc[ll] += cs;
             }
-            __syncwarp();
-          }
-          if (warp == (h == 0 ? 3 : 1)) {
-            if (umma::elect_one_sync()) {
-              umma::tc_fence_after();
-              tcb_issue_wgrad(lay, l, s_ghi, s_glo, umma::smem_u32(st_zhi), umma::smem_u32(st_zlo), tDwl, h);
-              umma::mma_commit(&bar_w);
+            // (F) dZ_l is complete.  Waited for BEFORE the weight-gradient batch is released: the tensor pipe runs its
+            // batches in order anyway, and once the shared-memory-bound SS MMAs are running an mbarrier poll from these
+            // warps is not served until they end (measured: tools/tcb_phases.py)
+            if (do_dgrad) {
+              mbar_wait_warp(&bar_d, ph_d, a.opt);
+              ph_d ^= 1;
             }
-            __syncwarp();
+            TCB_STAMP(6 + 6 * l);
           }
+          // (G) staged images ready: the issuer releases the weight-gradient MMAs dW_l^T += G^T Z
+          arrive(&bar_fs);
         }
-        if (do_dgrad) {
-          mbar_wait_warp(&bar_d, ph_d, a.opt);
-          ph_d ^= 1;
+        // the last layer's image has served its only use: bring stream_a's back (needed again by its own input-gradient
+        // MMAs further down and by the next tile's recompute)
+        if (streaming && l == a.stream_b && tid == 0) {
+          umma::fence_async_smem();
+          load_layer(a.stream_a, &bar_ring);
         }
         TCB_STAMP(7 + 6 * l);
         umma::tc_fence_after();
@@ -645,20 +733,21 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               }
             }
           }
-          // layer 0's dW^T block closes the tile
+          // layer 1's block (deferred) and layer 0's close the tile
+          if (a.dw_alt > 0 && L > 1) collect_dw(1, tDw + a.dw_alt);
           mbar_wait_warp(&bar_w, ph_w, a.opt);
           ph_w ^= 1;
           umma::tc_fence_after();
-          collect_dw(0, tDwl);
+          collect_dw(0, (l == 0) ? tmem + a.c_dw0 : tDw);
         }
         umma::tc_fence_before();
       }
 
       if (!NODE && a.need_dz0) {
-        __syncthreads();
+        worker_sync();
         const int dx = a.dx, ldz = Kd0 + 1;
         // source side: one row per edge, reduced later over the src-sorted transpose
-        for (int item = tid; item < ne * dx; item += TCB_THREADS) {
+        for (int item = tid; item < ne * dx; item += NW) {
           const int e = item / dx, c = item - e * dx;
           float v = 0.f;
           for (int si = 0; si < a.n_segs; ++si) {
@@ -671,7 +760,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         }
         // destination side: sequential over the row's edges, carried across tiles through dxdst itself
         if (a.has_dst_side) {
-          for (int item = tid; item < (n1 - n0) * dx; item += TCB_THREADS) {
+          for (int item = tid; item < (n1 - n0) * dx; item += NW) {
             const int jj = item / dx, c = item - jj * dx;
             const int j = n0 + jj;
             const int r0 = a.tg.rowptr[j], r1 = a.tg.rowptr[j + 1];
@@ -690,7 +779,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           }
         }
       }
-      __syncthreads();
+      worker_sync();
       TCB_STAMP(27);
       ++dbg_tile;
     }
@@ -715,15 +804,15 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
     }
     // bias gradients: the four row quarters of a column are summed in fixed order through shared memory
     float* dbx = reinterpret_cast<float*>(smem + a.off_stage);  // [L][4 quarters][64 columns]; the staging buffer is free now
-    __syncthreads();
+    worker_sync();
     if ((lane & 1) == 0) {
       const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 #pragma unroll
       for (int l = 0; l < TCB_MAXL; ++l)
         if (l < L) dbx[(l * 4 + lq) * 64 + col] = dbacc[l];
     }
-    __syncthreads();
-    for (int item = tid; item < L * 64; item += TCB_THREADS) {
+    worker_sync();
+    for (int item = tid; item < L * 64; item += NW) {
       const int l = item >> 6, col = item & 63;
       if (col < lay.N[l] && a.b_off[l] >= 0) {
         const float* pq = dbx + l * 256 + col;
@@ -731,6 +820,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       }
     }
   }
+  }  // workers
   umma::tc_fence_before();
   __syncthreads();
   if (tid < 32) umma::tmem_dealloc(tmem, a.tmem_cols);

@@ -29,7 +29,8 @@ struct TcLayout {
   int tmem_cols;                                   // allocation: power of two >= 32
 };
 
-constexpr int TCB_THREADS = 512;
+constexpr int TCB_WORKERS = 512;  // 16 worker warps: thread = (tile row, 16-column chunk)
+constexpr int TCB_THREADS = TCB_WORKERS + 32;  // + one dedicated MMA-issuing warp
 constexpr int TCB_MAXL = 4;     // register accumulators for at most 4 layers
 constexpr int TCB_HALF = 64;    // rows per weight-gradient staging pass
 
@@ -41,6 +42,11 @@ struct TcBwdPhase {
   int c_zs[NGPDE_MAX_LAYERS] = {0};
   int c_a = 0, a_width = 0, c_d = 0, c_dw = 0, c_d0 = 0, c_dw0 = 0, tmem_cols = 0, dw_alt = 0;
   int off_cols = 0, off_stage = 0, off_dz = 0, nzh = 0, nzl = 0;
+  // shared-memory placement of the weight images: float offset of layer l's hi image; full = whole-tile staging of the
+  // weight-gradient operands, which may need layers stream_a / stream_b to share one slot (ngpde_tc_bwd.cuh)
+  int woff[NGPDE_MAX_LAYERS] = {0};
+  int stream_a = -1, stream_b = -1;
+  bool full = false;
   size_t ws_off = 0;
   int grid = 0;
 };

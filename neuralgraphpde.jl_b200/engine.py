@@ -17,7 +17,9 @@ Tensor = torch.Tensor
 
 
 class RhsRunner:
-    def __init__(self, layer, x: Tensor, ps, st, use_cuda_graph: bool = False):
+    def __init__(self, layer, x: Tensor, ps, st, use_cuda_graph: bool = False, share: Optional["RhsRunner"] = None):
+        """`share`: another runner of the same layer / graph whose parameter buffers and workspaces this one uses too
+        (the stages of one Runge-Kutta step: same parameters, calls strictly one after the other)."""
         if not hasattr(layer, "prepare"):
             raise TypeError("RhsRunner binds one of ExplicitEdgeConv / VMHConv / MPPDEConv / GNOConv")
         self.lib = _lib.load()
@@ -26,8 +28,11 @@ class RhsRunner:
         dev = x_rm.device
         self.dev = dev
         self.x = x_rm.detach().clone()
-        self.phi = phi.detach().contiguous()
-        self.node = None if node is None else node.detach().contiguous()
+        if share is not None:
+            self.phi, self.node = share.phi, share.node
+        else:
+            self.phi = phi.detach().contiguous().clone()
+            self.node = None if node is None else node.detach().contiguous().clone()
         self.has_node = self.desc.node.n_layers > 0
         N = self.x.shape[0]
         self.mbar = torch.empty((N, dm), dtype=torch.float32, device=dev)
@@ -49,8 +54,11 @@ class RhsRunner:
             nbytes_f = self.lib.ngpde_conv_workspace_bytes(self.handle, C.byref(self.desc), 0)
             if nbytes_f == 0:
                 _lib.check(-1)
-        self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
-        self.ws_fwd = torch.empty(int(nbytes_f), dtype=torch.uint8, device=dev)
+        if share is not None and share.ws.numel() >= nbytes and share.ws_fwd.numel() >= nbytes_f:
+            self.ws, self.ws_fwd = share.ws, share.ws_fwd
+        else:
+            self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            self.ws_fwd = torch.empty(int(nbytes_f), dtype=torch.uint8, device=dev)
         p = ops._ptr
         self.io = _lib.ConvIO(x=p(self.x), snode=p(self.snode), edata=p(self.edata), theta=p(self.theta),
                               phi_params=p(self.phi), node_params=p(self.node), mbar=p(self.mbar), y=p(self.y),

@@ -83,3 +83,124 @@ def solve_fixed(layer, x: Tensor, ps, st, tspan: Tuple[float, float], dt: float,
         if saveat_every and (step + 1) % saveat_every == 0:
             saved.append(u.T)
     return u.T, saved, evals
+
+
+class GraphedRK:
+    """One explicit Runge-Kutta step of `du/dt = layer(u, ps, st)[1]` and its discrete adjoint, each captured ONCE as a
+    CUDA graph and replayed per step (SURVEY.md section 8f-1; the reference's solver loop is `solve(prob, Tsit5() | RK4();
+    adaptive = false, dt)`, docs/src/tutorials/graph_node.md:53-66, VMH.md:87).
+
+    Forward graph (S = number of stages):   for s: u_s = u + dt sum_{j<s} a_sj k_j   (ngpde_axpy_stages)
+                                                   k_s = layer(u_s)                  (fused layer forward, C ABI)
+                                            u <- u + dt sum_s b_s k_s
+    Adjoint graph, given lam = dL/du_next:  for s = S..1: kbar_s = dt b_s lam + dt sum_{i>s} a_is ubar_i
+                                                          (ubar_s, dps_s) = layer VJP at u_s with cotangent kbar_s
+                                            lam <- lam + sum_s ubar_s;   dparams += sum_s dps_s
+    Both graphs contain only libngpde kernels: no Python, no allocator and no autograd bookkeeping per RHS.  The stage
+    states u_s live in the stage runners (re-established by replaying the forward graph from the step's checkpointed u), so
+    a trajectory costs O(steps) state copies, and its gradient two forward replays + one adjoint replay per step.
+    """
+
+    def __init__(self, layer, x: Tensor, ps, st, dt: float, method: str = "rk4"):
+        from .engine import RhsRunner
+        self.c, self.A, self.b = TABLEAUS[method]
+        self.dt, self.S = float(dt), len(self.A)
+        first = RhsRunner(layer, x, ps, st)
+        self.stage: List[RhsRunner] = [first] + [RhsRunner(layer, x, ps, st, share=first) for _ in range(self.S - 1)]
+        self.dev = first.dev
+        self.u = first.x.clone()              # [N, d] current state (row-major image of Julia's (d, N))
+        self.lam = torch.zeros_like(self.u)   # adjoint state dL/du
+        self.dparams = torch.zeros_like(first.dparams)
+        self._tmp = torch.empty_like(self.u)
+        self.fwd_graph = self.bwd_graph = None
+        self.kernels_fwd = self.kernels_bwd = None
+        self.rhs_evals = 0
+        if first.y.shape != self.u.shape:
+            raise ValueError("an ODE right-hand side must map the state onto its own shape")
+        self._capture()
+
+    # ---- the two step bodies (launch-only: safe to capture) ----
+    def _fwd_body(self):
+        from .ops import axpy_stages
+        dt = self.dt
+        for s_, r in enumerate(self.stage):
+            nz = [(dt * a, self.stage[j].y) for j, a in enumerate(self.A[s_]) if a != 0.0]
+            axpy_stages(r.x, self.u, [k for _, k in nz], [c for c, _ in nz])
+            r.forward()
+        nz = [(dt * w, self.stage[j].y) for j, w in enumerate(self.b) if w != 0.0]
+        axpy_stages(self.u, self.u, [k for _, k in nz], [c for c, _ in nz])
+
+    def _bwd_body(self):
+        from .ops import axpy_stages
+        dt = self.dt
+        for s_ in range(self.S - 1, -1, -1):
+            r = self.stage[s_]
+            ks, cs = [self.lam], [dt * self.b[s_]]
+            for i in range(s_ + 1, self.S):
+                a = self.A[i][s_] if s_ < len(self.A[i]) else 0.0
+                if a != 0.0:
+                    ks.append(self.stage[i].dx)
+                    cs.append(dt * a)
+            axpy_stages(r.dy, None, ks, cs)   # kbar_s (u = NULL stands for zeros)
+            r.backward()                      # -> r.dx = ubar_s, r.dparams = dps_s
+        axpy_stages(self.lam, self.lam, [r.dx for r in self.stage], [1.0] * self.S)
+        axpy_stages(self.dparams, self.dparams, [r.dparams for r in self.stage], [1.0] * self.S)
+
+    def _capture(self):
+        from . import _lib
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        u0 = self.u.clone()
+        with torch.cuda.stream(side):   # warm-up outside capture (lazy layout builds, function attributes)
+            self._fwd_body()
+            self._bwd_body()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        graphs = []
+        for body in (self._fwd_body, self._bwd_body):
+            g = torch.cuda.CUDAGraph(keep_graph=True)
+            with torch.cuda.graph(g):
+                body()
+            try:
+                nk, _ = _lib.cuda_graph_kernel_nodes(g.raw_cuda_graph())
+            except Exception:  # noqa: BLE001
+                nk = None
+            g.instantiate()
+            graphs.append((g, nk))
+        (self.fwd_graph, self.kernels_fwd), (self.bwd_graph, self.kernels_bwd) = graphs
+        self.u.copy_(u0)
+        self.lam.zero_()
+        self.dparams.zero_()
+
+    # ---- public ----
+    def set_params(self, ps) -> None:
+        self.stage[0].set_params(ps)  # the other stages share its parameter buffers
+
+    def step(self) -> Tensor:
+        """u <- RK step(u): one graph replay."""
+        self.fwd_graph.replay()
+        self.rhs_evals += self.S
+        return self.u
+
+    def solve(self, u0: Tensor, nsteps: int, keep: bool = True) -> Tensor:
+        """Integrate `nsteps` steps from u0 (Julia-shaped (d, N) or row-major [N, d]); keeps the per-step states for `adjoint`."""
+        u0 = u0.T if u0.shape != self.u.shape else u0
+        self.u.copy_(u0)
+        self._ckpt = [] if keep else None
+        for _ in range(nsteps):
+            if keep:
+                self._ckpt.append(self.u.clone())
+            self.step()
+        return self.u
+
+    def adjoint(self, dL_duT: Tensor):
+        """Discrete adjoint of the last `solve`: returns (dL/du0 [N, d], dL/dparams flat [dphi | pad | dnode])."""
+        g = dL_duT.T if dL_duT.shape != self.u.shape else dL_duT
+        self.lam.copy_(g)
+        self.dparams.zero_()
+        for u_n in reversed(self._ckpt):
+            self.u.copy_(u_n)
+            self.fwd_graph.replay()   # re-establish the stage states u_s, k_s of this step
+            self.bwd_graph.replay()
+            self.rhs_evals += self.S
+        return self.lam, self.dparams

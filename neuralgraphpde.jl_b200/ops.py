@@ -178,14 +178,14 @@ def aggregate(handle, aggr: str, x_rm: Tensor, w: Optional[Tensor] = None) -> Te
     return out
 
 
-def axpy_stages(out: Tensor, u: Tensor, ks, coefs) -> Tensor:
-    """out = u + sum_i coefs[i] * ks[i]  (one fused kernel; ODE stage glue)."""
+def axpy_stages(out: Tensor, u: Optional[Tensor], ks, coefs) -> Tensor:
+    """out = u + sum_i coefs[i] * ks[i]  (one fused kernel; ODE stage glue).  u = None stands for zeros; out may alias u."""
     lib = _lib.load()
     nk = len(ks)
     arr = (C.c_void_p * max(nk, 1))(*[k.data_ptr() for k in ks])
     cf = (C.c_float * max(nk, 1))(*[float(c) for c in coefs])
-    with torch.cuda.device(u.device):
-        _lib.check(lib.ngpde_axpy_stages(out.data_ptr(), u.data_ptr(), arr, cf, nk, u.numel(), _stream(u.device)))
+    with torch.cuda.device(out.device):
+        _lib.check(lib.ngpde_axpy_stages(out.data_ptr(), _ptr(u), arr, cf, nk, out.numel(), _stream(out.device)))
     LAUNCHES["count"] += 1
     return out
 

@@ -60,7 +60,7 @@ def check_layer(layer, x, ps, st, g, tol=TOL, grads=True, block_tol=None, **kw):
     for name, a, b32, b64, blocks in groups:
         e64, e32, noise = block_relerrs(a, b64, blocks), block_relerrs(a, b32, blocks), block_relerrs(b32, b64, blocks)
         for k in e64:
-            bar = max(tol, 2.0 * noise[k])
+            bar = max(tol if block_tol is None else block_tol, 2.0 * noise[k])
             if not (e64[k] <= bar and e32[k] <= bar):
                 bad[k] = {"vs_f64": e64[k], "vs_f32": e32[k], "oracle_f32_vs_f64": noise[k]}
         if e64:

@@ -16,26 +16,29 @@ r.step()
 torch.cuda.synchronize()
 _lib.load().ngpde_debug_buffer(None)
 t = buf.cpu().view(8, 64)
-names = {0: "start", 1: "recompute", 2: "G_L"}
+names = {0: "start", 1: "gather + recompute", 2: "G_L load"}
 for l in (3, 2, 1, 0):
-    for k, nm in enumerate(["A:collect", "B:stage0+sync", "D:wait wgrad0", "D:stage1+sync", "F:wait dgrad", "F:next G"]):
+    for k, nm in enumerate(["G->TMEM + dgrad issue (from prev end)", "wait prev wgrad", "stage + wgrad issue", "colsum/collect", "wait dgrad"]):
         names[3 + 6 * l + k] = f"L{l} {nm}"
 names[27] = "dz0 scatter + end"
-order = [0, 1, 2] + [3 + 6 * l + k for l in (3, 2, 1, 0) for k in range(6)] + [27]
-for tile in (3,):
+order = [0, 1, 2] + [3 + 6 * l + k for l in (3, 2, 1, 0) for k in range(5)] + [27]
+for tile in (2, 5):
     print("tile", tile, "total cycles", int(t[tile, 27] - t[tile, 0]))
     prev = int(t[tile, 0])
     for sl in order[1:]:
         v = int(t[tile, sl])
-        print(f"   {names[sl]:22s} {v - prev:7d}")
+        print(f"   {names[sl]:48s} {v - prev:7d}   (t = {v - int(t[tile, 0])})")
         prev = v
+print("tile starts:", [int(t[i, 0] - t[0, 0]) for i in range(8)])
 
-t3 = t[3]
-base = int(t3[0])
-for l in (3, 2, 1, 0):
-    b = 32 + 6 * l
-    f = lambda i: int(t3[i]) - base
-    print(f"L{l}: layer top {f(3 + 6 * l)} | dgrad issue {f(b)}..{f(b + 1)} | S2 {f(4 + 6 * l)} | wgrad0 issue {f(b + 2)}..{f(b + 3)} | wgrad0 done(seen) {f(5 + 6 * l)} | "
-          f"S3 {f(6 + 6 * l)} | wgrad1 issue {f(b + 4)}..{f(b + 5)} | dgrad done(seen) {f(7 + 6 * l)} | next G done {f(8 + 6 * l)} | dgrad done (issuer polls) {f(56 + l)}")
-
-print("last layer: S3", int(t3[6]) - base, "| before bar_d wait", int(t3[60]) - base, "| lane 0 after wait", int(t3[61]) - base, "| after syncwarp", int(t3[7]) - base)
+for tile in (2, 5):
+    base = int(t[tile, 0])
+    for l in (3, 2, 1, 0):
+        f = lambda i: int(t[tile, i]) - base
+        print(f"tile {tile} L{l}: layer top {f(3 + 6 * l)} | dgrad issue {f(32 + 4 * l)}..{f(33 + 4 * l)} | prev wgrad seen done {f(4 + 6 * l)} | "
+              f"dgrad done (issuer polls, NGPDE_TCB_OPT=4) {f(48 + l)} | wgrad issue {f(34 + 4 * l)}..{f(35 + 4 * l)} | staged+issued {f(5 + 6 * l)} | collected {f(6 + 6 * l)} | dgrad seen done {f(7 + 6 * l)}")
+for tile in (5,):
+    base = int(t[tile, 0])
+    for l in (3, 2, 1, 0):
+        f = lambda i: int(t[tile, i]) - base
+        print(f"tile {tile} L{l}: collected {f(6 + 6 * l)} | warp 5 lane 0 poll returned {f(52 + l)} | lane 31 reached __syncwarp {f(56 + l)} | after __syncwarp {f(7 + 6 * l)}")
