@@ -195,15 +195,21 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
 constexpr int TCB_STAMP_TID = 160;  // warp 5 (rows 32..63, chunk 1): a worker that never issues MMAs
 
 // column sums of a 16-value chunk over the 32 rows of a warp (fixed butterfly order): afterwards every lane holds the
-// total of column  8*bit4 + 4*bit3 + 2*bit2 + bit1  of its lane id (lanes 2i and 2i+1 hold the same column)
-__device__ __forceinline__ float tcb_colsum16(const float (&g)[16], int lane) {
-  float w[8], x[4], y[2];
-  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+// total of column  8*bit4 + 4*bit3 + 2*bit2 + bit1  of its lane id (lanes 2i and 2i+1 hold the same column).
+// Split into three stages so that the caller can put independent work between them: while MMAs stream their operands
+// from shared memory a shuffle takes ~250 cycles instead of ~25 (same data path; measured with tools/mma_rate.cu), and the
+// five dependent levels of the butterfly would otherwise cost > 1000 cycles of pure latency per layer.
+__device__ __forceinline__ void tcb_colsum_a(const float (&g)[16], int lane, float (&w)[8]) {
+  const bool b4 = lane & 16;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float send = b4 ? g[j] : g[8 + j], keep = b4 ? g[8 + j] : g[j];
     w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
   }
+}
+__device__ __forceinline__ void tcb_colsum_b(const float (&w)[8], int lane, float (&y)[2]) {
+  float x[4];
+  const bool b3 = lane & 8, b2 = lane & 4;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float send = b3 ? w[j] : w[4 + j], keep = b3 ? w[4 + j] : w[j];
@@ -214,6 +220,9 @@ __device__ __forceinline__ float tcb_colsum16(const float (&g)[16], int lane) {
     const float send = b2 ? x[j] : x[2 + j], keep = b2 ? x[2 + j] : x[j];
     y[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
   }
+}
+__device__ __forceinline__ float tcb_colsum_c(const float (&y)[2], int lane) {
+  const bool b1 = lane & 2;
   const float send = b1 ? y[0] : y[1], keep = b1 ? y[1] : y[0];
   float z = keep + __shfl_xor_sync(0xffffffffu, send, 2);
   z += __shfl_xor_sync(0xffffffffu, z, 1);
@@ -338,13 +347,12 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           kend = a.tg.rowptr[a.tg.unit_ptr[unit + 1]];
         }
         for (int k0 = kbeg; k0 < kend; k0 += TC_TILE) {
-          for (int l = 0; l < L - 1; ++l) {  // recompute: two accumulators (tD, tDw), summed by the epilogue
-            const int nmma = 3 * (lay.Kd[l] / 8), isplit = (nmma + 1) / 2;
+          for (int l = 0; l < L - 1; ++l) {  // recompute
+            const int nmma = 3 * (lay.Kd[l] / 8);
             umma::mbar_wait(&bar_fg, pf);
             pf ^= 1;
             umma::tc_fence_after();
-            tcb_issue_fwd_part(lay, l, wblk_smem + 4u * a.woff[l], tD, tAhi, tAlo, 0, isplit);
-            tcb_issue_fwd_part(lay, l, wblk_smem + 4u * a.woff[l], tDw, tAhi, tAlo, isplit, nmma);
+            tcb_issue_fwd_part(lay, l, wblk_smem + 4u * a.woff[l], tD, tAhi, tAlo, 0, nmma);
             umma::mma_commit(&bar_d);
             pd ^= 1;
           }
@@ -391,13 +399,14 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 
   // register accumulators of dW^T: per layer 8 values of the 16-column chunk (k = c0 + 8*(lane>=16) + j, n = 16*lq +
   // lane%16) plus up to 2 values of the columns beyond 64 (k = 64 + 8*t + 2*q + (lane>=16)), and one bias-gradient value
-  float dwacc[TCB_MAXL][10];
+  constexpr int NACC = FULL ? 8 : 10;  // FULL kernels only take layers with Kd <= 64: no columns beyond 64
+  float dwacc[TCB_MAXL][NACC];
   float dbacc[TCB_MAXL];
 #pragma unroll
   for (int l = 0; l < TCB_MAXL; ++l) {
     dbacc[l] = 0.f;
 #pragma unroll
-    for (int j = 0; j < 10; ++j) dwacc[l][j] = 0.f;
+    for (int j = 0; j < NACC; ++j) dwacc[l][j] = 0.f;
   }
   const bool upper = lane >= 16;
   const int n_items = NODE ? a.tg.N : a.tg.rowptr[a.tg.N];  // edges in the edge phase
@@ -454,43 +463,48 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 
       // ---- 1. forward recompute: Z_1 .. Z_{L-1} (two issuing warps, accumulators tD and tDw, bias added here) ----
       if (L > 1) {
-        for (int cc = c0; cc < Kd0; cc += 64) {
-          uint32_t hi[16], lo[16];
+        // the four chunk warps of a row share the gather: a quarter of the Kd0 columns each, four at a time
+        const int gq = Kd0 >> 2;
+        for (int cc = q * gq; cc < (q + 1) * gq; cc += 4) {
+          uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 4; ++j) {
             const float v = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
             if (keep_z0) DZ[row * (Kd0 + 1) + cc + j] = v;  // re-read by layer 0's weight-gradient staging
             const float h = umma::tf32_hi(v);
             hi[j] = __float_as_uint(h);
             lo[j] = __float_as_uint(umma::tf32_lo(v, h));
           }
-          umma::tmem_st16(tAhi + lane_addr + cc, hi);
-          umma::tmem_st16(tAlo + lane_addr + cc, lo);
+          umma::tmem_st4(tAhi + lane_addr + cc, hi);
+          umma::tmem_st4(tAlo + lane_addr + cc, lo);
         }
         umma::tmem_wait_st();
         arrive(&bar_fg);
 #pragma unroll 1
         for (int l = 0; l < L - 1; ++l) {
-          mbar_wait_warp(&bar_d, ph_d, a.opt);
-          ph_d ^= 1;
-          umma::tc_fence_after();
           const int Np = lay.Np[l];
+          // bias row of the weight image (row Kd, unswizzled because Kd % 4 == 0): hi + lo.  Loaded BEFORE the wait: a
+          // shared-memory load issued while the MMAs stream their operands takes hundreds of cycles
+          float f[16];
           if (c0 < Np) {
-            uint32_t v[16], w[16];
-            umma::tmem_ld16(tD + lane_addr + c0, v);
-            umma::tmem_ld16(tDw + lane_addr + c0, w);
-            // bias row of the weight image (row Kd, unswizzled because Kd % 4 == 0): hi + lo
             const float* bh = wblk + a.woff[l] + (c0 >> 5) * lay.Kp[l] * 32 + lay.Kd[l] * 32 + (c0 & 31);
             const float* bl = bh + lay.img_floats[l];
-            float f[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               const float4 h4 = *reinterpret_cast<const float4*>(bh + j), l4 = *reinterpret_cast<const float4*>(bl + j);
               f[j] = h4.x + l4.x; f[j + 1] = h4.y + l4.y; f[j + 2] = h4.z + l4.z; f[j + 3] = h4.w + l4.w;
             }
+          }
+          mbar_wait_warp(&bar_d, ph_d, a.opt);
+          ph_d ^= 1;
+          umma::tc_fence_after();
+          TCB_STAMP(8 + 2 * l);
+          if (c0 < Np) {
+            uint32_t v[16];
+            umma::tmem_ld16(tD + lane_addr + c0, v);
             umma::tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += __uint_as_float(v[j]) + __uint_as_float(w[j]);
+            for (int j = 0; j < 16; ++j) f[j] += __uint_as_float(v[j]);
             tc_act16(a.act[l], f);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(f[j]);
@@ -543,6 +557,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         }
       }
 
+      // bias gradient = column sums of G: the butterfly is spread over the layer body (see tcb_colsum_a)
+      float cw[8];
+      tcb_colsum_a(g, lane, cw);
       TCB_STAMP(2);
       // ---- 3. back through the layers.  Per layer: G -> TMEM A operand, then warp 2 (idle while rows 0..63 are staged)
       // issues the input-gradient MMAs; rows 0..63 of G and Z are staged and warp 3 issues their weight-gradient MMAs;
@@ -550,9 +567,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       // is formed from dZ while it runs and the dW^T block is collected at the top of the following layer.  (The layer
       // loop is deliberately NOT unrolled: the unrolled kernel spent its time in instruction-cache misses.)
       auto collect_dw = [&](int l, uint32_t tDwl) {
-        float add[10];
+        float add[NACC];
 #pragma unroll
-        for (int j = 0; j < 10; ++j) add[j] = 0.f;
+        for (int j = 0; j < NACC; ++j) add[j] = 0.f;
         if (c0 < min(lay.Kd[l], 64)) {
           uint32_t v[16];
           umma::tmem_ld16(tDwl + lane_addr + c0, v);
@@ -564,7 +581,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           }
         }
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < NACC - 8; ++t) {
           if (64 + 8 * t < lay.Kd[l]) {
             uint32_t w8[8];
             umma::tmem_ld8(tDwl + lane_addr + 64 + 8 * t, w8);
@@ -580,7 +597,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         for (int ll = 0; ll < TCB_MAXL; ++ll) {
           if (ll == l) {
 #pragma unroll
-            for (int j = 0; j < 10; ++j) dwacc[ll][j] += add[j];
+            for (int j = 0; j < NACC; ++j) dwacc[ll][j] += add[j];
           }
         }
       };
@@ -619,6 +636,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           umma::tc_fence_after();
           if (!defer) collect_dw(l + 1, tDw);
         }
+        float cy[2];
+        tcb_colsum_b(cw, lane, cy);
         TCB_STAMP(4 + 6 * l);
         // (D) stage G_{l+1} and Z_l as MN-major hi/lo images -- the whole tile at once (FULL), or rows 0..63 and then, once
         // that batch has drained the buffer, rows 64..127 -- while the input-gradient MMAs run
@@ -656,17 +675,28 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           if (h == 0) {
             TCB_STAMP(5 + 6 * l);
             // (E) bias gradient: column sums of G over this warp's 32 rows
-            if (active) {
-              const float cs = tcb_colsum16(g, lane);
+            {
+              const float cs = tcb_colsum_c(cy, lane);
+              if (active) {
 #pragma unroll
-              for (int ll = 0; ll < TCB_MAXL; ++ll)
-                if (ll == l) dbacc[ll] += cs;
+                for (int ll = 0; ll < TCB_MAXL; ++ll)
+                  if (ll == l) dbacc[ll] += cs;
+              }
             }
             // (F) dZ_l is complete.  Waited for BEFORE the weight-gradient batch is released: the tensor pipe runs its
             // batches in order anyway, and once the shared-memory-bound SS MMAs are running an mbarrier poll from these
             // warps is not served until they end (measured: tools/tcb_phases.py)
+            TCB_STAMP(52 + l);
             if (do_dgrad) {
-              mbar_wait_warp(&bar_d, ph_d, a.opt);
+              if (a.dbg != nullptr && blockIdx.x == 0 && dbg_tile < 8) {  // diagnosis: poll vs warp re-convergence
+                if (lane == 0) {
+                  umma::mbar_spin(&bar_d, ph_d);
+                  if (tid == TCB_STAMP_TID) a.dbg[dbg_tile * 64 + 56 + l] = clock64();
+                }
+                __syncwarp();
+              } else {
+                mbar_wait_warp(&bar_d, ph_d, a.opt);
+              }
               ph_d ^= 1;
             }
             TCB_STAMP(6 + 6 * l);
@@ -712,6 +742,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               for (int j = 0; j < 16; ++j) g[j] = 0.f;
             }
           }
+          tcb_colsum_a(g, lane, cw);
         } else {
           if (a.need_dz0) {
             // ---- 4. dZ_0 back to its sources ----
@@ -733,12 +764,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               }
             }
           }
-          // layer 1's block (deferred) and layer 0's close the tile
+          // layer 1's block (deferred); layer 0's closes the tile, after the scatter below (its MMAs are still running)
           if (a.dw_alt > 0 && L > 1) collect_dw(1, tDw + a.dw_alt);
-          mbar_wait_warp(&bar_w, ph_w, a.opt);
-          ph_w ^= 1;
-          umma::tc_fence_after();
-          collect_dw(0, (l == 0) ? tmem + a.c_dw0 : tDw);
         }
         umma::tc_fence_before();
       }
@@ -779,6 +806,12 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           }
         }
       }
+      // layer 0's dW^T block: its weight-gradient batch ran under the scatter above
+      mbar_wait_warp(&bar_w, ph_w, a.opt);
+      ph_w ^= 1;
+      umma::tc_fence_after();
+      collect_dw(0, tmem + a.c_dw0);
+      umma::tc_fence_before();
       worker_sync();
       TCB_STAMP(27);
       ++dbg_tile;
@@ -800,7 +833,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 #pragma unroll
       for (int j = 0; j < 8; ++j) put(c0 + (upper ? 8 : 0) + j, dwacc[l][j]);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) put(64 + 8 * t + 2 * q + (upper ? 1 : 0), dwacc[l][8 + t]);
+      for (int t = 0; t < NACC - 8; ++t) put(64 + 8 * t + 2 * q + (upper ? 1 : 0), dwacc[l][8 + t]);
     }
     // bias gradients: the four row quarters of a column are summed in fixed order through shared memory
     float* dbx = reinterpret_cast<float*>(smem + a.off_stage);  // [L][4 quarters][64 columns]; the staging buffer is free now

@@ -41,4 +41,8 @@ for tile in (5,):
     base = int(t[tile, 0])
     for l in (3, 2, 1, 0):
         f = lambda i: int(t[tile, i]) - base
-        print(f"tile {tile} L{l}: collected {f(6 + 6 * l)} | warp 5 lane 0 poll returned {f(52 + l)} | lane 31 reached __syncwarp {f(56 + l)} | after __syncwarp {f(7 + 6 * l)}")
+        print(f"tile {tile} L{l}: staged+fenced {f(5 + 6 * l)} | colsum done {f(52 + l)} | lane 0 poll returned {f(56 + l)} | after __syncwarp {f(6 + 6 * l)} | arrived {f(7 + 6 * l)}")
+for tile in (5,):
+    base = int(t[tile, 0])
+    f = lambda i: int(t[tile, i]) - base
+    print(f"tile {tile} recompute: layer 0 MMAs seen done {f(8)} | layer 1 {f(10)} | layer 2 {f(12)} | recompute end {f(1)}")
