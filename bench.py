@@ -385,6 +385,9 @@ def main():
     ap.add_argument("--graphs", type=int, default=0, help="c5: total number of 64x64 graphs in the ensemble (default 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (reported under config)")
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                    help="N>1, one graph per GPU: the gradient sum over ranks -- 'peer': one-shot kernel over peer-mapped "
+                         "buffers (NVLink/NVSwitch, ngpde_peer_allreduce_sum), 'nccl': torch.distributed all_reduce")
     ap.add_argument("--no-strong-c4", action="store_true",
                     help="skip the node-partitioned C4 (1M-node GNOConv) strong-scaling block that the default C3 line carries")
     ap.add_argument("--c4-nodes", type=int, default=1_000_000)
@@ -441,13 +444,32 @@ def main():
             if world > 1:
                 dist.all_reduce(runner.dparams)
     else:
-        runner = engine.RhsRunner(w.layer, w.x, w.ps, w.st)
+        # data-parallel: the flat [dphi | dnode] gradient is summed over ranks once per step.  Default: the backward writes it
+        # into a peer-mapped symmetric buffer and ONE kernel per rank adds all copies over NVLink in rank order (deterministic,
+        # identical on every rank, no NCCL launch latency); --allreduce nccl: one coalesced NCCL all-reduce.  Either way it is
+        # captured into the same CUDA graph as the kernels when the capture accepts it.
+        par = None
+        if world > 1 and args.allreduce == "peer":
+            try:
+                from ngpde import distributed as D
+                par = D.PeerAllReduce(engine.RhsRunner.dparams_len(w.layer, w.x, w.ps, w.st), dev)
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write(f"bench.py: peer-memory all-reduce unavailable ({exc!r}); using NCCL\n")
+                par = None
+        # every rank must take the same path
+        if world > 1 and args.allreduce == "peer":
+            ok = torch.tensor([1 if par is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                par = None
+        runner = engine.RhsRunner(w.layer, w.x, w.ps, w.st, dparams=None if par is None else par.buffer)
         runner.dy.copy_(torch.randn(tuple(runner.dy.shape), generator=gen).to(dev))
 
-        # data-parallel: ONE collective over the flat [dphi | dnode] buffer (NCCL over NVLink), captured into the same CUDA
-        # graph as the kernels when the capture accepts it, so that no host launch gap separates it from the last kernel
         def grad_allreduce():
-            dist.all_reduce(runner.dparams)
+            if par is not None:
+                par.reduce()
+            else:
+                dist.all_reduce(runner.dparams)
 
         if args.cuda_graph:
             try:
@@ -562,7 +584,9 @@ def main():
                                 "VMHConv kernels only (the GCN aggregate is HBM-bound: DESIGN.md section 4)"} if chain else {}),
                    "step": "one RHS evaluation: layer forward + VJP w.r.t. (x, ps)", "aggr": "mean",
                    "l2": "warm (--no-flush)" if flush is None else "flushed between steps (256 MiB memset, untimed)",
-                   "parallelism": ("1 graph per GPU, one coalesced dW all-reduce over NCCL"
+                   "parallelism": ("1 graph per GPU, dW summed over ranks by "
+                                   + ("one kernel over peer-mapped buffers (NVLink, rank order)" if (world > 1 and not chain and par is not None)
+                                      else "one coalesced NCCL all-reduce")
                                    + (" captured in the step's CUDA graph" if allreduce_in_graph else "")) if world > 1 else "single GPU",
                    "cuda_graph": bool(args.cuda_graph) and not chain},
         "rhs_evals_per_sec": K * world / (total_ms * 1e-3),

@@ -224,6 +224,12 @@ int ngpde_rows_put(const float* x, const int32_t* rows, const int64_t* peer_ptr,
                    int64_t n_rows, int32_t d, void* stream);
 int ngpde_rows_segment_add(float* dst, const float* src, const int32_t* seg_rows, const int32_t* seg_ptr,
                            const int32_t* seg_pos, int64_t n_segs, int32_t d, void* stream);
+/* One-shot all-reduce of the flat parameter gradient over peer-mapped buffers (NVLink / NVSwitch): out[i] = sum over
+ * r = 0..world-1, in that order on EVERY rank, of peer_bufs[r][i] -- deterministic and bit-identical across ranks, one
+ * kernel, no NCCL call.  peer_bufs is a DEVICE array of `world` pointers (16-byte aligned buffers of n floats: this rank's
+ * own and its peers' symmetric allocations).  The caller brackets the call with a cross-GPU barrier on both sides (all
+ * ranks have written before; nobody overwrites its buffer until all have read). */
+int ngpde_peer_allreduce_sum(const float* const* peer_bufs, int32_t world, float* out, int64_t n, void* stream);
 
 /* ---- multi-GPU, host side: the node partitioner.  Owner-computes by destination over contiguous
  * node ranges: rank r owns [bounds[r], bounds[r+1]) and every edge whose target it owns, in the original relative order

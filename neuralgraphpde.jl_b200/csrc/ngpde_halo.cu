@@ -67,6 +67,27 @@ __global__ void rows_segment_add_kernel(float* __restrict__ dst, const float* __
   }
 }
 
+// One-shot all-reduce over peer-mapped buffers: every rank reads all `world` buffers (its own and its peers', over
+// NVLink / NVSwitch) and adds them in ascending rank order -- the same order on every rank, so the result is deterministic
+// and bit-identical across ranks.  Loads bypass L1 (the peers rewrite their buffers every step).
+__global__ void peer_allreduce_kernel(const float* const* __restrict__ peers, int world, float* __restrict__ out, int64_t n) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 acc = __ldcv(reinterpret_cast<const float4*>(peers[0]) + i);
+    for (int r = 1; r < world; ++r) {
+      const float4 v = __ldcv(reinterpret_cast<const float4*>(peers[r]) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float acc = __ldcv(peers[0] + i);
+    for (int r = 1; r < world; ++r) acc += __ldcv(peers[r] + i);
+    out[i] = acc;
+  }
+}
+
 int grid_for(int64_t total) { return (int)std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, 148 * 8)); }
 
 }  // namespace
@@ -108,6 +129,16 @@ extern "C" int ngpde_rows_segment_add(float* dst, const float* src, const int32_
   NGPDE_REQUIRE(dst && src && seg_rows && seg_ptr && seg_pos, "rows_segment_add: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rows_segment_add_kernel<<<grid_for(n_segs * d), 256, 0, st>>>(dst, src, seg_rows, seg_ptr, seg_pos, n_segs, d);
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
+extern "C" int ngpde_peer_allreduce_sum(const float* const* peer_bufs, int32_t world, float* out, int64_t n, void* stream) {
+  NGPDE_REQUIRE(peer_bufs && out && world >= 1 && n >= 0, "peer_allreduce_sum: bad argument");
+  NGPDE_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "peer_allreduce_sum: out must be 16-byte aligned");
+  if (n == 0) return NGPDE_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  peer_allreduce_kernel<<<grid_for((n + 3) / 4), 256, 0, st>>>(peer_bufs, world, out, n);
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;
 }

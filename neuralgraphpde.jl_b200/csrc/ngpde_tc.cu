@@ -216,7 +216,7 @@ int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base,
   a.off_cols = t.off_cols; a.off_stage = t.off_stage; a.off_dz = t.off_dz; a.nzh = t.nzh; a.nzl = t.nzl;
   std::memcpy(a.woff, t.woff, sizeof(a.woff));
   a.stream_a = t.stream_a; a.stream_b = t.stream_b;
-  a.dbg = NODE ? nullptr : g_tcb_dbg;
+  a.dbg = (NODE != (getenv("NGPDE_TCB_DBG_NODE") != nullptr)) ? nullptr : g_tcb_dbg;
   { const char* e = getenv("NGPDE_TCB_OPT"); a.opt = e ? atoi(e) : 0; }
   if (t.full) {
     NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_bwd_tc_kernel<NODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));

@@ -17,7 +17,8 @@ Tensor = torch.Tensor
 
 
 class RhsRunner:
-    def __init__(self, layer, x: Tensor, ps, st, use_cuda_graph: bool = False, share: Optional["RhsRunner"] = None):
+    def __init__(self, layer, x: Tensor, ps, st, use_cuda_graph: bool = False, share: Optional["RhsRunner"] = None,
+                 dparams: Optional[Tensor] = None):
         """`share`: another runner of the same layer / graph whose parameter buffers and workspaces this one uses too
         (the stages of one Runge-Kutta step: same parameters, calls strictly one after the other)."""
         if not hasattr(layer, "prepare"):
@@ -43,8 +44,13 @@ class RhsRunner:
         # with ONE collective, no staging copy
         nphi = self.phi.numel()
         pad = (-nphi) % 4
-        self.dparams = torch.zeros(nphi + pad + (0 if self.node is None else self.node.numel()), dtype=torch.float32,
-                                   device=dev)
+        n_dp = nphi + pad + (0 if self.node is None else self.node.numel())
+        if dparams is not None:  # caller-provided gradient buffer (e.g. a peer-mapped symmetric allocation)
+            if dparams.numel() != n_dp or dparams.dtype != torch.float32 or not dparams.is_contiguous():
+                raise ValueError(f"dparams must be a contiguous float32 vector of {n_dp} entries")
+            self.dparams = dparams
+        else:
+            self.dparams = torch.zeros(n_dp, dtype=torch.float32, device=dev)
         self.dphi = self.dparams[:nphi]
         self.dnode = None if self.node is None else self.dparams[nphi + pad:]
         with torch.cuda.device(dev):
@@ -77,6 +83,13 @@ class RhsRunner:
         self._keep = (self.snode, self.edata, self.theta, self.handle)
         if use_cuda_graph:
             self.capture()
+
+    @staticmethod
+    def dparams_len(layer, x: Tensor, ps, st) -> int:
+        """Length of the flat gradient buffer [dphi | pad | dnode] a runner of this layer uses."""
+        pr = layer.prepare(x, ps, st)
+        nphi = pr[1].numel()
+        return nphi + ((-nphi) % 4) + (0 if pr[2] is None else pr[2].numel())
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.dev).cuda_stream
