@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--graphs", type=int, default=0, help="c5: total number of 64x64 graphs in the ensemble (default 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (reported under config)")
-    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--allreduce", default="nccl", choices=["peer", "nccl"],
                     help="N>1, one graph per GPU: the gradient sum over ranks -- 'peer': one-shot kernel over peer-mapped "
                          "buffers (NVLink/NVSwitch, ngpde_peer_allreduce_sum), 'nccl': torch.distributed all_reduce")
     ap.add_argument("--no-strong-c4", action="store_true",
@@ -473,8 +473,11 @@ def main():
 
         if args.cuda_graph:
             try:
-                runner.capture(extra=grad_allreduce if world > 1 else None)
-                allreduce_in_graph = world > 1
+                # the peer-memory path is issued AFTER the replay: its cross-GPU barrier (symmetric-memory signal pads) must
+                # not be frozen into a captured graph (a replayed barrier dead-locked in testing)
+                in_graph = world > 1 and par is None
+                runner.capture(extra=grad_allreduce if in_graph else None)
+                allreduce_in_graph = in_graph
             except Exception as exc:  # noqa: BLE001
                 torch.cuda.synchronize(dev)
                 try:
