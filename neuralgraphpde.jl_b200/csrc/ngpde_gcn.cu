@@ -63,18 +63,38 @@ __global__ void __launch_bounds__(256) gcn_aggregate_kernel(int N, int d, const 
 #pragma unroll
   for (int v = 0; v < V; ++v) acc[v] = 0.f;
   const int q0 = ptr[r], q1 = ptr[r + 1];
-  for (int q = q0; q < q1; ++q) {
-    const int j = ent ? ent[q] : q;
-    const int s = other[j];
-    const float w = val[j], cs = c[s];
-    float xv[V];
-    if (V == 4) {
-      *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(x + (size_t)s * d + lane * 4);
-    } else {
-      xv[0] = x[(size_t)s * d + lane];
+  // Four entries per trip: their index / weight / normaliser loads and then their source rows are all in flight before the
+  // first add (the kernel is bound by memory latency, not by issue), and the adds still run in ascending entry order.
+  constexpr int U = 4;
+  for (int q = q0; q < q1; q += U) {
+    int sidx[U];
+    float w[U], cs[U];
+    float xv[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool on = q + u < q1;
+      const int j = on ? (ent ? __ldg(ent + q + u) : q + u) : 0;
+      sidx[u] = on ? __ldg(other + j) : -1;
+      w[u] = on ? __ldg(val + j) : 0.f;
     }
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(__fmul_rn(xv[v], cs), w));
+    for (int u = 0; u < U; ++u) {
+      if (sidx[u] >= 0) {
+        cs[u] = __ldg(c + sidx[u]);
+        if (V == 4) {
+          *reinterpret_cast<float4*>(xv[u]) = __ldg(reinterpret_cast<const float4*>(x + (size_t)sidx[u] * d + lane * 4));
+        } else {
+          xv[u][0] = __ldg(x + (size_t)sidx[u] * d + lane);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (sidx[u] >= 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(__fmul_rn(xv[u][v], cs[u]), w[u]));
+      }
+    }
   }
   const float cr = c[r];
 #pragma unroll
@@ -86,10 +106,91 @@ __global__ void __launch_bounds__(256) gcn_aggregate_kernel(int N, int d, const 
   }
 }
 
+// The same sum for rows that are a whole number of float4, with the row width a compile-time constant: no 64-bit division to
+// find (row, lane), one IMAD.WIDE per source row, four entries in flight per trip and a branch-free body for full groups.
+// (The generic kernel above spends most of its issue slots on index arithmetic: 75 % issue utilisation at 19 % of the HBM
+// peak, profiles/r02k_ncu_gcn_summary.md.)  Entry order and roundings are unchanged: ((x * c_s) * w) added in ascending order.
+template <int LPR, bool HAS_ENT>
+__global__ void __launch_bounds__(256) gcn_aggregate_v4_kernel(int N, const int* __restrict__ ptr, const int* __restrict__ ent,
+                                                                const int* __restrict__ other, const float* __restrict__ val,
+                                                                const float* __restrict__ c, const float4* __restrict__ x,
+                                                                float4* __restrict__ out) {
+  const unsigned gid = blockIdx.x * 256u + threadIdx.x;
+  const unsigned r = gid / LPR, lane = gid % LPR;
+  if (r >= (unsigned)N) return;
+  const float4* xl = x + lane;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto add = [&](const float4 v, const float cs, const float w) {
+    float4 t = make_float4(__fmul_rn(v.x, cs), __fmul_rn(v.y, cs), __fmul_rn(v.z, cs), __fmul_rn(v.w, cs));
+    if (w != 1.f) {  // an unweighted, duplicate-free entry has val == 1: multiplying by it is exact, so it is skipped
+      t.x = __fmul_rn(t.x, w); t.y = __fmul_rn(t.y, w); t.z = __fmul_rn(t.z, w); t.w = __fmul_rn(t.w, w);
+    }
+    acc.x = __fadd_rn(acc.x, t.x);
+    acc.y = __fadd_rn(acc.y, t.y);
+    acc.z = __fadd_rn(acc.z, t.z);
+    acc.w = __fadd_rn(acc.w, t.w);
+  };
+  int q = __ldg(ptr + r);
+  const int q1 = __ldg(ptr + r + 1);
+  for (; q + 4 <= q1; q += 4) {
+    int j[4], s[4];
+    float w[4], cs[4];
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) j[u] = HAS_ENT ? __ldg(ent + q + u) : q + u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[u] = __ldg(other + j[u]);
+      w[u] = __ldg(val + j[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      cs[u] = __ldg(c + s[u]);
+      v[u] = __ldg(xl + (size_t)s[u] * LPR);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) add(v[u], cs[u], w[u]);
+  }
+  for (; q < q1; ++q) {
+    const int j = HAS_ENT ? __ldg(ent + q) : q;
+    const int s = __ldg(other + j);
+    add(__ldg(xl + (size_t)s * LPR), __ldg(c + s), __ldg(val + j));
+  }
+  const float cr = __ldg(c + r);
+  acc.x = __fmul_rn(acc.x, cr);
+  acc.y = __fmul_rn(acc.y, cr);
+  acc.z = __fmul_rn(acc.z, cr);
+  acc.w = __fmul_rn(acc.w, cr);
+  out[(size_t)r * LPR + lane] = acc;
+}
+
+template <int LPR>
+int launch_gcn_v4(int N, const int* ptr, const int* ent, const int* other, const float* val, const float* c, const float* x,
+                  float* out, cudaStream_t st) {
+  const unsigned blocks = (unsigned)(((long long)N * LPR + 255) / 256);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* o4 = reinterpret_cast<float4*>(out);
+  if (ent) gcn_aggregate_v4_kernel<LPR, true><<<blocks, 256, 0, st>>>(N, ptr, ent, other, val, c, x4, o4);
+  else gcn_aggregate_v4_kernel<LPR, false><<<blocks, 256, 0, st>>>(N, ptr, ent, other, val, c, x4, o4);
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
 int launch_gcn_aggregate(int N, int d, const int* ptr, const int* ent, const int* other, const float* val,
                          const float* c, const float* x, float* out, cudaStream_t st) {
   if (N == 0) return NGPDE_OK;
   const bool v4 = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (v4 && (long long)N * (d / 4) < (1ll << 31)) {
+    switch (d / 4) {
+      case 1: return launch_gcn_v4<1>(N, ptr, ent, other, val, c, x, out, st);
+      case 2: return launch_gcn_v4<2>(N, ptr, ent, other, val, c, x, out, st);
+      case 4: return launch_gcn_v4<4>(N, ptr, ent, other, val, c, x, out, st);
+      case 8: return launch_gcn_v4<8>(N, ptr, ent, other, val, c, x, out, st);
+      case 16: return launch_gcn_v4<16>(N, ptr, ent, other, val, c, x, out, st);
+      case 32: return launch_gcn_v4<32>(N, ptr, ent, other, val, c, x, out, st);
+      default: break;
+    }
+  }
   const long long threads = (long long)N * (v4 ? d / 4 : d);
   const unsigned blocks = (unsigned)((threads + 255) / 256);
   if (v4) gcn_aggregate_kernel<4><<<blocks, 256, 0, st>>>(N, d, ptr, ent, other, val, c, x, out);

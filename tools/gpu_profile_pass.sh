@@ -5,19 +5,19 @@
 # kernels inside the C5 chain, 64 graphs), <tag>_bench_c5.json, <tag>_bench_c2.json, <tag>_bench_c1.json
 tag=${1:-r02}
 out=gpurun_out
-python -m pytest tests -m gpu -q 2>&1 | tail -15 > $out/${tag}_pytest_gpu.log
+timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -15 > $out/${tag}_pytest_gpu.log
 tail -3 $out/${tag}_pytest_gpu.log
-python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
+timeout 300 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 python tools/show_bench.py $out/${tag}_bench.json
-python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_reference_arm.json 2>/dev/null
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
+timeout 200 python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_reference_arm.json 2>/dev/null
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-strong-c4 --no-cuda-graph > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'mp_(fwd|bwd)_tc_kernel' -s 8 -c 4 -f -o $out/${tag}_c3_full \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'mp_(fwd|bwd)_tc_kernel' -s 8 -c 4 -f -o $out/${tag}_c3_full \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-strong-c4 --no-cuda-graph > /dev/null 2> $out/${tag}_ncu_c3.err
-ncu --set full --clock-control none -k regex:'gcn_aggregate' -s 12 -c 4 -f -o $out/${tag}_gcn_full \
+timeout 400 ncu --set full --clock-control none -k regex:'gcn_aggregate' -s 12 -c 4 -f -o $out/${tag}_gcn_full \
     python bench.py --workload c5 --graphs 64 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2> $out/${tag}_ncu_gcn.err
 for wl in c5 c2 c1; do
-  python bench.py --workload $wl --no-cpu-baseline > $out/${tag}_bench_${wl}.json 2>/dev/null
+  timeout 200 python bench.py --workload $wl --no-cpu-baseline > $out/${tag}_bench_${wl}.json 2>/dev/null
   python tools/show_bench.py $out/${tag}_bench_${wl}.json
 done
 sha256sum neuralgraphpde.jl_b200/libngpde.so > $out/${tag}_lib.sha256
