@@ -99,7 +99,7 @@ bool tc_bwd_make_impl(const MlpDev& m, bool contract, bool addend, bool node, in
   t->nzh = (kdmax + 31) / 32;
   t->nzl = t->nzh;
   const int dz_bytes = (!node && need_dz0) ? TC_TILE * (lay.Kd[0] + 1) * 4 : 0;
-  const int cols_bytes = (int)(sizeof(TcCol) + sizeof(TcDst)) * lay.Kd[0];
+  const int cols_bytes = (int)(sizeof(TcCol) + sizeof(TcDst)) * lay.Kd[0] + 2 * TC_MAX_CHUNKS * (int)sizeof(TcChunk);
   auto place = [&](bool full, bool stream) -> bool {
     int off = 0;  // floats
     const int sa = stream ? 1 : -1, sb = stream ? L - 1 : -1;
@@ -146,7 +146,7 @@ bool tc_make_layout_impl(const MlpDev& m, bool contract, bool addend, int dout, 
   while (cols < need) cols *= 2;
   lay->tmem_cols = cols;
   *off_cols = 4 * lay->block_floats;
-  *off_groups = (*off_cols + (int)sizeof(TcCol) * lay->Kd[0] + 127) & ~127;
+  *off_groups = (*off_cols + (int)sizeof(TcCol) * lay->Kd[0] + TC_MAX_CHUNKS * (int)sizeof(TcChunk) + 127) & ~127;
   *group_bytes = node ? 128 : ((TC_TILE * (dout + 1) * 4 + 127) & ~127);
   const int total = 1024 + *off_groups + TC_GROUPS * *group_bytes;
   // at least half of the SM's shared memory, so that two CTAs (and two 512-column TMEM allocations) never share an SM
@@ -155,11 +155,36 @@ bool tc_make_layout_impl(const MlpDev& m, bool contract, bool addend, int dout, 
 }
 
 
+// Node phase: put the input segments whose width is a multiple of 16 columns first (stable), so that a 16-column chunk of the
+// on-chip layer-0 input is an aligned run of one array (vector loads / stores, see TcChunk).  The weight image rows and the
+// parameter-gradient rows of layer 0 follow the same order through TcLayout::ps/po/pw.
+void tc_permute_node_segs(Seg* segs, int n_segs, TcLayout* lay) {
+  lay->np = 0;
+  if (n_segs <= 1 || n_segs > 8) return;
+  Seg out[8];
+  int n = 0, row = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < n_segs; ++i)
+      if (((segs[i].width & 15) == 0) == (pass == 0)) {
+        out[n] = segs[i];
+        lay->ps[n] = row;
+        lay->po[n] = segs[i].row;
+        lay->pw[n] = segs[i].width;
+        out[n].row = row;
+        row += segs[i].width;
+        ++n;
+      }
+  bool identity = true;
+  for (int i = 0; i < n; ++i) identity = identity && lay->ps[i] == lay->po[i];
+  if (identity) return;
+  lay->np = n;
+  for (int i = 0; i < n; ++i) segs[i] = out[i];
+}
+
 template <bool NODE>
 int launch_fwd_tc_t(int num_sms, const TcPhase& t, const MlpDev& mlp, const float* params, const FwdArgs& base,
                   float* wblock, cudaStream_t st) {
   if (base.tg.n_units <= 0) return NGPDE_OK;
-  tc_prep_weights_kernel<<<32, 256, 0, st>>>(params, mlp, t.lay, wblock);
   TcFwdArgs a{};
   a.tg = base.tg;
   std::memcpy(a.arr, base.arr, sizeof(a.arr));
@@ -167,6 +192,8 @@ int launch_fwd_tc_t(int num_sms, const TcPhase& t, const MlpDev& mlp, const floa
   a.n_segs = base.n_segs;
   std::memcpy(a.segs, base.segs, sizeof(a.segs));
   a.lay = t.lay;
+  if (NODE) tc_permute_node_segs(a.segs, a.n_segs, &a.lay);
+  tc_prep_weights_kernel<<<32, 256, 0, st>>>(params, mlp, a.lay, wblock);
   for (int l = 0; l < mlp.L; ++l) a.act[l] = mlp.act[l];
   a.wblock = wblock;
   a.aggr = base.aggr;
@@ -185,7 +212,6 @@ int launch_fwd_tc_t(int num_sms, const TcPhase& t, const MlpDev& mlp, const floa
 template <bool NODE>
 int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base, float* wblock, cudaStream_t st) {
   if (base.tg.n_units <= 0) return NGPDE_OK;
-  tc_prep_weights_kernel<<<32, 256, 0, st>>>(base.params, mlp, t.lay, wblock);
   TcBwdArgs a{};
   a.tg = base.tg;
   std::memcpy(a.arr, base.arr, sizeof(a.arr));
@@ -193,6 +219,8 @@ int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base,
   a.n_segs = base.n_segs;
   std::memcpy(a.segs, base.segs, sizeof(a.segs));
   a.lay = t.lay;
+  if (NODE) tc_permute_node_segs(a.segs, a.n_segs, &a.lay);
+  tc_prep_weights_kernel<<<32, 256, 0, st>>>(base.params, mlp, a.lay, wblock);
   for (int l = 0; l < mlp.L; ++l) {
     a.act[l] = mlp.act[l];
     a.w_off[l] = mlp.w_off[l];

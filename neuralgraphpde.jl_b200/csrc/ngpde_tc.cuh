@@ -55,7 +55,7 @@ __global__ void tc_prep_weights_kernel(const float* __restrict__ params, MlpDev 
       const int k = i / cols, n = i - k * cols;
       float w = 0.f;
       if (n < N) {
-        if (k < K) w = W[(size_t)k * N + n];
+        if (k < K) w = W[(size_t)(l == 0 ? tc_orig_row(lay, k) : k) * N + n];
         else if (k == Kd && b != nullptr) w = b[n];
       }
       const float h = umma::tf32_hi(w);
@@ -95,6 +95,43 @@ __device__ __forceinline__ void tc_build_cols(const Args& a, TcCol* cols, int nc
       }
     }
     cols[c] = t;
+  }
+}
+
+// A 16-column chunk of the node-phase input that is 16 consecutive, 16-byte aligned floats of ONE node array: loaded (and its
+// cotangent stored) as 4 float4 per row instead of 16 table-driven scalar accesses -- with one row per lane every scalar
+// access is its own 32-byte sector, so the load/store unit, not the memory, bounded those phases.
+struct TcChunk {
+  const float* base;  // array + first column of the chunk; nullptr: take the per-column path
+  int ld;
+};
+
+template <class Args>
+__device__ __forceinline__ void tc_build_chunks(const Args& a, TcChunk* chunks, int nchunks, int tid) {
+  if (tid >= nchunks) return;
+  TcChunk t{nullptr, 0};
+  const int c = 16 * tid;
+  for (int si = 0; si < a.n_segs; ++si) {
+    const Seg sg = a.segs[si];
+    const int f = c - sg.row;
+    if (sg.kind != SEG_DST || f < 0 || f + 16 > sg.width) continue;
+    const float* b = a.arr[sg.arr] + sg.col + f;
+    if (((sg.col + f) & 3) == 0 && (a.ld[sg.arr] & 3) == 0 && (reinterpret_cast<uintptr_t>(a.arr[sg.arr]) & 15) == 0) {
+      t.base = b;
+      t.ld = a.ld[sg.arr];
+    }
+  }
+  chunks[tid] = t;
+}
+
+// n (4 or 2) float4 of row `r` of an aligned chunk
+template <int NV>
+__device__ __forceinline__ void tc_load_chunk(const TcChunk ch, int r, int first, float* v) {
+  const float4* p = reinterpret_cast<const float4*>(ch.base + (size_t)r * ch.ld + first);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 t = __ldg(p + i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
   }
 }
 
@@ -194,6 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
   const int half = gt >> 7;  // which 16-column chunks of a layer's output it handles (chunk & 1 == half)
   float* wblk = reinterpret_cast<float*>(smem);
   TcCol* cols = reinterpret_cast<TcCol*>(smem + a.off_cols);
+  TcChunk* chunks = reinterpret_cast<TcChunk*>(cols + lay.Kd[0]);
   float* M = reinterpret_cast<float*>(smem + a.off_groups + grp * a.group_bytes);  // [128][dout + 1]
   const int dout = a.dout, ldm = dout + 1, aggr = a.aggr;
   float* __restrict__ out = a.out;
@@ -205,6 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
     umma::fence_mbar_init();
   }
   tc_build_cols(a, cols, lay.Kd[0], tid, TC_THREADS);
+  if (NODE) tc_build_chunks(a, chunks, lay.Kd[0] >> 4, tid);
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
@@ -258,9 +297,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
       // ---- gather this row's MLP input straight into TMEM (8-column chunks alternate between the two halves) ----
       for (int c0 = 8 * half; c0 < Kd0; c0 += 16) {
         uint32_t hi[8], lo[8];
+        float vv[8];
+        const TcChunk ch = NODE ? chunks[c0 >> 4] : TcChunk{nullptr, 0};
+        if (NODE && ch.base != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vv[j] = 0.f;
+          if (valid) tc_load_chunk<2>(ch, d, c0 & 15, vv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vv[j] = valid ? tc_gather_col(cols[c0 + j], s, d, p, pg) : 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float v = valid ? tc_gather_col(cols[c0 + j], s, d, p, pg) : 0.f;
+          const float v = vv[j];
           const float h = umma::tf32_hi(v);
           hi[j] = __float_as_uint(h);
           lo[j] = __float_as_uint(umma::tf32_lo(v, h));

@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   float* wblk = reinterpret_cast<float*>(smem);
   TcCol* cols = reinterpret_cast<TcCol*>(smem + a.off_cols);
   TcDst* dcols = reinterpret_cast<TcDst*>(cols + lay.Kd[0]);
+  TcChunk* chunks = reinterpret_cast<TcChunk*>(dcols + lay.Kd[0]);   // node phase: aligned 16-column chunks of the input ...
+  TcChunk* dchunks = chunks + TC_MAX_CHUNKS;                          // ... and of where its cotangent goes
   float* st_base = reinterpret_cast<float*>(smem + a.off_stage);  // Z hi | Z lo | G hi | G lo, each nz (2 for G) groups
   float* st_ghi = st_base + 2 * a.nzh * ROWS * 32;
   float* st_glo = st_ghi + 2 * ROWS * 32;
@@ -286,6 +288,23 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         if (sg.arr == ARR_M && a.dmbar != nullptr) t = TcDst{a.dmbar + sg.col + f, a.ld[ARR_M]};
       }
       dcols[c] = t;
+    }
+    tc_build_chunks(a, chunks, Kd0 >> 4, tid);
+    if (tid < (Kd0 >> 4)) {
+      // the cotangent of an aligned chunk of x / mbar goes to the same columns of dx_direct / dmbar
+      TcChunk t{nullptr, 0};
+      const int c = 16 * tid;
+      for (int si = 0; si < a.n_segs; ++si) {
+        const Seg sg = a.segs[si];
+        const int f = c - sg.row;
+        if (sg.kind != SEG_DST || f < 0 || f + 16 > sg.width) continue;
+        float* dstb = sg.arr == ARR_X ? a.dx_direct : (sg.arr == ARR_M ? a.dmbar : nullptr);
+        if (dstb != nullptr && ((sg.col + f) & 3) == 0 && (a.ld[sg.arr] & 3) == 0 && (reinterpret_cast<uintptr_t>(dstb) & 15) == 0) {
+          t.base = dstb + sg.col + f;
+          t.ld = a.ld[sg.arr];
+        }
+      }
+      dchunks[tid] = t;
     }
   }
   umma::tc_fence_before();
@@ -463,8 +482,27 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 
       // ---- 1. forward recompute: Z_1 .. Z_{L-1} (two issuing warps, accumulators tD and tDw, bias added here) ----
       if (L > 1) {
-        // the four chunk warps of a row share the gather: a quarter of the Kd0 columns each, four at a time
-        const int gq = Kd0 >> 2;
+        if (NODE) {
+          // node phase: whole 16-column chunks (vector loads where the chunk is an aligned run of one array)
+          for (int cc = c0; cc < Kd0; cc += 64) {
+            float v[16];
+            const TcChunk ch = chunks[cc >> 4];
+            if (ch.base != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = 0.f;
+              if (valid) tc_load_chunk<4>(ch, d, 0, v);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+            }
+            uint32_t hi[16], lo[16];
+            tc_split16(v, hi, lo);
+            umma::tmem_st16(tAhi + lane_addr + cc, hi);
+            umma::tmem_st16(tAlo + lane_addr + cc, lo);
+          }
+        }
+        // edge phase: the four chunk warps of a row share the gather: a quarter of the Kd0 columns each, four at a time
+        const int gq = NODE ? 0 : Kd0 >> 2;
         for (int cc = q * gq; cc < (q + 1) * gq; cc += 4) {
           uint32_t hi[4], lo[4];
 #pragma unroll
@@ -658,8 +696,15 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 #pragma unroll
                   for (int j = 0; j < 16; ++j) z[j] = DZ[row * (Kd0 + 1) + cc + j];
                 } else {
+                  const TcChunk ch = NODE ? chunks[cc >> 4] : TcChunk{nullptr, 0};
+                  if (NODE && ch.base != nullptr) {
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) z[j] = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+                    for (int j = 0; j < 16; ++j) z[j] = 0.f;
+                    if (valid) tc_load_chunk<4>(ch, d, 0, z);
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) z[j] = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+                  }
                 }
               } else {
                 uint32_t v[16];
@@ -751,7 +796,14 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               umma::tmem_ld16(tDl + lane_addr + cc, v);
               umma::tmem_wait_ld();
               if (NODE) {
-                if (valid) {
+                const TcChunk dch = dchunks[cc >> 4];
+                if (valid && dch.base != nullptr) {
+                  float4* o = reinterpret_cast<float4*>(const_cast<float*>(dch.base) + (size_t)(k0 + row) * dch.ld);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                       __uint_as_float(v[4 * j + 3]));
+                } else if (valid) {
 #pragma unroll
                   for (int j = 0; j < 16; ++j) {
                     const TcDst t = dcols[cc + j];
@@ -828,7 +880,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       const int K = lay.K[l], N = lay.N[l];
       if (n >= N) continue;
       auto put = [&](int k, float v) {
-        if (k < K) dWp[a.w_off[l] + (size_t)k * N + n] = v;
+        if (k < K) dWp[a.w_off[l] + (size_t)(l == 0 ? tc_orig_row(lay, k) : k) * N + n] = v;
       };
 #pragma unroll
       for (int j = 0; j < 8; ++j) put(c0 + (upper ? 8 : 0) + j, dwacc[l][j]);

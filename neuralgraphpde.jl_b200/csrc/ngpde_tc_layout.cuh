@@ -27,7 +27,19 @@ struct TcLayout {
   int kmax;                                        // widest Kp
   int cols_group;                                  // TMEM columns per group: TC_MAXN (D) + 2*kmax (A hi, A lo)
   int tmem_cols;                                   // allocation: power of two >= 32
+  // Node phase: the input segments of layer 0 may be re-ordered on chip (16-column-aligned segments first, so that a
+  // thread's 16-column chunk is 4 aligned float4 of ONE array).  Position p of the on-chip order holds original input row
+  // po[i] + (p - ps[i]) for the segment i with ps[i] <= p < ps[i] + pw[i]; np == 0: identity.
+  int np;
+  int ps[8], po[8], pw[8];
 };
+constexpr int TC_MAX_CHUNKS = 16;  // 16-column chunks of a layer-0 input (Kd0 <= 256)
+
+__host__ __device__ inline int tc_orig_row(const TcLayout& lay, int p) {
+  for (int i = 0; i < lay.np; ++i)
+    if (p >= lay.ps[i] && p < lay.ps[i] + lay.pw[i]) return lay.po[i] + (p - lay.ps[i]);
+  return p;
+}
 
 constexpr int TCB_WORKERS = 512;  // 16 worker warps: thread = (tile row, 16-column chunk)
 constexpr int TCB_THREADS = TCB_WORKERS + 32;  // + one dedicated MMA-issuing warp
