@@ -15,7 +15,7 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:'mp_(fwd|bwd)_tc_kernel' -s 8 -c 4 -f -o $out/${tag}_c3_full \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-strong-c4 --no-cuda-graph > /dev/null 2> $out/${tag}_ncu_c3.err
 timeout 400 ncu --set full --clock-control none -k regex:'gcn_aggregate' -s 12 -c 4 -f -o $out/${tag}_gcn_full \
-    python bench.py --workload c5 --graphs 64 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2> $out/${tag}_ncu_gcn.err
+    python bench.py --workload c5 --graphs 512 --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2> $out/${tag}_ncu_gcn.err
 for wl in c5 c2 c1; do
   timeout 200 python bench.py --workload $wl --no-cpu-baseline > $out/${tag}_bench_${wl}.json 2>/dev/null
   python tools/show_bench.py $out/${tag}_bench_${wl}.json
