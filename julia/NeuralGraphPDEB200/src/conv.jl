@@ -2,6 +2,8 @@
 # call per layer; the pullback is the matching hand-written backward kernel (ngpde_*_backward).
 
 workspace(nbytes::Integer) = CuArray{UInt8}(undef, max(Int(nbytes), 256))
+dm(desc::ConvDesc) = desc.family == FAM_GNO ? Int(desc.gno_out) : Int(desc.phi.dims[desc.phi.n_layers + 1])   # rows of mbar
+dy(desc::ConvDesc) = Int(desc.node.dims[desc.node.n_layers + 1])                                             # rows of y
 
 """
     fused_conv(h, desc, x, snode, edata, theta, phi, node) -> (y, mbar)
@@ -12,9 +14,8 @@ One message-passing layer call (`ngpde_conv_forward`): `x (dx, N)`, static node 
 function fused_conv(h::GraphHandle, desc::ConvDesc, x::CuMatrix{Float32}, snode, edata, theta, phi::CuVector{Float32}, node)
     N = size(x, 2)
     has_node = desc.node.n_layers > 0
-    dm = desc.family == FAM_GNO ? Int(desc.gno_out) : Int(desc.phi.dims[desc.phi.n_layers + 1])
-    mbar = CuMatrix{Float32}(undef, dm, N)
-    y = has_node ? CuMatrix{Float32}(undef, Int(desc.node.dims[desc.node.n_layers + 1]), N) : mbar
+    mbar = CuMatrix{Float32}(undef, dm(desc), N)
+    y = has_node ? CuMatrix{Float32}(undef, dy(desc), N) : mbar
     nb = conv_workspace_bytes(h, desc, false)
     nb == 0 && check(-1)
     ws = workspace(nb)
