@@ -231,6 +231,27 @@ int ngpde_rows_segment_add(float* dst, const float* src, const int32_t* seg_rows
  * ranks have written before; nobody overwrites its buffer until all have read). */
 int ngpde_peer_allreduce_sum(const float* const* peer_bufs, int32_t world, float* out, int64_t n, void* stream);
 
+/* ---- persistent fixed-step Runge-Kutta integrator for du/dt = ExplicitEdgeConv(u) on a small graph (SURVEY.md section 8f-1;
+ * the reference's `solve(prob, Tsit5(); adaptive = false, dt)` loop, docs/src/tutorials/graph_node.md:53-66): ONE kernel
+ * launch (a thread-block cluster, one cluster barrier per right-hand side) integrates `n_steps` steps; a second kernel is its
+ * discrete adjoint.  Limits: family EXPLICIT_EDGE_CONV, aggr + / mean, dx <= 4, phi input <= 16, phi layers <= 32 wide,
+ * <= 4 layers, <= 1024 parameters, activations whose derivative is a function of the output, 8 <= N <= 65536.
+ *   tableau   explicit: a[i][j] (j < i) and b[i]; stage i input = u + dt sum_j a[i][j] k_j; u_next = u + dt sum_i b[i] k_i
+ *   forward   u [N][dx] in/out; traj [n_steps][n_stages][N][dx] receives every stage input (the adjoint's checkpoint)
+ *   adjoint   lam [N][dx]: in dL/du(T), out dL/du(0); dphi_params: dL/dparams (overwritten); deterministic (no atomics) ---- */
+typedef struct {
+  int32_t n_stages;
+  float a[8][8];
+  float b[8];
+} ngpde_rk_tableau;
+size_t ngpde_edgeconv_ode_workspace_bytes(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_rk_tableau* tab);
+int ngpde_edgeconv_ode_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_rk_tableau* tab, float dt, int32_t n_steps,
+                               const float* phi_params, const float* snode, float* u, float* traj, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int ngpde_edgeconv_ode_adjoint(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_rk_tableau* tab, float dt, int32_t n_steps,
+                               const float* phi_params, const float* snode, const float* traj, float* lam, float* dphi_params,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- multi-GPU, host side: the node partitioner.  Owner-computes by destination over contiguous
  * node ranges: rank r owns [bounds[r], bounds[r+1]) and every edge whose target it owns, in the original relative order
  * (so each owned row reduces the same messages in the same order as on one GPU: the forward is bit-identical); sources

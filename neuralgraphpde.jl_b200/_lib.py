@@ -34,7 +34,8 @@ EXPORTS = [
     "ngpde_comm_unique_id", "ngpde_comm_init", "ngpde_comm_adopt", "ngpde_comm_destroy", "ngpde_halo_create",
     "ngpde_halo_destroy", "ngpde_halo_forward", "ngpde_halo_backward", "ngpde_allreduce_sum", "ngpde_adam_step",
     "ngpde_rprop_step", "ngpde_loss_workspace_bytes", "ngpde_mse_loss", "ngpde_logit_cross_entropy",
-    "ngpde_cuda_graph_kernel_nodes", "ngpde_peer_allreduce_sum",
+    "ngpde_cuda_graph_kernel_nodes", "ngpde_peer_allreduce_sum", "ngpde_edgeconv_ode_workspace_bytes",
+    "ngpde_edgeconv_ode_forward", "ngpde_edgeconv_ode_adjoint",
 ]
 PA = {"bounds": 0, "halo_global": 1, "recv_counts": 2, "send_counts": 3, "send_local": 4, "s_local": 5, "t_local": 6,
       "edge_ids": 7, "seg_rows": 8, "seg_ptr": 9, "seg_pos": 10, "peer_recv_offset": 11}
@@ -61,6 +62,10 @@ class ConvIO(C.Structure):
 class GcnDesc(C.Structure):
     _fields_ = [("in_chs", C.c_int32), ("out_chs", C.c_int32), ("act", C.c_int32), ("has_bias", C.c_int32),
                 ("add_self_loops", C.c_int32), ("use_edge_weight", C.c_int32)]
+
+
+class RkTableau(C.Structure):
+    _fields_ = [("n_stages", C.c_int32), ("a", (C.c_float * 8) * 8), ("b", C.c_float * 8)]
 
 
 class NgpdeError(RuntimeError):
@@ -132,6 +137,10 @@ def load() -> C.CDLL:
     lib.ngpde_mse_loss.argtypes = [vp, vp, i64, vp, vp, vp, sz, vp]
     lib.ngpde_logit_cross_entropy.argtypes = [vp, i64, i32, vp, vp, i64, vp, vp, vp, sz, vp]
     lib.ngpde_peer_allreduce_sum.argtypes = [vp, i32, vp, i64, vp]
+    lib.ngpde_edgeconv_ode_workspace_bytes.argtypes = [vp, C.POINTER(ConvDesc), C.POINTER(RkTableau)]
+    lib.ngpde_edgeconv_ode_workspace_bytes.restype = sz
+    lib.ngpde_edgeconv_ode_forward.argtypes = [vp, C.POINTER(ConvDesc), C.POINTER(RkTableau), C.c_float, i32, vp, vp, vp, vp, vp, sz, vp]
+    lib.ngpde_edgeconv_ode_adjoint.argtypes = [vp, C.POINTER(ConvDesc), C.POINTER(RkTableau), C.c_float, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.ngpde_cuda_graph_kernel_nodes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     _lib = lib
     return lib

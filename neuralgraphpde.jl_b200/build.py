@@ -22,7 +22,7 @@ CSRC = os.path.join(HERE, "csrc")
 _TAG = os.environ.get("NGPDE_BUILD_TAG", "")
 OUT = os.path.join(HERE, f"libngpde_{_TAG}.so" if _TAG else "libngpde.so")
 OBJ_DIR = os.path.join(HERE, f"build_{_TAG}" if _TAG else "build")
-SOURCES = ["ngpde_conv_bwd_edge.cu", "ngpde_conv_bwd_node.cu", "ngpde_conv_fwd.cu", "ngpde_graph.cu", "ngpde_conv.cu", "ngpde_tc.cu", "ngpde_gcn.cu", "ngpde_halo.cu", "ngpde_gno.cu", "ngpde_gno_tc.cu", "ngpde_train.cu", "ngpde_dist.cu"]
+SOURCES = ["ngpde_conv_bwd_edge.cu", "ngpde_conv_bwd_node.cu", "ngpde_conv_fwd.cu", "ngpde_graph.cu", "ngpde_conv.cu", "ngpde_tc.cu", "ngpde_gcn.cu", "ngpde_halo.cu", "ngpde_gno.cu", "ngpde_gno_tc.cu", "ngpde_train.cu", "ngpde_dist.cu", "ngpde_ode.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -60,6 +60,7 @@ struct ngpde_graph {
   int* units[3] = {nullptr, nullptr, nullptr};
   int n_units[3] = {0, 0, 0};
   ngpde::GcnLayout gcn[2];
+  int ode_max_edges = -1;  // largest in-edge count of the persistent ODE kernels' node ranges (computed on first use)
 };
 
 namespace ngpde {

@@ -204,3 +204,83 @@ class GraphedRK:
             self.bwd_graph.replay()
             self.rhs_evals += self.S
         return self.lam, self.dparams
+
+
+class PersistentRK:
+    """The whole fixed-step integration of `du/dt = ExplicitEdgeConv(u, ps, st)[1]` in ONE kernel launch, and its discrete
+    adjoint in a second one (`ngpde_edgeconv_ode_forward/adjoint`, csrc/ngpde_ode.cu: a thread-block cluster owns the graph,
+    one cluster barrier per right-hand side).  For graphs where a right-hand side is launch latency rather than work --
+    BASELINE config C1: 1,024 nodes, 121 RHS per trajectory.  Same results as `GraphedRK` / `solve_fixed` up to float32
+    rounding of the stage combinations (the aggregation order is the layer kernels').
+
+        rk = PersistentRK(layer, x, ps, st, dt, "tsit5")
+        uT = rk.solve(x, nsteps)                  # [N, d]
+        du0, dps = rk.adjoint(dL_duT)             # [N, d], flat phi-parameter gradient
+    """
+
+    def __init__(self, layer, x: Tensor, ps, st, dt: float, method: str = "rk4"):
+        import ctypes as C
+        from . import _lib
+        from .layers import ExplicitEdgeConv
+        if not isinstance(layer, ExplicitEdgeConv):
+            raise TypeError("PersistentRK integrates ExplicitEdgeConv right-hand sides; use GraphedRK for the other layers")
+        self._lib = _lib
+        self.lib = _lib.load()
+        (x_rm, phi, _, self.handle, self.desc, self.snode, _, _, _, _) = layer.prepare(x, ps, st)
+        self._layer, self._st = layer, st
+        self.dev = x_rm.device
+        self.phi = phi.detach().contiguous().clone()
+        _, A, b = TABLEAUS[method]
+        tab = _lib.RkTableau()
+        tab.n_stages = len(A)
+        for i, row in enumerate(A):
+            for j, a in enumerate(row):
+                tab.a[i][j] = float(a)
+        for i, w in enumerate(b):
+            tab.b[i] = float(w)
+        self.tab, self.S, self.dt = tab, len(A), float(dt)
+        with torch.cuda.device(self.dev):
+            nbytes = self.lib.ngpde_edgeconv_ode_workspace_bytes(self.handle, C.byref(self.desc), C.byref(tab))
+        if nbytes == 0:
+            _lib.check(-1)
+        self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev)
+        self.u = x_rm.detach().clone()
+        self.lam = torch.zeros_like(self.u)
+        self.dparams = torch.zeros_like(self.phi)
+        self.traj: Optional[Tensor] = None
+        self.nsteps = 0
+        self.rhs_evals = 0
+
+    def set_params(self, ps) -> None:
+        pr = self._layer.prepare(self.u.T, ps, self._st)
+        self.phi.copy_(pr[1].detach())
+
+    def solve(self, u0: Tensor, nsteps: int) -> Tensor:
+        import ctypes as C
+        from .ops import _ptr, _stream, LAUNCHES
+        u0 = u0.T if u0.shape != self.u.shape else u0
+        self.u.copy_(u0)
+        if self.traj is None or self.nsteps != nsteps:
+            self.traj = torch.empty((nsteps, self.S) + tuple(self.u.shape), dtype=torch.float32, device=self.dev)
+            self.nsteps = nsteps
+        with torch.cuda.device(self.dev):
+            self._lib.check(self.lib.ngpde_edgeconv_ode_forward(
+                self.handle, C.byref(self.desc), C.byref(self.tab), self.dt, nsteps, self.phi.data_ptr(), _ptr(self.snode),
+                self.u.data_ptr(), self.traj.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream(self.dev)))
+        LAUNCHES["count"] += 1
+        self.rhs_evals += nsteps * self.S
+        return self.u
+
+    def adjoint(self, dL_duT: Tensor):
+        import ctypes as C
+        from .ops import _ptr, _stream, LAUNCHES
+        g = dL_duT.T if dL_duT.shape != self.u.shape else dL_duT
+        self.lam.copy_(g)
+        with torch.cuda.device(self.dev):
+            self._lib.check(self.lib.ngpde_edgeconv_ode_adjoint(
+                self.handle, C.byref(self.desc), C.byref(self.tab), self.dt, self.nsteps, self.phi.data_ptr(), _ptr(self.snode),
+                self.traj.data_ptr(), self.lam.data_ptr(), self.dparams.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                _stream(self.dev)))
+        LAUNCHES["count"] += 1
+        self.rhs_evals += self.nsteps * self.S
+        return self.lam, self.dparams

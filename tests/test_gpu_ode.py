@@ -74,3 +74,32 @@ def test_cuda_graph_step_and_adjoint(name, method, kw, dt, t1):
     uT3 = rk.solve(w.x, nsteps).clone()
     _, dps3 = rk.adjoint(2.0 * uT3 / n)
     assert torch.equal(uT, uT3) and torch.equal(g, unpad(dps3))
+
+
+@pytest.mark.parametrize("method,dt,t1,side", [("tsit5", 0.05, 1.0, 32), ("rk4", 0.05, 0.5, 17)])
+def test_persistent_kernel_integrator_and_adjoint(method, dt, t1, side):
+    """One-launch integrator + one-launch adjoint (ode.PersistentRK, thread-block cluster) on the C1 model: trajectory and
+    gradient against the float64 oracle (<= 1e-4) and against the CUDA-graph path built from the layer kernels."""
+    w = workloads.c1_edgeconv("cuda", side=side)
+    nsteps = int(round(t1 / dt))
+    prk = ode.PersistentRK(w.layer, w.x, w.ps, w.st, dt, method)
+    uT = prk.solve(w.x, nsteps).clone()
+    n = uT.numel()
+    lam, dps = prk.adjoint(2.0 * uT / n)
+    u64, g64 = _oracle_traj(w, method, dt, t1, torch.float64, True)
+    errs = dict(u=relerr(uT.T, u64), g=relerr(dps, g64))
+    assert all(v <= TRAJ_TOL for v in errs.values()), errs
+    rk = ode.GraphedRK(w.layer, w.x, w.ps, w.st, dt, method)
+    uT2 = rk.solve(w.x, nsteps).clone()
+    lam2, dps2 = rk.adjoint(2.0 * uT2 / n)
+    assert relerr(uT, uT2) <= 1e-6 and relerr(lam, lam2) <= 1e-5 and relerr(dps, dps2[:dps.numel()]) <= 1e-5
+    # deterministic
+    uT3 = prk.solve(w.x, nsteps).clone()
+    _, dps3 = prk.adjoint(2.0 * uT3 / n)
+    assert torch.equal(uT, uT3) and torch.equal(dps, dps3)
+
+
+def test_persistent_kernel_rejects_what_it_cannot_take():
+    w = workloads.c3_vmh("cuda", side=8)
+    with pytest.raises(TypeError):
+        ode.PersistentRK(w.layer, w.x, w.ps, w.st, 0.1)
