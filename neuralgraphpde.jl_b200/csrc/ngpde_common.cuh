@@ -60,7 +60,9 @@ struct ngpde_graph {
   int* units[3] = {nullptr, nullptr, nullptr};
   int n_units[3] = {0, 0, 0};
   ngpde::GcnLayout gcn[2];
-  int ode_max_edges = -1;  // largest in-edge count of the persistent ODE kernels' node ranges (computed on first use)
+  int ode_max_tedges[2] = {-1, -1};
+  int ode_wide_cluster[2] = {-1, -1};  // [forward, adjoint]: can a 16-CTA cluster be scheduled on this device (-1: not probed yet)
+  int ode_max_edges[2] = {-1, -1};  // largest in-edge count of the persistent ODE kernels' node ranges (computed on first use)
 };
 
 namespace ngpde {

@@ -277,6 +277,7 @@ int launch_bwd_tc(bool node, const TcBwdPhase& t, const MlpDev& mlp, const BwdAr
 void tc_set_enabled(bool on) { g_use_tc = on; }
 bool tc_get_enabled() { return g_use_tc; }
 void tc_set_debug_buffer(long long* p) { g_tcb_dbg = p; }
+long long* tc_get_debug_buffer() { return g_tcb_dbg; }
 
 }  // namespace ngpde
 // 

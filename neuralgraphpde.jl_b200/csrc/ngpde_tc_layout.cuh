@@ -80,6 +80,7 @@ int launch_fwd_tc(bool node, int num_sms, const TcPhase& t, const MlpDev& mlp, c
                   float* wblock, cudaStream_t st);
 int launch_bwd_tc(bool node, const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base, float* wblock, cudaStream_t st);
 void tc_set_enabled(bool on);          // NGPDE_OPT_TENSOR_CORES
+long long* tc_get_debug_buffer();
 void tc_set_debug_buffer(long long* p);  // phase timestamps of the edge-phase backward (tools/tcb_phases.py)
 
 }  // namespace ngpde
