@@ -446,13 +446,23 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
 // ---- a bare Chain of Dense layers over the node axis (used by GCNConv's W*x) ----
 int make_mlp_dev(const ngpde_mlp& m, MlpDev* out, const char* what) { return make_mlp(m, out, what); }
 
+namespace {
+bool node_tc_fwd_plan(const MlpDev& mlp, TcPhase* t) {
+  *t = TcPhase{};
+  t->on = tc_make_layout(mlp, 0, false, mlp.dims[mlp.L], true, &t->lay, &t->smem, &t->off_cols, &t->off_groups, &t->group_bytes);
+  return t->on;
+}
+}  // namespace
+
+// bytes of the prepared weight block the tensor-core node kernel wants (0: the MLP runs on the FFMA engine)
+size_t node_mlp_forward_ws(const MlpDev& mlp) {
+  TcPhase t;
+  return node_tc_fwd_plan(mlp, &t) ? align256(4 * (size_t)t.lay.block_floats) : 0;
+}
+
 int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, float* y,
-                     cudaStream_t st) {
-  int te = 0, smem = 0;
-  if (int rc = pick_tile([&](int t) { return 4 * fwd_smem(mlp, 0, 0, 0, t).floats; }, &te, &smem)) return rc;
-  FwdSmem fs = fwd_smem(mlp, 0, 0, 0, te);
+                     cudaStream_t st, void* workspace, size_t ws_bytes) {
   FwdArgs n{};
-  n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + te - 1) / te), (int)g->N, 1};
   n.arr[ARR_X] = x;
   n.ld[ARR_X] = mlp.dims[0];
   n.n_segs = 1;
@@ -461,6 +471,16 @@ int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* param
   n.params = params;
   n.dout = mlp.dims[mlp.L];
   n.out = y;
+  TcPhase t;
+  if (workspace != nullptr && aligned16(workspace) && node_tc_fwd_plan(mlp, &t) && ws_bytes >= 4 * (size_t)t.lay.block_floats) {
+    // tcgen05 node kernel (ngpde_tc.cuh): layers <= 64 wide
+    n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + TC_TILE - 1) / TC_TILE), (int)g->N, 1};
+    return launch_fwd_tc(true, g->num_sms, t, mlp, params, n, static_cast<float*>(workspace), st);
+  }
+  int te = 0, smem = 0;
+  if (int rc = pick_tile([&](int t) { return 4 * fwd_smem(mlp, 0, 0, 0, t).floats; }, &te, &smem)) return rc;
+  FwdSmem fs = fwd_smem(mlp, 0, 0, 0, te);
+  n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + te - 1) / te), (int)g->N, 1};
   n.offA = fs.offA; n.offB = fs.offB; n.offW = fs.offW; n.offH = fs.offH;
   return launch_fwd_node(te, n, smem, g->num_sms, st);
 }
@@ -469,15 +489,26 @@ namespace {
 struct NodeBwdLayout {
   int te, smem, grid;
   BwdSmem s;
+  TcBwdPhase tc;
   size_t off_wt, off_part, total;
 };
 int node_bwd_layout(const ngpde_graph* g, const MlpDev& mlp, NodeBwdLayout* L) {
-  if (int rc = pick_tile([&](int te) { return 4 * bwd_smem(mlp, 0, 0, 0, 0, true, true, te).floats; }, &L->te, &L->smem))
-    return rc;
-  L->s = bwd_smem(mlp, 0, 0, 0, 0, true, true, L->te);
-  const int nu = (int)((g->N + L->te - 1) / L->te);
-  if (int rc = bwd_grid_node(L->te, L->smem, std::max(1, nu), g->num_sms, &L->grid)) return rc;
   size_t off = 0;
+  L->tc = TcBwdPhase{};
+  if (tc_bwd_make(mlp, 0, false, true, NGPDE_AGGR_SUM, true, &L->tc)) {  // tcgen05 node kernel (ngpde_tc_bwd.cuh)
+    L->te = TC_TILE;
+    L->smem = L->tc.smem;
+    L->tc.grid = std::max(1, std::min((int)((g->N + TC_TILE - 1) / TC_TILE), g->num_sms));
+    L->grid = L->tc.grid;
+    L->tc.ws_off = off;
+    off = align256(off + 4 * (size_t)L->tc.lay.block_floats);
+  } else {
+    if (int rc = pick_tile([&](int te) { return 4 * bwd_smem(mlp, 0, 0, 0, 0, true, true, te).floats; }, &L->te, &L->smem))
+      return rc;
+    L->s = bwd_smem(mlp, 0, 0, 0, 0, true, true, L->te);
+    const int nu = (int)((g->N + L->te - 1) / L->te);
+    if (int rc = bwd_grid_node(L->te, L->smem, std::max(1, nu), g->num_sms, &L->grid)) return rc;
+  }
   L->off_wt = off;   off = align256(off + sizeof(float) * mlp.n_params);
   L->off_part = off; off = align256(off + sizeof(float) * (size_t)L->grid * mlp.n_params);
   L->total = off;
@@ -504,7 +535,7 @@ int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* para
   float* wt = reinterpret_cast<float*>(ws + L.off_wt);
   float* part = reinterpret_cast<float*>(ws + L.off_part);
   NGPDE_CUDA_TRY(cudaMemsetAsync(part, 0, L.total - L.off_part, st));
-  transpose_weights_kernel<<<64, 256, 0, st>>>(params, wt, mlp);
+  if (!L.tc.on) transpose_weights_kernel<<<64, 256, 0, st>>>(params, wt, mlp);
   BwdArgs n{};
   n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + L.te - 1) / L.te), (int)g->N, 1};
   n.arr[ARR_X] = x;
@@ -524,7 +555,11 @@ int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* para
   n.store_last = L.s.store_last;
   std::memcpy(n.zoff, L.s.zoff, sizeof(n.zoff));
   n.offG0 = L.s.offG0; n.offG1 = L.s.offG1; n.offW = L.s.offW;
-  if (int rc = launch_bwd_node(L.te, n, L.smem, L.grid, st)) return rc;
+  if (L.tc.on) {
+    if (int rc = launch_bwd_tc(true, L.tc, mlp, n, reinterpret_cast<float*>(ws + L.tc.ws_off), st)) return rc;
+  } else {
+    if (int rc = launch_bwd_node(L.te, n, L.smem, L.grid, st)) return rc;
+  }
   reduce_partials_kernel<<<(mlp.n_params + 255) / 256, 256, 0, st>>>(part, L.grid, mlp.n_params, dparams);
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;

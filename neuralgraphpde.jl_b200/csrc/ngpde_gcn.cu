@@ -164,13 +164,102 @@ __global__ void __launch_bounds__(256) gcn_aggregate_v4_kernel(int N, const int*
   out[(size_t)r * LPR + lane] = acc;
 }
 
+// Same sum once more (developer variant, NOT the default: see gcn_variant), for Blackwell's packed FP32 pipe: `mul.rn.f32x2` / `add.rn.f32x2` round each half exactly like the scalar
+// instructions (so entry order and roundings are STILL ((x * c_s) * w) added in ascending order) at half the issue slots,
+// and U entries per trip are in flight, predicated instead of split into a full-group loop and a tail.
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+template <int LPR, bool HAS_ENT, int U>
+__global__ void __launch_bounds__(256) gcn_aggregate_v5_kernel(int N, const int* __restrict__ ptr, const int* __restrict__ ent,
+                                                                const int* __restrict__ other, const float* __restrict__ val,
+                                                                const float* __restrict__ c, const float4* __restrict__ x,
+                                                                float4* __restrict__ out) {
+  const unsigned gid = blockIdx.x * 256u + threadIdx.x;
+  const unsigned r = gid / LPR, lane = gid % LPR;
+  if (r >= (unsigned)N) return;
+  const float4* xl = x + lane;
+  unsigned long long a01 = 0ull, a23 = 0ull;  // (+0, +0)
+  int q = __ldg(ptr + r);
+  const int q1 = __ldg(ptr + r + 1);
+  const float cr = __ldg(c + r);
+  for (; q < q1; q += U) {
+    int s[U];
+    float w[U], cs[U];
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool on = q + u < q1;
+      const int j = on ? (HAS_ENT ? __ldg(ent + q + u) : q + u) : 0;
+      s[u] = on ? __ldg(other + j) : -1;
+      w[u] = on ? __ldg(val + j) : 1.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (s[u] >= 0) {
+        cs[u] = __ldg(c + s[u]);
+        v[u] = __ldg(xl + (size_t)s[u] * LPR);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (s[u] >= 0) {
+        const unsigned long long c2 = f2_pack(cs[u], cs[u]);
+        unsigned long long t01 = f2_mul(f2_pack(v[u].x, v[u].y), c2), t23 = f2_mul(f2_pack(v[u].z, v[u].w), c2);
+        if (w[u] != 1.f) {  // an unweighted, duplicate-free entry has val == 1: multiplying by it is exact, so it is skipped
+          const unsigned long long w2 = f2_pack(w[u], w[u]);
+          t01 = f2_mul(t01, w2);
+          t23 = f2_mul(t23, w2);
+        }
+        a01 = f2_add(a01, t01);
+        a23 = f2_add(a23, t23);
+      }
+    }
+  }
+  const unsigned long long cr2 = f2_pack(cr, cr);
+  a01 = f2_mul(a01, cr2);
+  a23 = f2_mul(a23, cr2);
+  float4 o;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(a01));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.z), "=f"(o.w) : "l"(a23));
+  out[(size_t)r * LPR + lane] = o;
+}
+
+// developer switch NGPDE_GCN_V: 0 (default) scalar kernel with 4 entries in flight; 1 / 2 the packed kernel with 4 / 8 in flight.
+// Measured on the C5 graph (2M nodes, d = 64, profiles/r02p_gcn_variants.csv): 420 / 612 / 870 us -- the packed kernels need 48 /
+// 80 registers against 32, and this latency-bound gather wants resident warps more than it wants issue slots.
+int gcn_variant() {
+  const char* e = getenv("NGPDE_GCN_V");
+  return e ? atoi(e) : 0;
+}
+
 template <int LPR>
 int launch_gcn_v4(int N, const int* ptr, const int* ent, const int* other, const float* val, const float* c, const float* x,
                   float* out, cudaStream_t st) {
   const unsigned blocks = (unsigned)(((long long)N * LPR + 255) / 256);
   const float4* x4 = reinterpret_cast<const float4*>(x);
   float4* o4 = reinterpret_cast<float4*>(out);
-  if (ent) gcn_aggregate_v4_kernel<LPR, true><<<blocks, 256, 0, st>>>(N, ptr, ent, other, val, c, x4, o4);
+  const int variant = gcn_variant();
+  if (variant == 2) {
+    if (ent) gcn_aggregate_v5_kernel<LPR, true, 8><<<blocks, 256, 0, st>>>(N, ptr, ent, other, val, c, x4, o4);
+    else gcn_aggregate_v5_kernel<LPR, false, 8><<<blocks, 256, 0, st>>>(N, ptr, ent, other, val, c, x4, o4);
+  } else if (variant == 1) {
+    if (ent) gcn_aggregate_v5_kernel<LPR, true, 4><<<blocks, 256, 0, st>>>(N, ptr, ent, other, val, c, x4, o4);
+    else gcn_aggregate_v5_kernel<LPR, false, 4><<<blocks, 256, 0, st>>>(N, ptr, ent, other, val, c, x4, o4);
+  } else if (ent) gcn_aggregate_v4_kernel<LPR, true><<<blocks, 256, 0, st>>>(N, ptr, ent, other, val, c, x4, o4);
   else gcn_aggregate_v4_kernel<LPR, false><<<blocks, 256, 0, st>>>(N, ptr, ent, other, val, c, x4, o4);
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;
@@ -272,7 +361,7 @@ __global__ void axpy_stages_kernel(float* __restrict__ out, const float* __restr
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct GcnWs {
-  size_t off_val, off_c, off_agg, off_lin, off_tmp, off_tmp2, off_cs, off_mlp, total;
+  size_t off_val, off_c, off_agg, off_lin, off_tmp, off_tmp2, off_tmp3, off_cs, off_wblk, wblk_bytes, off_mlp, total;
   int dmin;
   int cs_blocks, cs_rows;
 };
@@ -286,6 +375,15 @@ int gcn_mlp(const ngpde_gcn_desc& d, bool first, MlpDev* m) {
   h.act[0] = first ? NGPDE_ACT_IDENTITY : d.act;
   h.has_bias[0] = first ? 0 : d.has_bias;
   return make_mlp_dev(h, m, "GCNConv weight");
+}
+
+// activation the Dense backward of the out >= in branch runs with: identity when act' is a function of the output (the
+// cotangent is pre-multiplied by act'(y) in one elementwise pass), else the activation itself (swish / gelu)
+int gcn_bwd_act(int act) { return act_grad_from_y(act) ? NGPDE_ACT_IDENTITY : act; }
+
+__global__ void act_grad_y_kernel(const float* __restrict__ y, const float* __restrict__ dy, int act, size_t total, float* __restrict__ dp) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) dp[i] = dy[i] * act_grad_y(act, y[i]);
 }
 
 int gcn_ws(const ngpde_graph* g, const ngpde_gcn_desc& d, bool backward, GcnWs* w) {
@@ -302,11 +400,21 @@ int gcn_ws(const ngpde_graph* g, const ngpde_gcn_desc& d, bool backward, GcnWs* 
   w->cs_rows = 256;
   w->cs_blocks = (int)((N + w->cs_rows - 1) / w->cs_rows);
   w->off_cs = off;  off = align256(off + (backward ? sizeof(float) * (size_t)std::max(w->cs_blocks, 1) * d.out_chs : 0));
-  w->off_mlp = off;
-  if (backward) {
+  {
+    const bool first = d.out_chs < d.in_chs;
     MlpDev m;
-    if (int rc = gcn_mlp(d, d.out_chs < d.in_chs, &m)) return rc;
-    off = align256(off + node_mlp_backward_ws(g, m));
+    if (int rc = gcn_mlp(d, first, &m)) return rc;
+    w->off_wblk = off;  // prepared weight block of the tensor-core Dense (0 bytes: FFMA engine)
+    w->wblk_bytes = node_mlp_forward_ws(m);
+    off = align256(off + w->wblk_bytes);
+    // out >= in, backward: dP = dy * act'(y) so that the Dense backward sees an identity activation (tensor-core eligible)
+    w->off_tmp3 = off;
+    off = align256(off + ((backward && !first) ? sizeof(float) * N * d.out_chs : 0));
+    w->off_mlp = off;
+    if (backward) {
+      m.act[0] = first ? m.act[0] : gcn_bwd_act(d.act);
+      off = align256(off + node_mlp_backward_ws(g, m));
+    }
   }
   w->total = off;
   return NGPDE_OK;
@@ -362,7 +470,7 @@ extern "C" int ngpde_gcn_conv_forward(ngpde_graph_t g, const ngpde_gcn_desc* des
   MlpDev m;
   if (int rc = gcn_mlp(*desc, first, &m)) return rc;
   if (first) {
-    if (int rc = node_mlp_forward(g, m, weight, x, lin, st)) return rc;  // layers.jl:220-223
+    if (int rc = node_mlp_forward(g, m, weight, x, lin, st, ws + w.off_wblk, w.wblk_bytes)) return rc;  // layers.jl:220-223
     if (int rc = launch_gcn_aggregate(N, desc->out_chs, L.colptr, nullptr, L.rowval, val, c, lin, agg, st)) return rc;
     const size_t total = (size_t)N * desc->out_chs;
     bias_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(agg, desc->has_bias ? bias : nullptr, desc->act, total,
@@ -372,7 +480,7 @@ extern "C" int ngpde_gcn_conv_forward(ngpde_graph_t g, const ngpde_gcn_desc* des
     // weight and bias are adjacent in the flat parameter vector; pass them as one segment when they are
     NGPDE_REQUIRE(!desc->has_bias || bias == weight + (size_t)desc->in_chs * desc->out_chs,
                   "GCNConv expects bias to follow weight in the flat parameter vector");
-    if (int rc = node_mlp_forward(g, m, weight, agg, y, st)) return rc;  // layers.jl:235-238
+    if (int rc = node_mlp_forward(g, m, weight, agg, y, st, ws + w.off_wblk, w.wblk_bytes)) return rc;  // layers.jl:235-238
   }
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;
@@ -382,7 +490,6 @@ extern "C" int ngpde_gcn_conv_backward(ngpde_graph_t g, const ngpde_gcn_desc* de
                                        const float* bias, const float* edge_weight, const float* graph_weight,
                                        const float* y, const float* dy, float* dx, float* dweight, float* dbias,
                                        void* workspace, size_t workspace_bytes, void* stream) {
-  (void)y;
   if (int rc = gcn_check(g, desc)) return rc;
   NGPDE_REQUIRE(x && weight && dy && dx && dweight, "null tensor argument");
   NGPDE_REQUIRE(!desc->has_bias || (bias && dbias), "bias/dbias is NULL");
@@ -417,7 +524,7 @@ extern "C" int ngpde_gcn_conv_backward(ngpde_graph_t g, const ngpde_gcn_desc* de
   if (int rc = gcn_mlp(*desc, first, &m)) return rc;
   if (first) {
     // y = act(A(Wx) + b):  dP = dy*act'(.), db = colsum(dP), du = A^T dP, (dW, dx) from the bare Dense
-    if (int rc = node_mlp_forward(g, m, weight, x, lin, st)) return rc;
+    if (int rc = node_mlp_forward(g, m, weight, x, lin, st, ws + w.off_wblk, w.wblk_bytes)) return rc;
     if (int rc = launch_gcn_aggregate(N, desc->out_chs, L.colptr, nullptr, L.rowval, val, c, lin, agg, st)) return rc;
     const size_t total = (size_t)N * desc->out_chs;
     bias_act_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(agg, desc->has_bias ? bias : nullptr, desc->act,
@@ -434,7 +541,16 @@ extern "C" int ngpde_gcn_conv_backward(ngpde_graph_t g, const ngpde_gcn_desc* de
                                      dbias == dweight + (size_t)desc->in_chs * desc->out_chs),
                   "GCNConv expects bias to follow weight in the flat parameter vector (and dbias to follow dweight)");
     if (int rc = launch_gcn_aggregate(N, desc->in_chs, L.colptr, nullptr, L.rowval, val, c, x, agg, st)) return rc;
-    if (int rc = node_mlp_backward(g, m, weight, agg, dy, tmp, dweight, mlp_ws, mlp_ws_bytes, st)) return rc;
+    const float* dp = dy;
+    if (gcn_bwd_act(desc->act) != desc->act) {
+      NGPDE_REQUIRE(y != nullptr, "GCNConv backward needs the forward output y");
+      const size_t total = (size_t)N * desc->out_chs;
+      float* tmp3 = reinterpret_cast<float*>(ws + w.off_tmp3);
+      act_grad_y_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, dy, desc->act, total, tmp3);
+      dp = tmp3;
+      m.act[0] = NGPDE_ACT_IDENTITY;
+    }
+    if (int rc = node_mlp_backward(g, m, weight, agg, dp, tmp, dweight, mlp_ws, mlp_ws_bytes, st)) return rc;
     if (int rc = launch_gcn_aggregate(N, desc->in_chs, L.tptr, L.tpos, L.colidx, val, c, tmp, dx, st)) return rc;
   }
   NGPDE_CUDA_TRY(cudaGetLastError());
