@@ -133,7 +133,8 @@ int ngpde_version(void);
 const char* ngpde_last_error(void);
 /* Process-wide switches (benchmarks and tests only).  NGPDE_OPT_TENSOR_CORES: 1 (default) runs MLPs whose layers are at
  * most 64 wide on the tcgen05 tensor-core kernels (3xTF32, fp32-accurate); 0 forces the FP32-FFMA kernels everywhere. */
-enum { NGPDE_OPT_TENSOR_CORES = 0, NGPDE_OPT_GNO_FACTORED = 1, NGPDE_OPT_DEBUG_SKIP = 2 /* developer aid: phase timing */ };
+enum { NGPDE_OPT_TENSOR_CORES = 0, NGPDE_OPT_GNO_FACTORED = 1, NGPDE_OPT_DEBUG_SKIP = 2 /* developer aid: phase timing */,
+       NGPDE_OPT_HOIST = 3 };
 /* NGPDE_OPT_GNO_FACTORED: 1 (default) evaluates GNOConv whose phi ends in an affine layer, with aggr = + or mean, in
  * factored form (per-destination outer-product sums + dense GEMMs; csrc/ngpde_gno.cuh); 0 forces the per-edge contraction. */
 int ngpde_set_option(int32_t option, int32_t value);

@@ -53,6 +53,101 @@ __global__ void dx_combine_kernel(const float* __restrict__ dx_direct, const flo
 }
 
 
+// ---- first-layer hoisting (see Plan::hoist below) ----
+struct HoistMap {
+  Seg segs[8];
+  int n_segs;
+  int dx, ds;   // node input row r: r < dx -> x column r, else snode column r - dx
+  int n1;       // width of phi's first hidden layer
+  int w_off0, b_off0, w_off1;  // phi layer 0 weight / bias offsets, offset where layer 1 starts (= end of layer 0)
+  int n_params;                // of phi
+};
+
+__device__ __forceinline__ int hoist_node_row(const HoistMap& h, const Seg& sg, int f) {
+  return sg.arr == ARR_X ? sg.col + f : h.dx + sg.col + f;
+}
+
+// phi's first Dense acts on [a_t-side columns; a_s-side columns; differences]: every column is a node quantity, so the layer is
+//   W1 z_e + b1 = (Wt' h_t + b1) + Ws' h_s,  h = [x; snode],  Wt = sum_seg coef_dst W1[seg rows], Ws = sum_seg coef_src W1[seg rows]
+// out_t: [hdin][n1] then b1 [n1];  out_s: [hdin][n1];  out_in: [n1][n1] identity, then phi's parameters from layer 1 on.
+__global__ void hoist_fold_kernel(const float* __restrict__ phi, HoistMap h, float* __restrict__ out_t, float* __restrict__ out_s,
+                                  float* __restrict__ out_in) {
+  const int hdin = h.dx + h.ds, n1 = h.n1;
+  const int total_w = hdin * n1, tail = h.n_params - h.w_off1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_w + n1 + n1 * n1 + tail; i += gridDim.x * blockDim.x) {
+    if (i < total_w) {
+      const int nr = i / n1, n = i - nr * n1;
+      float wt = 0.f, ws = 0.f;
+      for (int si = 0; si < h.n_segs; ++si) {
+        const Seg sg = h.segs[si];
+        const int f = (sg.arr == ARR_X ? nr : nr - h.dx) - sg.col;
+        if ((sg.arr == ARR_X) != (nr < h.dx) || f < 0 || f >= sg.width) continue;
+        const float w = phi[h.w_off0 + (size_t)(sg.row + f) * n1 + n];
+        wt = fmaf(coef_dst(sg.kind), w, wt);
+        ws = fmaf(coef_src(sg.kind), w, ws);
+      }
+      out_t[i] = wt;
+      out_s[i] = ws;
+    } else if (i < total_w + n1) {
+      const int n = i - total_w;
+      out_t[total_w + n] = h.b_off0 >= 0 ? phi[h.b_off0 + n] : 0.f;
+    } else if (i < total_w + n1 + n1 * n1) {
+      const int j = i - total_w - n1;
+      out_in[j] = (j / n1 == j % n1) ? 1.f : 0.f;
+    } else {
+      const int j = i - total_w - n1 - n1 * n1;
+      out_in[n1 * n1 + j] = phi[h.w_off1 + j];
+    }
+  }
+}
+
+// the transpose of the fold: gradients of (Wt, b1, Ws) and of the inner MLP -> dphi
+__global__ void hoist_unfold_kernel(HoistMap h, const float* __restrict__ d_t, const float* __restrict__ d_s,
+                                    const float* __restrict__ d_in, int din0, float* __restrict__ dphi) {
+  const int n1 = h.n1, total_w = (h.dx + h.ds) * n1, tail = h.n_params - h.w_off1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < din0 * n1 + n1 + tail; i += gridDim.x * blockDim.x) {
+    if (i < din0 * n1) {
+      const int ir = i / n1, n = i - ir * n1;
+      float v = 0.f;
+      for (int si = 0; si < h.n_segs; ++si) {
+        const Seg sg = h.segs[si];
+        const int f = ir - sg.row;
+        if (f < 0 || f >= sg.width) continue;
+        const int nr = hoist_node_row(h, sg, f);
+        v = coef_dst(sg.kind) * d_t[(size_t)nr * n1 + n] + coef_src(sg.kind) * d_s[(size_t)nr * n1 + n];
+      }
+      dphi[h.w_off0 + i] = v;
+    } else if (i < din0 * n1 + n1) {
+      const int n = i - din0 * n1;
+      if (h.b_off0 >= 0) dphi[h.b_off0 + n] = d_t[total_w + n];
+    } else {
+      const int j = i - din0 * n1 - n1;
+      dphi[h.w_off1 + j] = d_in[n1 * n1 + j];
+    }
+  }
+}
+
+// q[n] = [a[n]; b[n]]  (rows of `w` floats, w % 4 == 0) and its inverse
+__global__ void hoist_join_kernel(const float4* __restrict__ a, const float4* __restrict__ b, size_t rows, int w4, float4* __restrict__ q) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 2 * w4) return;
+  const size_t r = i / (2 * w4);
+  const int c = (int)(i - r * 2 * w4);
+  q[i] = c < w4 ? a[r * w4 + c] : b[r * w4 + c - w4];
+}
+__global__ void hoist_split_kernel(const float4* __restrict__ q, size_t rows, int w4, float4* __restrict__ a, float4* __restrict__ b) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 2 * w4) return;
+  const size_t r = i / (2 * w4);
+  const int c = (int)(i - r * 2 * w4);
+  if (c < w4) a[r * w4 + c] = q[i]; else b[r * w4 + c - w4] = q[i];
+}
+// out = a + b + c (a may be NULL)
+__global__ void add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, size_t n, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (a ? a[i] : 0.f) + b[i] + c[i];
+}
+
 namespace {
 
 // ---- optional per-kernel timing (ngpde_profile_*): CUDA events recorded on the launching stream around the four
@@ -127,13 +222,91 @@ struct Plan {
   bool node_addend = false;
   bool edge_need_dz0 = false;
   bool edge_dst_side = false;
+  // First-layer hoisting.  When phi's first Dense is too wide for the tensor-core kernels (C5: 130 columns, limit 80) and
+  // every input column is a node quantity, W1 z_e + b1 = Pt[dst] + Ps[src] with two per-NODE projections (1/deg of the
+  // work); the edge kernels then run the INNER problem: x' = Q = [Pt | Ps] ([N][2 n1]), input = Q[dst][0:n1] + Q[src][n1:2n1]
+  // (two segments over the same input rows, summed by the gather), MLP = [identity n1 x n1, phi's first activation] followed
+  // by phi's layers 1.. -- the unchanged tcgen05 kernels, whose cotangent machinery returns dQ.
+  bool hoist = false;
+  MlpDev phi_in{}, mlp_t{}, mlp_s{};
+  Seg hsegs[2];
+  int h_n1 = 0, h_din = 0;
 };
+bool g_hoist = true;  // NGPDE_OPT_HOIST
 
 void push_seg(Seg* segs, int* n, int* row, int kind, int arr, int col, int width) {
   if (width <= 0) return;
   segs[*n] = Seg{kind, arr, col, width, *row};
   *row += width;
   ++*n;
+}
+
+int one_layer_mlp(int din, int dout, bool bias, MlpDev* m) {
+  ngpde_mlp h{};
+  h.n_layers = 1;
+  h.dims[0] = din;
+  h.dims[1] = dout;
+  h.act[0] = NGPDE_ACT_IDENTITY;
+  h.has_bias[0] = bias ? 1 : 0;
+  return make_mlp(h, m, "hoisted projection");
+}
+
+// decides Plan::hoist and fills the inner problem
+void plan_hoist(const ngpde_conv_desc& d, Plan* p) {
+  p->hoist = false;
+  if (!g_hoist || p->contract || p->phi.L < 2 || p->phi.L > NGPDE_MAX_LAYERS) return;
+  if (!(d.aggr == NGPDE_AGGR_SUM || d.aggr == NGPDE_AGGR_MEAN)) return;
+  for (int i = 0; i < p->n_esegs; ++i) {
+    const Seg& sg = p->esegs[i];
+    if (!(sg.arr == ARR_X || sg.arr == ARR_S)) return;          // edge / graph features are not node quantities
+    if (sg.kind == SEG_EDGE || sg.kind == SEG_GRAPH) return;
+  }
+  const int din0 = p->phi.dims[0], n1 = p->phi.dims[1], hdin = d.dx + p->ds;
+  if ((din0 + 15) / 16 * 16 <= 80) return;                      // narrow enough for the tensor-core kernels as it is
+  if (n1 > TC_MAXN || (n1 & 3) != 0 || hdin > 80) return;
+  TcBwdPhase tb;
+  TcLayout lay;
+  int a, b, c, e;
+  {  // the original MLP must be off the tensor-core path, the inner one on it (forward and backward)
+    if (tc_make_layout(p->phi, 0, false, p->dm, false, &lay, &a, &b, &c, &e) && tc_bwd_make(p->phi, 0, false, false, d.aggr, true, &tb)) return;
+  }
+  MlpDev in{};
+  in.L = p->phi.L;
+  in.dims[0] = n1;
+  for (int l = 1; l <= in.L; ++l) in.dims[l] = p->phi.dims[l];
+  in.act[0] = p->phi.act[0];
+  in.w_off[0] = 0;
+  in.b_off[0] = -1;
+  const int shift = n1 * n1 - p->phi.w_off[1];
+  for (int l = 1; l < in.L; ++l) {
+    in.act[l] = p->phi.act[l];
+    in.w_off[l] = p->phi.w_off[l] + shift;
+    in.b_off[l] = p->phi.b_off[l] >= 0 ? p->phi.b_off[l] + shift : -1;
+  }
+  in.n_params = p->phi.n_params + shift;
+  if (!tc_make_layout(in, 0, false, p->dm, false, &lay, &a, &b, &c, &e)) return;
+  if (!tc_bwd_make(in, 0, false, false, d.aggr, true, &tb)) return;
+  if (one_layer_mlp(hdin, n1, true, &p->mlp_t) || one_layer_mlp(hdin, n1, false, &p->mlp_s)) return;
+  p->phi_in = in;
+  p->h_n1 = n1;
+  p->h_din = hdin;
+  p->hsegs[0] = Seg{SEG_DST, ARR_X, 0, n1, 0};
+  p->hsegs[1] = Seg{SEG_SRC, ARR_X, n1, n1, 0};
+  p->hoist = true;
+}
+
+HoistMap hoist_map(const ngpde_conv_desc& d, const Plan& p) {
+  HoistMap h{};
+  h.n_segs = p.n_esegs;
+  std::memcpy(h.segs, p.esegs, sizeof(p.esegs));
+  h.dx = d.dx;
+  h.ds = p.ds;
+  h.n1 = p.h_n1;
+  h.w_off0 = p.phi.w_off[0];
+  h.b_off0 = p.phi.b_off[0];
+  h.w_off1 = p.phi.w_off[1];
+  h.n_params = p.phi.n_params;
+  return h;
 }
 
 int make_plan(const ngpde_graph* g, const ngpde_conv_desc& d, Plan* p) {
@@ -228,6 +401,7 @@ int make_plan(const ngpde_graph* g, const ngpde_conv_desc& d, Plan* p) {
       if (coef_dst_host(p->esegs[i].kind)) p->edge_dst_side = true;
     }
   }
+  plan_hoist(d, p);
   return NGPDE_OK;
 }
 
@@ -359,6 +533,41 @@ int check_io(const ngpde_conv_desc& d, const Plan& p, const ngpde_conv_io& io, b
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// workspace of the hoisted first layer (forward; the backward recomputes it): folded parameters, the two projections, Q
+struct HoistWs {
+  size_t off_ft = 0, off_fs = 0, off_fin = 0, off_pt = 0, off_ps = 0, off_q = 0, off_wblk = 0, wblk_bytes = 0;
+};
+size_t hoist_ws(const Plan& p, int64_t N, size_t off, HoistWs* h) {
+  h->off_ft = off;  off = align256(off + sizeof(float) * p.mlp_t.n_params);
+  h->off_fs = off;  off = align256(off + sizeof(float) * p.mlp_s.n_params);
+  h->off_fin = off; off = align256(off + sizeof(float) * p.phi_in.n_params);
+  h->off_pt = off;  off = align256(off + sizeof(float) * (size_t)N * p.h_n1);
+  h->off_ps = off;  off = align256(off + sizeof(float) * (size_t)N * p.h_n1);
+  h->off_q = off;   off = align256(off + sizeof(float) * (size_t)N * 2 * p.h_n1);
+  h->wblk_bytes = std::max(node_mlp_forward_ws(p.mlp_t), node_mlp_forward_ws(p.mlp_s));
+  h->off_wblk = off; off = align256(off + h->wblk_bytes);
+  return off;
+}
+
+// fold the parameters, project the nodes, interleave: Q = [x|s] Wt + b1 | [x|s] Ws
+int hoist_forward(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, const ngpde_conv_io& io, char* ws, const HoistWs& h,
+                  cudaStream_t st) {
+  float* ft = reinterpret_cast<float*>(ws + h.off_ft);
+  float* fs = reinterpret_cast<float*>(ws + h.off_fs);
+  float* fin = reinterpret_cast<float*>(ws + h.off_fin);
+  float* pt = reinterpret_cast<float*>(ws + h.off_pt);
+  float* ps = reinterpret_cast<float*>(ws + h.off_ps);
+  float* q = reinterpret_cast<float*>(ws + h.off_q);
+  hoist_fold_kernel<<<32, 256, 0, st>>>(io.phi_params, hoist_map(d, p), ft, fs, fin);
+  if (int rc = node_mlp_forward(g, p.mlp_t, ft, io.x, pt, st, ws + h.off_wblk, h.wblk_bytes, io.snode, p.ds)) return rc;
+  if (int rc = node_mlp_forward(g, p.mlp_s, fs, io.x, ps, st, ws + h.off_wblk, h.wblk_bytes, io.snode, p.ds)) return rc;
+  const size_t n4 = (size_t)g->N * 2 * (p.h_n1 / 4);
+  hoist_join_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(pt), reinterpret_cast<const float4*>(ps),
+                                                                  (size_t)g->N, p.h_n1 / 4, reinterpret_cast<float4*>(q));
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
 struct BwdLayout {
   int te_e, smem_e, grid_e;
   int te_n, smem_n, grid_n;
@@ -368,11 +577,17 @@ struct BwdLayout {
   // factored GNO
   size_t off_S = 0, off_T = 0, off_DM = 0, off_dBpart = 0, off_B = 0;
   int part_stride = 0, gno_splits = 1;
+  // hoisted first layer: recomputed forward part, then dQ and what hangs off it
+  HoistWs hoist;
+  size_t off_dq = 0, off_dpt = 0, off_dps = 0, off_dxt = 0, off_dxs = 0, off_dft = 0, off_dfs = 0, off_dfin = 0, off_nodews = 0,
+         nodews_bytes = 0;
+  int dxe = 0;  // width of the array the edge phase differentiates: dx, or 2 n1 when hoisted
 };
 
 int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, BwdLayout* L) {
   L->te_e = 0; L->smem_e = 0; L->grid_e = 0;
-  if (tc_bwd_make(p.phi, p.contract, false, false, d.aggr, p.edge_need_dz0, &L->tce)) {
+  L->dxe = p.hoist ? 2 * p.h_n1 : d.dx;
+  if (tc_bwd_make(p.hoist ? p.phi_in : p.phi, p.contract, false, false, d.aggr, p.hoist || p.edge_need_dz0, &L->tce)) {
     L->tce.grid = std::max(1, std::min(g->n_units[2], g->num_sms));
     L->grid_e = L->tce.grid;
   } else {
@@ -408,9 +623,23 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
   L->off_wt_node = off;   off = align256(off + sizeof(float) * p.node.n_params);
   L->off_dmbar = off;     off = align256(off + (p.has_node ? sizeof(float) * g->N * p.dm : 0));
   L->off_dxdirect = off;  off = align256(off + (p.has_node ? sizeof(float) * g->N * d.dx : 0));
-  L->off_dxdst = off;     off = align256(off + (p.edge_dst_side ? sizeof(float) * g->N * d.dx : 0));
-  L->off_desrc = off;     off = align256(off + sizeof(float) * g->E * d.dx);
-  L->part_stride = p.phi.n_params;
+  L->off_dxdst = off;     off = align256(off + ((p.edge_dst_side || p.hoist) ? sizeof(float) * g->N * L->dxe : 0));
+  L->off_desrc = off;     off = align256(off + sizeof(float) * g->E * L->dxe);
+  L->part_stride = p.hoist ? p.phi_in.n_params : p.phi.n_params;
+  if (p.hoist) {
+    NGPDE_REQUIRE(L->tce.on, "internal: hoisted plan without a tensor-core edge phase");
+    off = hoist_ws(p, g->N, off, &L->hoist);
+    L->off_dq = off;   off = align256(off + sizeof(float) * g->N * 2 * p.h_n1);
+    L->off_dpt = off;  off = align256(off + sizeof(float) * g->N * p.h_n1);
+    L->off_dps = off;  off = align256(off + sizeof(float) * g->N * p.h_n1);
+    L->off_dxt = off;  off = align256(off + sizeof(float) * g->N * d.dx);
+    L->off_dxs = off;  off = align256(off + sizeof(float) * g->N * d.dx);
+    L->off_dft = off;  off = align256(off + sizeof(float) * p.mlp_t.n_params);
+    L->off_dfs = off;  off = align256(off + sizeof(float) * p.mlp_s.n_params);
+    L->off_dfin = off; off = align256(off + sizeof(float) * p.phi_in.n_params);
+    L->nodews_bytes = std::max(node_mlp_backward_ws(g, p.mlp_t), node_mlp_backward_ws(g, p.mlp_s));
+    L->off_nodews = off; off = align256(off + L->nodews_bytes);
+  }
   if (p.contract == 2) {
     const size_t R = (size_t)p.gno_Ka * d.gno_in;
     L->part_stride = p.phi.w_off[p.phi.L - 1];  // the last layer's gradient comes from the GEMM dB = S' DM
@@ -460,13 +689,27 @@ size_t node_mlp_forward_ws(const MlpDev& mlp) {
   return node_tc_fwd_plan(mlp, &t) ? align256(4 * (size_t)t.lay.block_floats) : 0;
 }
 
+namespace {
+// node input = [x (dx columns) ; snode (ds columns)]; ds = 0: x alone
+template <class Args>
+void node_input_segs(Args* n, const float* x, int dx, const float* snode, int ds) {
+  n->arr[ARR_X] = x;
+  n->ld[ARR_X] = dx;
+  n->n_segs = 1;
+  n->segs[0] = Seg{SEG_DST, ARR_X, 0, dx, 0};
+  if (ds > 0) {
+    n->arr[ARR_S] = snode;
+    n->ld[ARR_S] = ds;
+    n->segs[1] = Seg{SEG_DST, ARR_S, 0, ds, dx};
+    n->n_segs = 2;
+  }
+}
+}  // namespace
+
 int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, float* y,
-                     cudaStream_t st, void* workspace, size_t ws_bytes) {
+                     cudaStream_t st, void* workspace, size_t ws_bytes, const float* snode, int ds) {
   FwdArgs n{};
-  n.arr[ARR_X] = x;
-  n.ld[ARR_X] = mlp.dims[0];
-  n.n_segs = 1;
-  n.segs[0] = Seg{SEG_DST, ARR_X, 0, mlp.dims[0], 0};
+  node_input_segs(&n, x, mlp.dims[0] - ds, snode, ds);
   n.mlp = mlp;
   n.params = params;
   n.dout = mlp.dims[mlp.L];
@@ -524,7 +767,7 @@ size_t node_mlp_backward_ws(const ngpde_graph* g, const MlpDev& mlp) {
 
 // dy -> dx (may be nullptr... it is always produced here), dparams
 int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, const float* dy,
-                      float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st) {
+                      float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st, const float* snode, int ds) {
   NodeBwdLayout L;
   if (int rc = node_bwd_layout(g, mlp, &L)) return rc;
   if (ws_bytes < L.total) {
@@ -538,10 +781,7 @@ int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* para
   if (!L.tc.on) transpose_weights_kernel<<<64, 256, 0, st>>>(params, wt, mlp);
   BwdArgs n{};
   n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + L.te - 1) / L.te), (int)g->N, 1};
-  n.arr[ARR_X] = x;
-  n.ld[ARR_X] = mlp.dims[0];
-  n.n_segs = 1;
-  n.segs[0] = Seg{SEG_DST, ARR_X, 0, mlp.dims[0], 0};
+  node_input_segs(&n, x, mlp.dims[0] - ds, snode, ds);
   n.mlp = mlp;
   n.params = params;
   n.wt = wt;
@@ -550,7 +790,7 @@ int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* para
   n.dparams_partial = part;
   n.part_stride = mlp.n_params;
   n.dx_direct = dx;
-  n.dx = mlp.dims[0];
+  n.dx = mlp.dims[0] - ds;
   n.need_dz0 = 1;
   n.store_last = L.s.store_last;
   std::memcpy(n.zoff, L.s.zoff, sizeof(n.zoff));
@@ -575,15 +815,18 @@ struct FwdPlan {
   TcPhase edge, node;
   size_t ws_bytes = 0;
   size_t off_S = 0, off_B = 0;
+  HoistWs hoist;
 };
 
 FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin) {
   FwdPlan f;
   size_t off = 0;
+  if (p.hoist) off = hoist_ws(p, N, off, &f.hoist);
+  const MlpDev& ephi = p.hoist ? p.phi_in : p.phi;
   // max/min: the backward's tie mask compares recomputed messages with the forward's bit for bit, so both must run
   // the same arithmetic -- those aggregations stay on the FFMA kernels until the backward has a tensor-core twin.
   const bool aggr_ok = aggr == NGPDE_AGGR_SUM || aggr == NGPDE_AGGR_MEAN;
-  f.edge.on = aggr_ok && tc_make_layout(p.phi, p.contract, false, p.dm, false, &f.edge.lay, &f.edge.smem, &f.edge.off_cols,
+  f.edge.on = aggr_ok && tc_make_layout(ephi, p.contract, false, p.dm, false, &f.edge.lay, &f.edge.smem, &f.edge.off_cols,
                                         &f.edge.off_groups, &f.edge.group_bytes);
   if (f.edge.on) {
     f.edge.ws_off = off;
@@ -614,6 +857,7 @@ extern "C" int ngpde_set_option(int32_t option, int32_t value) {
     case NGPDE_OPT_TENSOR_CORES: tc_set_enabled(value != 0); return NGPDE_OK;
     case NGPDE_OPT_GNO_FACTORED: g_gno_factored = value != 0; return NGPDE_OK;
     case NGPDE_OPT_DEBUG_SKIP: g_debug_skip = value; return NGPDE_OK;
+    case NGPDE_OPT_HOIST: g_hoist = value != 0; return NGPDE_OK;
     default: set_error("unknown option %d", option); return NGPDE_ERR_INVALID;
   }
 }
@@ -685,7 +929,22 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
   a.gno_S = p.contract == 2 ? reinterpret_cast<float*>(fws + fp.off_S) : nullptr;
   {
     ProfScope prof(NGPDE_PROF_FWD_EDGE, st);
-    if (fp.edge.on) {
+    if (p.hoist) {
+      // first layer hoisted to the nodes; the edge kernel runs the inner problem on Q (Plan::hoist)
+      NGPDE_REQUIRE(fp.edge.on, "internal: hoisted plan without a tensor-core edge phase");
+      if (int rc = hoist_forward(g, *desc, p, *io, fws, fp.hoist, st)) return rc;
+      a.arr[ARR_X] = reinterpret_cast<const float*>(fws + fp.hoist.off_q);
+      a.ld[ARR_X] = 2 * p.h_n1;
+      a.n_segs = 2;
+      a.segs[0] = p.hsegs[0];
+      a.segs[1] = p.hsegs[1];
+      a.mlp = p.phi_in;
+      a.params = reinterpret_cast<const float*>(fws + fp.hoist.off_fin);
+      a.tg.unit_ptr = g->units[2];
+      a.tg.n_units = g->n_units[2];
+      if (int rc = launch_fwd_tc(false, g->num_sms, fp.edge, p.phi_in, a.params, a, reinterpret_cast<float*>(fws + fp.edge.ws_off), st))
+        return rc;
+    } else if (fp.edge.on) {
       a.tg.unit_ptr = g->units[2];
       a.tg.n_units = g->n_units[2];
       if (int rc = launch_fwd_tc(false, g->num_sms, fp.edge, p.phi, io->phi_params, a, reinterpret_cast<float*>(fws + fp.edge.ws_off), st))
@@ -765,7 +1024,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   float* wt_node = reinterpret_cast<float*>(ws + L.off_wt_node);
   float* dmbar = p.has_node ? reinterpret_cast<float*>(ws + L.off_dmbar) : nullptr;
   float* dxdirect = p.has_node ? reinterpret_cast<float*>(ws + L.off_dxdirect) : nullptr;
-  float* dxdst = p.edge_dst_side ? reinterpret_cast<float*>(ws + L.off_dxdst) : nullptr;
+  float* dxdst = (p.edge_dst_side || p.hoist) ? reinterpret_cast<float*>(ws + L.off_dxdst) : nullptr;
   float* desrc = reinterpret_cast<float*>(ws + L.off_desrc);
   float* part_phi = reinterpret_cast<float*>(ws + L.off_part_phi);
   float* part_node = reinterpret_cast<float*>(ws + L.off_part_node);
@@ -840,6 +1099,16 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     std::memcpy(a.segs, p.esegs, sizeof(p.esegs));
     a.mlp = p.phi;
     a.params = io->phi_params;
+    if (p.hoist) {  // the inner problem on Q (Plan::hoist); its forward part is recomputed here
+      if (int rc = hoist_forward(g, *desc, p, *io, ws, L.hoist, st)) return rc;
+      a.arr[ARR_X] = reinterpret_cast<const float*>(ws + L.hoist.off_q);
+      a.ld[ARR_X] = 2 * p.h_n1;
+      a.n_segs = 2;
+      a.segs[0] = p.hsegs[0];
+      a.segs[1] = p.hsegs[1];
+      a.mlp = p.phi_in;
+      a.params = reinterpret_cast<const float*>(ws + L.hoist.off_fin);
+    }
     a.wt = wt_phi;
     a.contract = p.contract;
     a.gin = desc->gno_in;
@@ -855,10 +1124,10 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     a.debug_skip = g_debug_skip;
     a.dxdst = dxdst;
     a.desrc = desrc;
-    a.dx = desc->dx;
-    a.need_dz0 = p.edge_need_dz0 ? 1 : 0;
+    a.dx = L.dxe;
+    a.need_dz0 = (p.edge_need_dz0 || p.hoist) ? 1 : 0;
     a.store_last = L.se.store_last;
-    a.has_dst_side = p.edge_dst_side ? 1 : 0;
+    a.has_dst_side = (p.edge_dst_side || p.hoist) ? 1 : 0;
     std::memcpy(a.zoff, L.se.zoff, sizeof(a.zoff));
     a.offG0 = L.se.offG0; a.offG1 = L.se.offG1; a.offW = L.se.offW; a.offH = L.se.offH;
     a.offDM = L.se.offDM; a.offP = L.se.offP; a.offDH = L.se.offDH; a.offRed = L.se.offRed;
@@ -873,7 +1142,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       if (L.tce.on) {
         a.tg.unit_ptr = g->units[2];
         a.tg.n_units = g->n_units[2];
-        if (int rc = launch_bwd_tc(false, L.tce, p.phi, a, reinterpret_cast<float*>(ws + L.tce.ws_off), st)) return rc;
+        if (int rc = launch_bwd_tc(false, L.tce, a.mlp, a, reinterpret_cast<float*>(ws + L.tce.ws_off), st)) return rc;
       } else {
         if (int rc = launch_bwd_edge(te, a, L.smem_e, L.grid_e, st)) return rc;
       }
@@ -885,10 +1154,37 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
         reduce_partials_kernel<<<(PB + 255) / 256, 256, 0, st>>>(gdB, L.gno_splits, PB, io->dphi_params + p.phi.w_off[p.phi.L - 1]);
       }
     } else if (dxdst) {
-      NGPDE_CUDA_TRY(cudaMemsetAsync(dxdst, 0, sizeof(float) * g->N * desc->dx, st));
+      NGPDE_CUDA_TRY(cudaMemsetAsync(dxdst, 0, sizeof(float) * g->N * L.dxe, st));
     }
     const int P = L.part_stride;
-    if (P > 0) reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_phi, L.grid_e, P, io->dphi_params);
+    float* dphi_target = p.hoist ? reinterpret_cast<float*>(ws + L.off_dfin) : io->dphi_params;
+    if (P > 0) reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_phi, L.grid_e, P, dphi_target);
+    if (p.hoist) {
+      // dQ = dxdst + transpose-gather(desrc) -> (dPt, dPs) -> the two projections' backward -> dx, d(Wt, b1, Ws) -> dphi
+      ProfScope prof(NGPDE_PROF_BWD_EDGE, st);
+      float* dq = reinterpret_cast<float*>(ws + L.off_dq);
+      float* dpt = reinterpret_cast<float*>(ws + L.off_dpt);
+      float* dps = reinterpret_cast<float*>(ws + L.off_dps);
+      float* dxt = reinterpret_cast<float*>(ws + L.off_dxt);
+      float* dxs = reinterpret_cast<float*>(ws + L.off_dxs);
+      float* dft = reinterpret_cast<float*>(ws + L.off_dft);
+      float* dfs = reinterpret_cast<float*>(ws + L.off_dfs);
+      const size_t totq = (size_t)g->N * L.dxe;
+      dx_combine_kernel<<<(unsigned)((totq + 255) / 256), 256, 0, st>>>(nullptr, dxdst, g->E > 0 ? desrc : nullptr, g->tptr, g->tpos,
+                                                                         (int)g->N, L.dxe, dq);
+      const size_t n4 = totq / 4;
+      hoist_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(dq), (size_t)g->N, p.h_n1 / 4,
+                                                                       reinterpret_cast<float4*>(dpt), reinterpret_cast<float4*>(dps));
+      const float* ft = reinterpret_cast<const float*>(ws + L.hoist.off_ft);
+      const float* fs = reinterpret_cast<const float*>(ws + L.hoist.off_fs);
+      if (int rc = node_mlp_backward(g, p.mlp_t, ft, io->x, dpt, dxt, dft, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds)) return rc;
+      if (int rc = node_mlp_backward(g, p.mlp_s, fs, io->x, dps, dxs, dfs, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds)) return rc;
+      hoist_unfold_kernel<<<32, 256, 0, st>>>(hoist_map(*desc, p), dft, dfs, dphi_target, p.phi.dims[0], io->dphi_params);
+      const size_t total = (size_t)g->N * desc->dx;
+      add3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dxdirect, dxt, dxs, total, io->dx);
+      NGPDE_CUDA_TRY(cudaGetLastError());
+      return NGPDE_OK;
+    }
   }
 
   // ---- dx = dx_direct + dxdst + transpose-gather(desrc) ----

@@ -100,9 +100,10 @@ __device__ __forceinline__ float coef_src(int kind) {
 int make_mlp_dev(const ngpde_mlp& m, MlpDev* out, const char* what);
 size_t node_mlp_forward_ws(const MlpDev& mlp);
 int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, float* y,
-                     cudaStream_t st, void* workspace = nullptr, size_t ws_bytes = 0);
+                     cudaStream_t st, void* workspace = nullptr, size_t ws_bytes = 0, const float* snode = nullptr, int ds = 0);
 size_t node_mlp_backward_ws(const ngpde_graph* g, const MlpDev& mlp);
 int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, const float* dy,
-                      float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st);
+                      float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st, const float* snode = nullptr,
+                      int ds = 0);
 
 }  // namespace ngpde

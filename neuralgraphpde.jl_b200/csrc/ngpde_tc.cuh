@@ -80,19 +80,43 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                : "memory");
 }
 
-// column table of the gather: cols[c] for c < Kd[0] (padding columns get kind = -1)
+// column table of the gather: cols[c] for c < Kd[0] (padding columns get kind = -1).
+// Two segments may cover the SAME input rows (the hoisted first layer, ngpde_conv.cu: a destination-side and a source-side
+// projection of one array): the column is then their sum, kind = TC_KIND_DPS with the float distance of the source-side
+// column from `base` in the bits above TC_KIND_SHIFT.  TC_KIND_VEC4 marks a 4-aligned column whose group of four is one
+// aligned float4 on either side.
+constexpr int TC_KIND_DPS = 6, TC_KIND_MASK = 127, TC_KIND_VEC4 = 128, TC_KIND_SHIFT = 8;
+
+template <class Args>
+__device__ __forceinline__ TcCol tc_match_col(const Args& a, int c) {
+  TcCol t{nullptr, 0, -1};
+  for (int si = 0; si < a.n_segs; ++si) {
+    const Seg sg = a.segs[si];
+    const int f = c - sg.row;
+    if (f >= 0 && f < sg.width) {
+      const float* b = a.arr[sg.arr] + sg.col + f;
+      if (t.kind < 0) {
+        t.base = b;
+        t.ld = a.ld[sg.arr];
+        t.kind = sg.kind;
+      } else if (t.kind == SEG_DST && sg.kind == SEG_SRC && a.ld[sg.arr] == t.ld) {
+        t.kind = TC_KIND_DPS | ((int)(b - t.base) << TC_KIND_SHIFT);
+      }
+    }
+  }
+  return t;
+}
+
 template <class Args>
 __device__ __forceinline__ void tc_build_cols(const Args& a, TcCol* cols, int ncols, int tid, int nthreads) {
   for (int c = tid; c < ncols; c += nthreads) {
-    TcCol t{nullptr, 0, -1};
-    for (int si = 0; si < a.n_segs; ++si) {
-      const Seg sg = a.segs[si];
-      const int f = c - sg.row;
-      if (f >= 0 && f < sg.width) {
-        t.base = a.arr[sg.arr] + sg.col + f;
-        t.ld = a.ld[sg.arr];
-        t.kind = sg.kind;
-      }
+    TcCol t = tc_match_col(a, c);
+    if ((c & 3) == 0 && c + 3 < ncols && (t.kind & TC_KIND_MASK) == TC_KIND_DPS && t.kind > 0) {
+      const TcCol u = tc_match_col(a, c + 3);
+      const int delta = t.kind >> TC_KIND_SHIFT;
+      if (u.kind == t.kind && u.base == t.base + 3 && (t.ld & 3) == 0 && (delta & 3) == 0 &&
+          (reinterpret_cast<uintptr_t>(t.base) & 15) == 0)
+        t.kind |= TC_KIND_VEC4;
     }
     cols[c] = t;
   }
@@ -137,11 +161,20 @@ __device__ __forceinline__ void tc_load_chunk(const TcChunk ch, int r, int first
 
 __device__ __forceinline__ float tc_gather_col(const TcCol t, int s, int d, int p, int pg) {
   if (t.kind < 0) return 0.f;
+  if ((t.kind & TC_KIND_MASK) == TC_KIND_DPS)
+    return __ldg(t.base + (size_t)d * t.ld) + __ldg(t.base + (size_t)s * t.ld + (t.kind >> TC_KIND_SHIFT));
   const int i0 = (t.kind == SEG_SRC || t.kind == SEG_SMD) ? s : (t.kind == SEG_EDGE ? p : (t.kind == SEG_GRAPH ? pg : d));
   float v = t.base[(size_t)i0 * t.ld];
   if (t.kind == SEG_SMD) v -= t.base[(size_t)d * t.ld];
   if (t.kind == SEG_DMS) v -= t.base[(size_t)s * t.ld];
   return v;
+}
+
+// four columns of a TC_KIND_VEC4 group: one float4 from the destination's row plus one from the source's
+__device__ __forceinline__ void tc_gather_dps4(const TcCol t, int s, int d, float* v) {
+  const float4 x = __ldg(reinterpret_cast<const float4*>(t.base + (size_t)d * t.ld));
+  const float4 y = __ldg(reinterpret_cast<const float4*>(t.base + (size_t)s * t.ld + (t.kind >> TC_KIND_SHIFT)));
+  v[0] = x.x + y.x; v[1] = x.y + y.y; v[2] = x.z + y.z; v[3] = x.w + y.w;
 }
 
 // tanh(x) = 1 - 2 / (2^(2x log2 e) + 1) on the SFU exponential and reciprocal: 5 instructions, absolute error <= 1.5e-7
@@ -304,8 +337,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
           for (int j = 0; j < 8; ++j) vv[j] = 0.f;
           if (valid) tc_load_chunk<2>(ch, d, c0 & 15, vv);
         } else {
+          const TcCol t0 = cols[c0], t4 = cols[c0 + 4];
+          if (!NODE && (t0.kind & TC_KIND_VEC4) && (t4.kind & TC_KIND_VEC4) && t0.kind > 0 && t4.kind > 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) vv[j] = valid ? tc_gather_col(cols[c0 + j], s, d, p, pg) : 0.f;
+            for (int j = 0; j < 8; ++j) vv[j] = 0.f;
+            if (valid) {
+              tc_gather_dps4(t0, s, d, vv);
+              tc_gather_dps4(t4, s, d, vv + 4);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vv[j] = valid ? tc_gather_col(cols[c0 + j], s, d, p, pg) : 0.f;
+          }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {

@@ -505,9 +505,19 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         const int gq = NODE ? 0 : Kd0 >> 2;
         for (int cc = q * gq; cc < (q + 1) * gq; cc += 4) {
           uint32_t hi[4], lo[4];
+          float v4[4];
+          const TcCol t0 = cols[cc];
+          if ((t0.kind & TC_KIND_VEC4) && t0.kind > 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v4[j] = 0.f;
+            if (valid) tc_gather_dps4(t0, s, d, v4);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v4[j] = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float v = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+            const float v = v4[j];
             if (keep_z0) DZ[row * (Kd0 + 1) + cc + j] = v;  // re-read by layer 0's weight-gradient staging
             const float h = umma::tf32_hi(v);
             hi[j] = __float_as_uint(h);

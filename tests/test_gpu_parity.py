@@ -749,3 +749,56 @@ def test_kernel_path_query_reports_the_engine_that_runs():
         assert p4["fwd_edge"] == 0 and p4["bwd_edge"] == 0
     finally:
         ngpde._lib.set_option(ngpde._lib.OPT_GNO_FACTORED, 1)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# first-layer hoisting (csrc/ngpde_conv.cu, Plan::hoist): phi's wide first Dense as two per-node projections, the
+# tcgen05 edge kernels on the inner problem
+# ------------------------------------------------------------------------------------------------------------
+
+def _wide_first_layer_case(family, aggr, dx, hidden, depth, seed=41, n=1200, e=11000):
+    rng = np.random.default_rng(seed)
+    s, t = rng.integers(0, n, e), rng.integers(0, n, e)
+    # a destination row longer than a tile (two under `mean`; an unnormalised float32 sum over ~300 messages is itself only good
+    # to ~1e-5 -- the float32 and float64 oracles differ by that much -- so `+` stops at 130, as in the tensor-core tests above)
+    t[:(280 if aggr == "mean" else 130)] = 17
+    s[:40] = 17           # ... that is also a busy source
+    t[300:306] = n - 1
+    g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"x": jl_rand(rng, 2, n)}).to(DEV)
+    acts = ["tanh", "sigmoid", "elu"]
+    din = 2 * dx + 2
+    dims = [din] + [hidden] * (depth - 1) + [hidden if family == "vmh" else dx]
+    phi = Chain(*[Dense(dims[i], dims[i + 1], acts[i % 3] if i < len(dims) - 2 else "identity") for i in range(len(dims) - 1)])
+    if family == "vmh":
+        layer = VMHConv(phi, Chain(Dense(dx + hidden, 48, "tanh"), Dense(48, 3)), initialgraph=g, aggr=aggr)
+    else:
+        layer = ExplicitEdgeConv(phi, initialgraph=g, aggr=aggr)
+    ps, st = setup(rng, layer, DEV)
+    return layer, jl_rand(rng, dx, n, DEV), ps, st, g
+
+
+@pytest.mark.parametrize("family,aggr,dx,hidden,depth", [("vmh", "mean", 64, 64, 2),   # the C5 VMHConv shape: phi 130 => 64 => 64
+                                                         ("vmh", "+", 47, 32, 3),      # odd input width, narrower hidden layers
+                                                         ("edge", "mean", 50, 64, 3)])  # ExplicitEdgeConv: [h_i; h_j; pos_j - pos_i]
+def test_hoisted_first_layer_against_oracle_and_unhoisted(family, aggr, dx, hidden, depth):
+    from ngpde import engine
+    layer, x, ps, st, g = _wide_first_layer_case(family, aggr, dx, hidden, depth)
+    r = engine.RhsRunner(layer, x, ps, st)
+    paths = ngpde._lib.kernel_paths(r.handle, r.desc)
+    assert paths["fwd_edge"] == 1 and paths["bwd_edge"] == 1, paths   # tcgen05 kernels on the inner problem
+    check_layer(layer, x, ps, st, g)
+    rng = np.random.default_rng(9)
+    y, _, _ = product_fwd_bwd(layer, x, ps, st)
+    dy = torch.from_numpy(rng.standard_normal(tuple(y.shape)).astype(np.float32)).to(DEV)
+    y1, dx1, dp1 = product_fwd_bwd(layer, x, ps, st, dy)
+    y2, dx2, dp2 = product_fwd_bwd(layer, x, ps, st, dy)
+    assert torch.equal(y1, y2) and torch.equal(dx1, dx2) and torch.equal(dp1, dp2)   # deterministic
+    ngpde._lib.set_option(ngpde._lib.OPT_HOIST, 0)
+    try:
+        assert ngpde._lib.kernel_paths(r.handle, r.desc)["bwd_edge"] == 0            # the FFMA engine without it
+        y0, dx0, dp0 = product_fwd_bwd(layer, x, ps, st, dy)
+    finally:
+        ngpde._lib.set_option(ngpde._lib.OPT_HOIST, 1)
+    assert not torch.equal(y0, y1)
+    errs = dict(y=relerr(y1, y0), dx=relerr(dx1, dx0), dp=relerr(dp1, dp0))
+    assert all(v <= TOL for v in errs.values()), errs
