@@ -127,6 +127,33 @@ __global__ void hoist_unfold_kernel(HoistMap h, const float* __restrict__ d_t, c
   }
 }
 
+// Node phase (gamma over [x; mbar]): W1 [x; m] + b1 = (Wx' x + b1) + Wm' m.  out_u: [dx][n1] then b1; out_v: [dm][n1];
+// out_in: identity [n1][n1] then the parameters from layer 1 on.  `row_x` / `row_m`: first input row of the x / mbar segment.
+struct NodeHoistMap {
+  int dx, dm, n1, row_x, row_m, w_off0, b_off0, w_off1, n_params;
+};
+__global__ void nhoist_fold_kernel(const float* __restrict__ prm, NodeHoistMap h, float* __restrict__ out_u, float* __restrict__ out_v,
+                                   float* __restrict__ out_in) {
+  const int n1 = h.n1, nu = h.dx * n1, nv = h.dm * n1, tail = h.n_params - h.w_off1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nu + n1 + nv + n1 * n1 + tail; i += gridDim.x * blockDim.x) {
+    if (i < nu) out_u[i] = prm[h.w_off0 + h.row_x * n1 + i];
+    else if (i < nu + n1) out_u[i] = h.b_off0 >= 0 ? prm[h.b_off0 + i - nu] : 0.f;
+    else if (i < nu + n1 + nv) out_v[i - nu - n1] = prm[h.w_off0 + h.row_m * n1 + (i - nu - n1)];
+    else if (i < nu + n1 + nv + n1 * n1) { const int j = i - nu - n1 - nv; out_in[j] = (j / n1 == j % n1) ? 1.f : 0.f; }
+    else { const int j = i - nu - n1 - nv - n1 * n1; out_in[n1 * n1 + j] = prm[h.w_off1 + j]; }
+  }
+}
+__global__ void nhoist_unfold_kernel(NodeHoistMap h, const float* __restrict__ d_u, const float* __restrict__ d_v,
+                                     const float* __restrict__ d_in, float* __restrict__ dprm) {
+  const int n1 = h.n1, nu = h.dx * n1, nv = h.dm * n1, tail = h.n_params - h.w_off1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nu + n1 + nv + tail; i += gridDim.x * blockDim.x) {
+    if (i < nu) dprm[h.w_off0 + h.row_x * n1 + i] = d_u[i];
+    else if (i < nu + n1) { if (h.b_off0 >= 0) dprm[h.b_off0 + i - nu] = d_u[i]; }
+    else if (i < nu + n1 + nv) dprm[h.w_off0 + h.row_m * n1 + (i - nu - n1)] = d_v[i - nu - n1];
+    else { const int j = i - nu - n1 - nv; dprm[h.w_off1 + j] = d_in[n1 * n1 + j]; }
+  }
+}
+
 // q[n] = [a[n]; b[n]]  (rows of `w` floats, w % 4 == 0) and its inverse
 __global__ void hoist_join_kernel(const float4* __restrict__ a, const float4* __restrict__ b, size_t rows, int w4, float4* __restrict__ q) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,6 +258,10 @@ struct Plan {
   MlpDev phi_in{}, mlp_t{}, mlp_s{};
   Seg hsegs[2];
   int h_n1 = 0, h_din = 0;
+  // the same for the node update over [x; mbar] (C5's gamma: 128 columns): U = x Wx + b1, V = mbar Wm, inner input U + V
+  bool nhoist = false;
+  MlpDev node_in{}, mlp_u{}, mlp_v{};
+  int nh_n1 = 0, nh_row_x = 0, nh_row_m = 0;
 };
 bool g_hoist = true;  // NGPDE_OPT_HOIST
 
@@ -249,6 +280,26 @@ int one_layer_mlp(int din, int dout, bool bias, MlpDev* m) {
   h.act[0] = NGPDE_ACT_IDENTITY;
   h.has_bias[0] = bias ? 1 : 0;
   return make_mlp(h, m, "hoisted projection");
+}
+
+// inner MLP of a hoisted first layer: [identity n1 x n1 with the first activation] + layers 1.., parameters = [I | tail]
+MlpDev hoist_inner_mlp(const MlpDev& m) {
+  MlpDev in{};
+  const int n1 = m.dims[1];
+  in.L = m.L;
+  in.dims[0] = n1;
+  for (int l = 1; l <= in.L; ++l) in.dims[l] = m.dims[l];
+  in.act[0] = m.act[0];
+  in.w_off[0] = 0;
+  in.b_off[0] = -1;
+  const int shift = n1 * n1 - m.w_off[1];
+  for (int l = 1; l < in.L; ++l) {
+    in.act[l] = m.act[l];
+    in.w_off[l] = m.w_off[l] + shift;
+    in.b_off[l] = m.b_off[l] >= 0 ? m.b_off[l] + shift : -1;
+  }
+  in.n_params = m.n_params + shift;
+  return in;
 }
 
 // decides Plan::hoist and fills the inner problem
@@ -270,29 +321,57 @@ void plan_hoist(const ngpde_conv_desc& d, Plan* p) {
   {  // the original MLP must be off the tensor-core path, the inner one on it (forward and backward)
     if (tc_make_layout(p->phi, 0, false, p->dm, false, &lay, &a, &b, &c, &e) && tc_bwd_make(p->phi, 0, false, false, d.aggr, true, &tb)) return;
   }
-  MlpDev in{};
-  in.L = p->phi.L;
-  in.dims[0] = n1;
-  for (int l = 1; l <= in.L; ++l) in.dims[l] = p->phi.dims[l];
-  in.act[0] = p->phi.act[0];
-  in.w_off[0] = 0;
-  in.b_off[0] = -1;
-  const int shift = n1 * n1 - p->phi.w_off[1];
-  for (int l = 1; l < in.L; ++l) {
-    in.act[l] = p->phi.act[l];
-    in.w_off[l] = p->phi.w_off[l] + shift;
-    in.b_off[l] = p->phi.b_off[l] >= 0 ? p->phi.b_off[l] + shift : -1;
-  }
-  in.n_params = p->phi.n_params + shift;
+  const MlpDev in = hoist_inner_mlp(p->phi);
   if (!tc_make_layout(in, 0, false, p->dm, false, &lay, &a, &b, &c, &e)) return;
   if (!tc_bwd_make(in, 0, false, false, d.aggr, true, &tb)) return;
   if (one_layer_mlp(hdin, n1, true, &p->mlp_t) || one_layer_mlp(hdin, n1, false, &p->mlp_s)) return;
+  if (!tc_make_layout(p->mlp_t, 0, false, n1, true, &lay, &a, &b, &c, &e) || !tc_bwd_make(p->mlp_t, 0, false, true, d.aggr, true, &tb)) return;
   p->phi_in = in;
   p->h_n1 = n1;
   p->h_din = hdin;
   p->hsegs[0] = Seg{SEG_DST, ARR_X, 0, n1, 0};
   p->hsegs[1] = Seg{SEG_SRC, ARR_X, n1, n1, 0};
   p->hoist = true;
+}
+
+void plan_nhoist(const ngpde_conv_desc& d, Plan* p) {
+  p->nhoist = false;
+  if (!g_hoist || !p->has_node || p->node_addend || p->node.L < 2 || p->node.L > NGPDE_MAX_LAYERS) return;
+  if (p->n_nsegs != 2) return;
+  int row_x = -1, row_m = -1;
+  for (int i = 0; i < 2; ++i) {
+    const Seg& sg = p->nsegs[i];
+    if (sg.kind != SEG_DST || sg.col != 0) return;
+    if (sg.arr == ARR_X && sg.width == d.dx) row_x = sg.row;
+    else if (sg.arr == ARR_M && sg.width == p->dm) row_m = sg.row;
+    else return;
+  }
+  if (row_x < 0 || row_m < 0) return;
+  const int din0 = p->node.dims[0], n1 = p->node.dims[1];
+  if ((din0 + 15) / 16 * 16 <= 80) return;
+  if (n1 > TC_MAXN || (n1 & 3) != 0 || d.dx > 80 || p->dm > 80) return;
+  TcBwdPhase tb;
+  TcLayout lay;
+  int a, b, c, e;
+  if (tc_make_layout(p->node, 0, false, p->dy, true, &lay, &a, &b, &c, &e) && tc_bwd_make(p->node, 0, false, true, d.aggr, true, &tb)) return;
+  const MlpDev in = hoist_inner_mlp(p->node);
+  if (!tc_make_layout(in, 0, false, p->dy, true, &lay, &a, &b, &c, &e)) return;
+  if (!tc_bwd_make(in, 0, false, true, d.aggr, true, &tb)) return;
+  if (one_layer_mlp(d.dx, n1, true, &p->mlp_u) || one_layer_mlp(p->dm, n1, false, &p->mlp_v)) return;
+  if (!tc_make_layout(p->mlp_u, 0, false, n1, true, &lay, &a, &b, &c, &e) || !tc_bwd_make(p->mlp_u, 0, false, true, d.aggr, true, &tb)) return;
+  if (!tc_make_layout(p->mlp_v, 0, false, n1, true, &lay, &a, &b, &c, &e) || !tc_bwd_make(p->mlp_v, 0, false, true, d.aggr, true, &tb)) return;
+  p->node_in = in;
+  p->nh_n1 = n1;
+  p->nh_row_x = row_x;
+  p->nh_row_m = row_m;
+  p->nhoist = true;
+}
+
+NodeHoistMap nhoist_map(const ngpde_conv_desc& d, const Plan& p) {
+  NodeHoistMap h{};
+  h.dx = d.dx; h.dm = p.dm; h.n1 = p.nh_n1; h.row_x = p.nh_row_x; h.row_m = p.nh_row_m;
+  h.w_off0 = p.node.w_off[0]; h.b_off0 = p.node.b_off[0]; h.w_off1 = p.node.w_off[1]; h.n_params = p.node.n_params;
+  return h;
 }
 
 HoistMap hoist_map(const ngpde_conv_desc& d, const Plan& p) {
@@ -402,6 +481,7 @@ int make_plan(const ngpde_graph* g, const ngpde_conv_desc& d, Plan* p) {
     }
   }
   plan_hoist(d, p);
+  plan_nhoist(d, p);
   return NGPDE_OK;
 }
 
@@ -568,6 +648,49 @@ int hoist_forward(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p,
   return NGPDE_OK;
 }
 
+struct NodeHoistWs {
+  size_t off_fu = 0, off_fv = 0, off_fin = 0, off_u = 0, off_v = 0, off_q = 0, off_wblk = 0, wblk_bytes = 0;
+};
+size_t nhoist_ws(const Plan& p, int64_t N, size_t off, NodeHoistWs* h) {
+  h->off_fu = off;  off = align256(off + sizeof(float) * p.mlp_u.n_params);
+  h->off_fv = off;  off = align256(off + sizeof(float) * p.mlp_v.n_params);
+  h->off_fin = off; off = align256(off + sizeof(float) * p.node_in.n_params);
+  h->off_u = off;   off = align256(off + sizeof(float) * (size_t)N * p.nh_n1);
+  h->off_v = off;   off = align256(off + sizeof(float) * (size_t)N * p.nh_n1);
+  h->off_q = off;   off = align256(off + sizeof(float) * (size_t)N * 2 * p.nh_n1);
+  h->wblk_bytes = std::max(node_mlp_forward_ws(p.mlp_u), node_mlp_forward_ws(p.mlp_v));
+  h->off_wblk = off; off = align256(off + h->wblk_bytes);
+  return off;
+}
+// Q' = [x Wx + b1 | mbar Wm]
+int nhoist_forward(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, const ngpde_conv_io& io, char* ws, const NodeHoistWs& h,
+                   cudaStream_t st) {
+  float* fu = reinterpret_cast<float*>(ws + h.off_fu);
+  float* fv = reinterpret_cast<float*>(ws + h.off_fv);
+  float* fin = reinterpret_cast<float*>(ws + h.off_fin);
+  float* u = reinterpret_cast<float*>(ws + h.off_u);
+  float* v = reinterpret_cast<float*>(ws + h.off_v);
+  float* q = reinterpret_cast<float*>(ws + h.off_q);
+  nhoist_fold_kernel<<<32, 256, 0, st>>>(io.node_params, nhoist_map(d, p), fu, fv, fin);
+  if (int rc = node_mlp_forward(g, p.mlp_u, fu, io.x, u, st, ws + h.off_wblk, h.wblk_bytes)) return rc;
+  if (int rc = node_mlp_forward(g, p.mlp_v, fv, io.mbar, v, st, ws + h.off_wblk, h.wblk_bytes)) return rc;
+  const size_t n4 = (size_t)g->N * 2 * (p.nh_n1 / 4);
+  hoist_join_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(u), reinterpret_cast<const float4*>(v),
+                                                                  (size_t)g->N, p.nh_n1 / 4, reinterpret_cast<float4*>(q));
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+// the inner node problem's argument block: x' = Q', input = Q'[:, 0:n1] + Q'[:, n1:2n1]
+template <class Args>
+void nhoist_args(const Plan& p, const float* q, Args* n) {
+  n->arr[ARR_X] = q;
+  n->ld[ARR_X] = 2 * p.nh_n1;
+  n->n_segs = 2;
+  n->segs[0] = Seg{SEG_DST, ARR_X, 0, p.nh_n1, 0};
+  n->segs[1] = Seg{SEG_SRC, ARR_X, p.nh_n1, p.nh_n1, 0};
+  n->mlp = p.node_in;
+}
+
 struct BwdLayout {
   int te_e, smem_e, grid_e;
   int te_n, smem_n, grid_n;
@@ -578,6 +701,8 @@ struct BwdLayout {
   size_t off_S = 0, off_T = 0, off_DM = 0, off_dBpart = 0, off_B = 0;
   int part_stride = 0, gno_splits = 1;
   // hoisted first layer: recomputed forward part, then dQ and what hangs off it
+  NodeHoistWs nhoist;
+  size_t off_ndq = 0, off_ng = 0, off_njunk = 0, off_ndfu = 0, off_ndfv = 0, off_ndfin = 0, off_nnodews = 0, nnodews_bytes = 0;
   HoistWs hoist;
   size_t off_dq = 0, off_dpt = 0, off_dps = 0, off_dxt = 0, off_dxs = 0, off_dft = 0, off_dfs = 0, off_dfin = 0, off_nodews = 0,
          nodews_bytes = 0;
@@ -604,7 +729,7 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
   L->te_n = 0; L->smem_n = 0; L->grid_n = 0;
   L->tcn = TcBwdPhase{};
   if (p.has_node) {
-    if (tc_bwd_make(p.node, 0, p.node_addend, true, d.aggr, true, &L->tcn)) {
+    if (tc_bwd_make(p.nhoist ? p.node_in : p.node, 0, p.node_addend, true, d.aggr, true, &L->tcn)) {
       L->tcn.grid = std::max(1, std::min((int)((g->N + TC_TILE - 1) / TC_TILE), g->num_sms));
       L->grid_n = L->tcn.grid;
     } else {
@@ -626,6 +751,18 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
   L->off_dxdst = off;     off = align256(off + ((p.edge_dst_side || p.hoist) ? sizeof(float) * g->N * L->dxe : 0));
   L->off_desrc = off;     off = align256(off + sizeof(float) * g->E * L->dxe);
   L->part_stride = p.hoist ? p.phi_in.n_params : p.phi.n_params;
+  if (p.nhoist) {
+    NGPDE_REQUIRE(L->tcn.on, "internal: hoisted node plan without a tensor-core node phase");
+    off = nhoist_ws(p, g->N, off, &L->nhoist);
+    L->off_ndq = off;   off = align256(off + sizeof(float) * g->N * 2 * p.nh_n1);
+    L->off_ng = off;    off = align256(off + sizeof(float) * g->N * p.nh_n1);
+    L->off_njunk = off; off = align256(off + sizeof(float) * g->N * p.nh_n1);
+    L->off_ndfu = off;  off = align256(off + sizeof(float) * p.mlp_u.n_params);
+    L->off_ndfv = off;  off = align256(off + sizeof(float) * p.mlp_v.n_params);
+    L->off_ndfin = off; off = align256(off + sizeof(float) * p.node_in.n_params);
+    L->nnodews_bytes = std::max(node_mlp_backward_ws(g, p.mlp_u), node_mlp_backward_ws(g, p.mlp_v));
+    L->off_nnodews = off; off = align256(off + L->nnodews_bytes);
+  }
   if (p.hoist) {
     NGPDE_REQUIRE(L->tce.on, "internal: hoisted plan without a tensor-core edge phase");
     off = hoist_ws(p, g->N, off, &L->hoist);
@@ -664,7 +801,7 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
     L->off_B = off;      off = align256(off + sizeof(float) * R * d.gno_out);
   }
   L->off_part_phi = off;  off = align256(off + sizeof(float) * (size_t)L->grid_e * L->part_stride);
-  L->off_part_node = off; off = align256(off + sizeof(float) * (size_t)L->grid_n * p.node.n_params);
+  L->off_part_node = off; off = align256(off + sizeof(float) * (size_t)L->grid_n * (p.nhoist ? p.node_in.n_params : p.node.n_params));
   L->total = off;
   return NGPDE_OK;
 }
@@ -812,6 +949,7 @@ using namespace ngpde;
 namespace {
 
 struct FwdPlan {
+  NodeHoistWs nhoist;
   TcPhase edge, node;
   size_t ws_bytes = 0;
   size_t off_S = 0, off_B = 0;
@@ -832,8 +970,9 @@ FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin) {
     f.edge.ws_off = off;
     off = align256(off + 4 * (size_t)f.edge.lay.block_floats);
   }
+  if (p.nhoist) off = nhoist_ws(p, N, off, &f.nhoist);
   if (p.has_node) {
-    f.node.on = tc_make_layout(p.node, 0, p.node_addend, p.dy, true, &f.node.lay, &f.node.smem, &f.node.off_cols,
+    f.node.on = tc_make_layout(p.nhoist ? p.node_in : p.node, 0, p.node_addend, p.dy, true, &f.node.lay, &f.node.smem, &f.node.off_cols,
                                &f.node.off_groups, &f.node.group_bytes);
     if (f.node.on) {
       f.node.ws_off = off;
@@ -988,7 +1127,15 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
     n.addend = p.node_addend ? io->mbar : nullptr;
     n.offA = fs.offA; n.offB = fs.offB; n.offW = fs.offW; n.offH = fs.offH;
     ProfScope prof(NGPDE_PROF_FWD_NODE, st);
-    if (fp.node.on) {
+    if (p.nhoist) {
+      NGPDE_REQUIRE(fp.node.on, "internal: hoisted node plan without a tensor-core node phase");
+      if (int rc = nhoist_forward(g, *desc, p, *io, fws, fp.nhoist, st)) return rc;
+      nhoist_args(p, reinterpret_cast<const float*>(fws + fp.nhoist.off_q), &n);
+      n.params = reinterpret_cast<const float*>(fws + fp.nhoist.off_fin);
+      n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
+      if (int rc = launch_fwd_tc(true, g->num_sms, fp.node, p.node_in, n.params, n, reinterpret_cast<float*>(fws + fp.node.ws_off), st))
+        return rc;
+    } else if (fp.node.on) {
       n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
       if (int rc = launch_fwd_tc(true, g->num_sms, fp.node, p.node, io->node_params, n, reinterpret_cast<float*>(fws + fp.node.ws_off), st))
         return rc;
@@ -1074,17 +1221,48 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     n.store_last = L.sn.store_last;
     std::memcpy(n.zoff, L.sn.zoff, sizeof(n.zoff));
     n.offG0 = L.sn.offG0; n.offG1 = L.sn.offG1; n.offW = L.sn.offW;
-    {
+    if (p.nhoist) {
+      // first layer of gamma hoisted (Plan::nhoist): inner backward on Q' gives g = d(U + V); the two projections' backward
+      // then produce exactly what this phase owes: dx_direct (from U = x Wx + b1) and dmbar (from V = mbar Wm)
       ProfScope prof(NGPDE_PROF_BWD_NODE, st);
-      if (L.tcn.on) {
-        n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
-        if (int rc = launch_bwd_tc(true, L.tcn, p.node, n, reinterpret_cast<float*>(ws + L.tcn.ws_off), st)) return rc;
-      } else {
-        if (int rc = launch_bwd_node(te, n, L.smem_n, L.grid_n, st)) return rc;
+      if (int rc = nhoist_forward(g, *desc, p, *io, ws, L.nhoist, st)) return rc;
+      float* ndq = reinterpret_cast<float*>(ws + L.off_ndq);
+      float* ng = reinterpret_cast<float*>(ws + L.off_ng);
+      float* ndfu = reinterpret_cast<float*>(ws + L.off_ndfu);
+      float* ndfv = reinterpret_cast<float*>(ws + L.off_ndfv);
+      float* ndfin = reinterpret_cast<float*>(ws + L.off_ndfin);
+      nhoist_args(p, reinterpret_cast<const float*>(ws + L.nhoist.off_q), &n);
+      n.params = reinterpret_cast<const float*>(ws + L.nhoist.off_fin);
+      n.part_stride = p.node_in.n_params;
+      n.dx_direct = ndq;   // only columns [0, n1) of a row are written: the cotangent is the same for both halves
+      n.dmbar = nullptr;
+      n.dx = 2 * p.nh_n1;
+      n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
+      if (int rc = launch_bwd_tc(true, L.tcn, p.node_in, n, reinterpret_cast<float*>(ws + L.tcn.ws_off), st)) return rc;
+      const int Pin = p.node_in.n_params;
+      reduce_partials_kernel<<<(Pin + 255) / 256, 256, 0, st>>>(part_node, L.grid_n, Pin, ndfin);
+      const size_t n4 = (size_t)g->N * 2 * (p.nh_n1 / 4);
+      hoist_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(ndq), (size_t)g->N, p.nh_n1 / 4,
+                                                                       reinterpret_cast<float4*>(ng),
+                                                                       reinterpret_cast<float4*>(ws + L.off_njunk));
+      const float* fu = reinterpret_cast<const float*>(ws + L.nhoist.off_fu);
+      const float* fv = reinterpret_cast<const float*>(ws + L.nhoist.off_fv);
+      if (int rc = node_mlp_backward(g, p.mlp_u, fu, io->x, ng, dxdirect, ndfu, ws + L.off_nnodews, L.nnodews_bytes, st)) return rc;
+      if (int rc = node_mlp_backward(g, p.mlp_v, fv, io->mbar, ng, dmbar, ndfv, ws + L.off_nnodews, L.nnodews_bytes, st)) return rc;
+      nhoist_unfold_kernel<<<32, 256, 0, st>>>(nhoist_map(*desc, p), ndfu, ndfv, ndfin, io->dnode_params);
+    } else {
+      {
+        ProfScope prof(NGPDE_PROF_BWD_NODE, st);
+        if (L.tcn.on) {
+          n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
+          if (int rc = launch_bwd_tc(true, L.tcn, p.node, n, reinterpret_cast<float*>(ws + L.tcn.ws_off), st)) return rc;
+        } else {
+          if (int rc = launch_bwd_node(te, n, L.smem_n, L.grid_n, st)) return rc;
+        }
       }
+      const int P = p.node.n_params;
+      reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_node, L.grid_n, P, io->dnode_params);
     }
-    const int P = p.node.n_params;
-    reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_node, L.grid_n, P, io->dnode_params);
   }
 
   // ---- edge phase: dmbar -> (dxdst, desrc, dphi_params) ----

@@ -161,6 +161,9 @@ bool tc_make_layout_impl(const MlpDev& m, bool contract, bool addend, int dout, 
 void tc_permute_node_segs(Seg* segs, int n_segs, TcLayout* lay) {
   lay->np = 0;
   if (n_segs <= 1 || n_segs > 8) return;
+  for (int i = 0; i < n_segs; ++i)
+    for (int j = i + 1; j < n_segs; ++j)
+      if (segs[i].row < segs[j].row + segs[j].width && segs[j].row < segs[i].row + segs[i].width) return;  // summed segments stay put
   Seg out[8];
   int n = 0, row = 0;
   for (int pass = 0; pass < 2; ++pass)

@@ -135,7 +135,10 @@ __device__ __forceinline__ void tc_build_chunks(const Args& a, TcChunk* chunks, 
   if (tid >= nchunks) return;
   TcChunk t{nullptr, 0};
   const int c = 16 * tid;
-  for (int si = 0; si < a.n_segs; ++si) {
+  int covering = 0;  // segments over these rows: more than one = a summed (hoisted) input, which takes the per-column path
+  for (int si = 0; si < a.n_segs; ++si)
+    if (a.segs[si].row < c + 16 && c < a.segs[si].row + a.segs[si].width) ++covering;
+  for (int si = 0; si < a.n_segs && covering == 1; ++si) {
     const Seg sg = a.segs[si];
     const int f = c - sg.row;
     if (sg.kind != SEG_DST || f < 0 || f + 16 > sg.width) continue;

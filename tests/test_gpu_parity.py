@@ -786,6 +786,8 @@ def test_hoisted_first_layer_against_oracle_and_unhoisted(family, aggr, dx, hidd
     r = engine.RhsRunner(layer, x, ps, st)
     paths = ngpde._lib.kernel_paths(r.handle, r.desc)
     assert paths["fwd_edge"] == 1 and paths["bwd_edge"] == 1, paths   # tcgen05 kernels on the inner problem
+    if family == "vmh" and dx + hidden > 80:   # gamma's first Dense over [x; mbar] is hoisted as well (Plan::nhoist)
+        assert paths["fwd_node"] == 1 and paths["bwd_node"] == 1, paths
     check_layer(layer, x, ps, st, g)
     rng = np.random.default_rng(9)
     y, _, _ = product_fwd_bwd(layer, x, ps, st)
