@@ -39,15 +39,15 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nc
 // dx[i][c] = dx_direct[i][c] + dxdst[i][c] + sum over out-edges of i (src-sorted, stable) of desrc[edge][c]
 __global__ void dx_combine_kernel(const float* __restrict__ dx_direct, const float* __restrict__ dxdst,
                                   const float* __restrict__ desrc, const int* __restrict__ tptr,
-                                  const int* __restrict__ tpos, int N, int dx, float* __restrict__ out) {
+                                  const int* __restrict__ tpos, int N, int dx, int src_c0, int src_w, float* __restrict__ out) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)N * dx) return;
   const int i = (int)(idx / dx), c = (int)(idx - (size_t)i * dx);
   float s = 0.f;
   if (dx_direct) s = dx_direct[idx];
   if (dxdst) s += dxdst[idx];
-  if (desrc) {
-    for (int q = tptr[i]; q < tptr[i + 1]; ++q) s += desrc[(size_t)tpos[q] * dx + c];
+  if (desrc && c >= src_c0 && c < src_c0 + src_w) {  // desrc is [E][src_w]: the x columns with a source-side use
+    for (int q = tptr[i]; q < tptr[i + 1]; ++q) s += desrc[(size_t)tpos[q] * src_w + (c - src_c0)];
   }
   out[idx] = s;
 }
@@ -621,8 +621,7 @@ size_t hoist_ws(const Plan& p, int64_t N, size_t off, HoistWs* h) {
   h->off_ft = off;  off = align256(off + sizeof(float) * p.mlp_t.n_params);
   h->off_fs = off;  off = align256(off + sizeof(float) * p.mlp_s.n_params);
   h->off_fin = off; off = align256(off + sizeof(float) * p.phi_in.n_params);
-  h->off_pt = off;  off = align256(off + sizeof(float) * (size_t)N * p.h_n1);
-  h->off_ps = off;  off = align256(off + sizeof(float) * (size_t)N * p.h_n1);
+  h->off_pt = h->off_ps = off;  // (the projections are written into Q directly)
   h->off_q = off;   off = align256(off + sizeof(float) * (size_t)N * 2 * p.h_n1);
   h->wblk_bytes = std::max(node_mlp_forward_ws(p.mlp_t), node_mlp_forward_ws(p.mlp_s));
   h->off_wblk = off; off = align256(off + h->wblk_bytes);
@@ -639,11 +638,9 @@ int hoist_forward(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p,
   float* ps = reinterpret_cast<float*>(ws + h.off_ps);
   float* q = reinterpret_cast<float*>(ws + h.off_q);
   hoist_fold_kernel<<<32, 256, 0, st>>>(io.phi_params, hoist_map(d, p), ft, fs, fin);
-  if (int rc = node_mlp_forward(g, p.mlp_t, ft, io.x, pt, st, ws + h.off_wblk, h.wblk_bytes, io.snode, p.ds)) return rc;
-  if (int rc = node_mlp_forward(g, p.mlp_s, fs, io.x, ps, st, ws + h.off_wblk, h.wblk_bytes, io.snode, p.ds)) return rc;
-  const size_t n4 = (size_t)g->N * 2 * (p.h_n1 / 4);
-  hoist_join_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(pt), reinterpret_cast<const float4*>(ps),
-                                                                  (size_t)g->N, p.h_n1 / 4, reinterpret_cast<float4*>(q));
+  (void)pt; (void)ps;  // the projections land in the two halves of Q's rows directly (strided output of the node kernel)
+  if (int rc = node_mlp_forward(g, p.mlp_t, ft, io.x, q, st, ws + h.off_wblk, h.wblk_bytes, io.snode, p.ds, 2 * p.h_n1)) return rc;
+  if (int rc = node_mlp_forward(g, p.mlp_s, fs, io.x, q + p.h_n1, st, ws + h.off_wblk, h.wblk_bytes, io.snode, p.ds, 2 * p.h_n1)) return rc;
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;
 }
@@ -655,8 +652,7 @@ size_t nhoist_ws(const Plan& p, int64_t N, size_t off, NodeHoistWs* h) {
   h->off_fu = off;  off = align256(off + sizeof(float) * p.mlp_u.n_params);
   h->off_fv = off;  off = align256(off + sizeof(float) * p.mlp_v.n_params);
   h->off_fin = off; off = align256(off + sizeof(float) * p.node_in.n_params);
-  h->off_u = off;   off = align256(off + sizeof(float) * (size_t)N * p.nh_n1);
-  h->off_v = off;   off = align256(off + sizeof(float) * (size_t)N * p.nh_n1);
+  h->off_u = h->off_v = off;
   h->off_q = off;   off = align256(off + sizeof(float) * (size_t)N * 2 * p.nh_n1);
   h->wblk_bytes = std::max(node_mlp_forward_ws(p.mlp_u), node_mlp_forward_ws(p.mlp_v));
   h->off_wblk = off; off = align256(off + h->wblk_bytes);
@@ -672,11 +668,9 @@ int nhoist_forward(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p
   float* v = reinterpret_cast<float*>(ws + h.off_v);
   float* q = reinterpret_cast<float*>(ws + h.off_q);
   nhoist_fold_kernel<<<32, 256, 0, st>>>(io.node_params, nhoist_map(d, p), fu, fv, fin);
-  if (int rc = node_mlp_forward(g, p.mlp_u, fu, io.x, u, st, ws + h.off_wblk, h.wblk_bytes)) return rc;
-  if (int rc = node_mlp_forward(g, p.mlp_v, fv, io.mbar, v, st, ws + h.off_wblk, h.wblk_bytes)) return rc;
-  const size_t n4 = (size_t)g->N * 2 * (p.nh_n1 / 4);
-  hoist_join_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(u), reinterpret_cast<const float4*>(v),
-                                                                  (size_t)g->N, p.nh_n1 / 4, reinterpret_cast<float4*>(q));
+  (void)u; (void)v;
+  if (int rc = node_mlp_forward(g, p.mlp_u, fu, io.x, q, st, ws + h.off_wblk, h.wblk_bytes, nullptr, 0, 2 * p.nh_n1)) return rc;
+  if (int rc = node_mlp_forward(g, p.mlp_v, fv, io.mbar, q + p.nh_n1, st, ws + h.off_wblk, h.wblk_bytes, nullptr, 0, 2 * p.nh_n1)) return rc;
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;
 }
@@ -755,8 +749,7 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
     NGPDE_REQUIRE(L->tcn.on, "internal: hoisted node plan without a tensor-core node phase");
     off = nhoist_ws(p, g->N, off, &L->nhoist);
     L->off_ndq = off;   off = align256(off + sizeof(float) * g->N * 2 * p.nh_n1);
-    L->off_ng = off;    off = align256(off + sizeof(float) * g->N * p.nh_n1);
-    L->off_njunk = off; off = align256(off + sizeof(float) * g->N * p.nh_n1);
+    L->off_ng = L->off_njunk = off;
     L->off_ndfu = off;  off = align256(off + sizeof(float) * p.mlp_u.n_params);
     L->off_ndfv = off;  off = align256(off + sizeof(float) * p.mlp_v.n_params);
     L->off_ndfin = off; off = align256(off + sizeof(float) * p.node_in.n_params);
@@ -767,8 +760,7 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
     NGPDE_REQUIRE(L->tce.on, "internal: hoisted plan without a tensor-core edge phase");
     off = hoist_ws(p, g->N, off, &L->hoist);
     L->off_dq = off;   off = align256(off + sizeof(float) * g->N * 2 * p.h_n1);
-    L->off_dpt = off;  off = align256(off + sizeof(float) * g->N * p.h_n1);
-    L->off_dps = off;  off = align256(off + sizeof(float) * g->N * p.h_n1);
+    L->off_dpt = L->off_dps = off;
     L->off_dxt = off;  off = align256(off + sizeof(float) * g->N * d.dx);
     L->off_dxs = off;  off = align256(off + sizeof(float) * g->N * d.dx);
     L->off_dft = off;  off = align256(off + sizeof(float) * p.mlp_t.n_params);
@@ -844,8 +836,9 @@ void node_input_segs(Args* n, const float* x, int dx, const float* snode, int ds
 }  // namespace
 
 int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, float* y,
-                     cudaStream_t st, void* workspace, size_t ws_bytes, const float* snode, int ds) {
+                     cudaStream_t st, void* workspace, size_t ws_bytes, const float* snode, int ds, int out_ld) {
   FwdArgs n{};
+  n.out_ld = out_ld;
   node_input_segs(&n, x, mlp.dims[0] - ds, snode, ds);
   n.mlp = mlp;
   n.params = params;
@@ -857,6 +850,7 @@ int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* param
     n.tg = TileGraph{nullptr, nullptr, nullptr, nullptr, nullptr, (int)((g->N + TC_TILE - 1) / TC_TILE), (int)g->N, 1};
     return launch_fwd_tc(true, g->num_sms, t, mlp, params, n, static_cast<float*>(workspace), st);
   }
+  NGPDE_REQUIRE(out_ld == 0 || out_ld == n.dout, "internal: strided node-MLP output needs the tensor-core kernel");
   int te = 0, smem = 0;
   if (int rc = pick_tile([&](int t) { return 4 * fwd_smem(mlp, 0, 0, 0, t).floats; }, &te, &smem)) return rc;
   FwdSmem fs = fwd_smem(mlp, 0, 0, 0, te);
@@ -904,7 +898,8 @@ size_t node_mlp_backward_ws(const ngpde_graph* g, const MlpDev& mlp) {
 
 // dy -> dx (may be nullptr... it is always produced here), dparams
 int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, const float* dy,
-                      float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st, const float* snode, int ds) {
+                      float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st, const float* snode, int ds,
+                      int dy_ld) {
   NodeBwdLayout L;
   if (int rc = node_bwd_layout(g, mlp, &L)) return rc;
   if (ws_bytes < L.total) {
@@ -932,9 +927,11 @@ int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* para
   n.store_last = L.s.store_last;
   std::memcpy(n.zoff, L.s.zoff, sizeof(n.zoff));
   n.offG0 = L.s.offG0; n.offG1 = L.s.offG1; n.offW = L.s.offW;
+  n.gout_ld = dy_ld;
   if (L.tc.on) {
     if (int rc = launch_bwd_tc(true, L.tc, mlp, n, reinterpret_cast<float*>(ws + L.tc.ws_off), st)) return rc;
   } else {
+    NGPDE_REQUIRE(dy_ld == 0 || dy_ld == n.dout, "internal: strided node-MLP cotangent needs the tensor-core kernel");
     if (int rc = launch_bwd_node(L.te, n, L.smem, L.grid, st)) return rc;
   }
   reduce_partials_kernel<<<(mlp.n_params + 255) / 256, 256, 0, st>>>(part, L.grid, mlp.n_params, dparams);
@@ -1241,14 +1238,12 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       if (int rc = launch_bwd_tc(true, L.tcn, p.node_in, n, reinterpret_cast<float*>(ws + L.tcn.ws_off), st)) return rc;
       const int Pin = p.node_in.n_params;
       reduce_partials_kernel<<<(Pin + 255) / 256, 256, 0, st>>>(part_node, L.grid_n, Pin, ndfin);
-      const size_t n4 = (size_t)g->N * 2 * (p.nh_n1 / 4);
-      hoist_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(ndq), (size_t)g->N, p.nh_n1 / 4,
-                                                                       reinterpret_cast<float4*>(ng),
-                                                                       reinterpret_cast<float4*>(ws + L.off_njunk));
+      (void)ng;  // the projections' backward reads the first n1 columns of dQ' in place (strided cotangent)
       const float* fu = reinterpret_cast<const float*>(ws + L.nhoist.off_fu);
       const float* fv = reinterpret_cast<const float*>(ws + L.nhoist.off_fv);
-      if (int rc = node_mlp_backward(g, p.mlp_u, fu, io->x, ng, dxdirect, ndfu, ws + L.off_nnodews, L.nnodews_bytes, st)) return rc;
-      if (int rc = node_mlp_backward(g, p.mlp_v, fv, io->mbar, ng, dmbar, ndfv, ws + L.off_nnodews, L.nnodews_bytes, st)) return rc;
+      const int ldq = 2 * p.nh_n1;
+      if (int rc = node_mlp_backward(g, p.mlp_u, fu, io->x, ndq, dxdirect, ndfu, ws + L.off_nnodews, L.nnodews_bytes, st, nullptr, 0, ldq)) return rc;
+      if (int rc = node_mlp_backward(g, p.mlp_v, fv, io->mbar, ndq, dmbar, ndfv, ws + L.off_nnodews, L.nnodews_bytes, st, nullptr, 0, ldq)) return rc;
       nhoist_unfold_kernel<<<32, 256, 0, st>>>(nhoist_map(*desc, p), ndfu, ndfv, ndfin, io->dnode_params);
     } else {
       {
@@ -1266,6 +1261,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   }
 
   // ---- edge phase: dmbar -> (dxdst, desrc, dphi_params) ----
+  int src_c0_all = 0, src_w_all = desc->dx;
   {
     BwdArgs a{};
     const int te = L.tce.on ? TC_TILE : L.te_e;
@@ -1303,6 +1299,22 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     a.dxdst = dxdst;
     a.desrc = desrc;
     a.dx = L.dxe;
+    // x columns that receive source-side cotangents (the per-edge spill covers only these on the tensor-core path)
+    int src_c0 = 0, src_w = L.dxe;
+    if (L.tce.on) {
+      int lo = L.dxe, hi = 0;
+      for (int i = 0; i < a.n_segs; ++i) {
+        const Seg& sg = a.segs[i];
+        if (sg.arr != ARR_X || sg.kind == SEG_DST || sg.kind == SEG_EDGE || sg.kind == SEG_GRAPH) continue;
+        lo = std::min(lo, sg.col);
+        hi = std::max(hi, sg.col + sg.width);
+      }
+      if (hi > lo) { src_c0 = lo; src_w = hi - lo; }
+    }
+    a.src_c0 = src_c0;
+    a.src_w = src_w;
+    src_c0_all = src_c0;
+    src_w_all = src_w;
     a.need_dz0 = (p.edge_need_dz0 || p.hoist) ? 1 : 0;
     a.store_last = L.se.store_last;
     a.has_dst_side = (p.edge_dst_side || p.hoist) ? 1 : 0;
@@ -1349,14 +1361,12 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       float* dfs = reinterpret_cast<float*>(ws + L.off_dfs);
       const size_t totq = (size_t)g->N * L.dxe;
       dx_combine_kernel<<<(unsigned)((totq + 255) / 256), 256, 0, st>>>(nullptr, dxdst, g->E > 0 ? desrc : nullptr, g->tptr, g->tpos,
-                                                                         (int)g->N, L.dxe, dq);
-      const size_t n4 = totq / 4;
-      hoist_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(dq), (size_t)g->N, p.h_n1 / 4,
-                                                                       reinterpret_cast<float4*>(dpt), reinterpret_cast<float4*>(dps));
+                                                                         (int)g->N, L.dxe, src_c0, src_w, dq);
+      (void)dpt; (void)dps;  // dPt / dPs are the two halves of dQ's rows, read in place
       const float* ft = reinterpret_cast<const float*>(ws + L.hoist.off_ft);
       const float* fs = reinterpret_cast<const float*>(ws + L.hoist.off_fs);
-      if (int rc = node_mlp_backward(g, p.mlp_t, ft, io->x, dpt, dxt, dft, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds)) return rc;
-      if (int rc = node_mlp_backward(g, p.mlp_s, fs, io->x, dps, dxs, dfs, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds)) return rc;
+      if (int rc = node_mlp_backward(g, p.mlp_t, ft, io->x, dq, dxt, dft, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds, L.dxe)) return rc;
+      if (int rc = node_mlp_backward(g, p.mlp_s, fs, io->x, dq + p.h_n1, dxs, dfs, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds, L.dxe)) return rc;
       hoist_unfold_kernel<<<32, 256, 0, st>>>(hoist_map(*desc, p), dft, dfs, dphi_target, p.phi.dims[0], io->dphi_params);
       const size_t total = (size_t)g->N * desc->dx;
       add3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dxdirect, dxt, dxs, total, io->dx);
@@ -1370,7 +1380,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     const size_t total = (size_t)g->N * desc->dx;
     const bool has_src = (p.edge_need_dz0 || p.contract) && g->E > 0;
     dx_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dxdirect, dxdst, has_src ? desrc : nullptr,
-                                                                        g->tptr, g->tpos, (int)g->N, desc->dx, io->dx);
+                                                                        g->tptr, g->tpos, (int)g->N, desc->dx, src_c0_all, src_w_all, io->dx);
   }
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;

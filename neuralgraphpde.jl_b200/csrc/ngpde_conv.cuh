@@ -50,6 +50,7 @@ struct FwdArgs {
   int aggr;
   int dout;             // rows of the result tile
   float* out;           // edge phase: mbar [N][dout]; node phase: y [N][dout]
+  int out_ld;           // node phase, tensor-core kernels: leading dimension of `out` (0: dout)
   const float* addend;  // node phase (GNO): [N][dout] added before the last activation
   int offA, offB, offW, offH;  // shared-memory float offsets
 };
@@ -78,6 +79,9 @@ struct BwdArgs {
   int need_dz0;
   int store_last;         // Z_L has to be recomputed (activation on the last layer, or max/min)
   int has_dst_side;
+  int gout_ld;            // node phase, tensor-core kernels: leading dimension of gout_ptr (0: dout)
+  int src_c0, src_w;      // tensor-core edge kernels: x columns [src_c0, src_c0 + src_w) carry source-side cotangents; desrc is
+                          // [E][src_w] (src_w == 0: all dx columns)
   int zoff[NGPDE_MAX_LAYERS + 1];
   int offG0, offG1, offW, offH, offDM, offP, offDZ, offDH, offRed;
   float* gno_S;        // contract == 2 (ngpde_gno.cuh): [N][gno_Ka * gin], rebuilt here for dB = S' DM
@@ -100,10 +104,11 @@ __device__ __forceinline__ float coef_src(int kind) {
 int make_mlp_dev(const ngpde_mlp& m, MlpDev* out, const char* what);
 size_t node_mlp_forward_ws(const MlpDev& mlp);
 int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, float* y,
-                     cudaStream_t st, void* workspace = nullptr, size_t ws_bytes = 0, const float* snode = nullptr, int ds = 0);
+                     cudaStream_t st, void* workspace = nullptr, size_t ws_bytes = 0, const float* snode = nullptr, int ds = 0,
+                     int out_ld = 0);
 size_t node_mlp_backward_ws(const ngpde_graph* g, const MlpDev& mlp);
 int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, const float* dy,
                       float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st, const float* snode = nullptr,
-                      int ds = 0);
+                      int ds = 0, int dy_ld = 0);
 
 }  // namespace ngpde

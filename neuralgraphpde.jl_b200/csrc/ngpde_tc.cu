@@ -202,6 +202,7 @@ int launch_fwd_tc_t(int num_sms, const TcPhase& t, const MlpDev& mlp, const floa
   a.aggr = base.aggr;
   a.dout = base.dout;
   a.out = base.out;
+  a.out_ld = base.out_ld > 0 ? base.out_ld : base.dout;
   a.off_cols = t.off_cols;
   a.off_groups = t.off_groups;
   a.group_bytes = t.group_bytes;
@@ -234,6 +235,9 @@ int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base,
   a.aggr = base.aggr;
   a.dout = base.dout;
   a.gout_ptr = base.gout_ptr;
+  a.gout_ld = base.gout_ld > 0 ? base.gout_ld : base.dout;
+  a.src_c0 = base.src_w > 0 ? base.src_c0 : 0;
+  a.src_w = base.src_w > 0 ? base.src_w : base.dx;
   a.dparams_partial = base.dparams_partial;
   a.dx_direct = base.dx_direct;
   a.dmbar = base.dmbar;

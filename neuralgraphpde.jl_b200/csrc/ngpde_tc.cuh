@@ -35,7 +35,8 @@ struct TcFwdArgs {
   const float* wblock;  // prepared weight block in global memory (tc_prep_weights_kernel)
   int aggr;
   int dout;
-  float* out;           // edge phase: mbar [N][dout]; node phase: y [N][dout]
+  float* out;           // edge phase: mbar [N][dout]; node phase: y [N][out_ld]
+  int out_ld;
   int off_cols;         // byte offsets into dynamic shared memory: column table, per-group regions
   int off_groups;
   int group_bytes;
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
             umma::tmem_st16(tAlo + lane_addr + c0, lo);
           } else if (NODE) {
             if (valid) {
-              float* o = out + (size_t)(k0 + row) * dout + c0;
+              float* o = out + (size_t)(k0 + row) * a.out_ld + c0;
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 if (c0 + j < dout) o[j] = f[j];

@@ -38,7 +38,9 @@ struct TcBwdArgs {
   const float* wblock;
   int aggr;
   int dout;                // width of the MLP output (= N[L-1])
-  const float* gout_ptr;   // edge: dmbar / dy [N][dout]; node: dy [N][dout]
+  const float* gout_ptr;   // edge: dmbar / dy [N][dout]; node: dy [N][gout_ld]
+  int gout_ld;
+  int src_c0, src_w;       // x columns with source-side cotangents; desrc is [E][src_w]
   float* dparams_partial;  // [gridDim.x][n_params]
   float* dx_direct;        // node phase
   float* dmbar;            // node phase
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       TCB_STAMP(0);
       // the cotangent rows are first needed after the recompute: pull their lines towards L1 now
       if (valid && c0 < lay.Np[L - 1])
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.gout_ptr + (size_t)(NODE ? (k0 + row) : d) * dout + c0));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.gout_ptr + (size_t)(NODE ? (k0 + row) : d) * a.gout_ld + c0));
       // mean: the cotangent of a message is dmbar / deg -- formed as dmbar * rn(1 / deg) (one rounding more than the true
       // division, far inside the gradient tolerance; sixteen IEEE divisions per thread cost ~1,000 cycles per tile)
       float rdeg = 1.f;
@@ -586,8 +588,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 16; ++j) g[j] = 0.f;
         if (valid && c0 < Np) {
-          const float* gp = a.gout_ptr + (size_t)(NODE ? (k0 + row) : d) * dout + c0;
-          if ((dout & 3) == 0 && c0 + 16 <= dout) {
+          const float* gp = a.gout_ptr + (size_t)(NODE ? (k0 + row) : d) * a.gout_ld + c0;
+          if ((a.gout_ld & 3) == 0 && c0 + 16 <= dout) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               const float4 t = *reinterpret_cast<const float4*>(gp + j);
@@ -835,9 +837,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       if (!NODE && a.need_dz0) {
         worker_sync();
         const int dx = a.dx, ldz = Kd0 + 1;
-        // source side: one row per edge, reduced later over the src-sorted transpose
-        for (int item = tid; item < ne * dx; item += NW) {
-          const int e = item / dx, c = item - e * dx;
+        // source side: one row per edge (the x columns that have a source-side use), reduced later over the src-sorted transpose
+        const int sw = a.src_w, sc0 = a.src_c0;
+        auto src_cot = [&](int e, int cc) {
+          const int c = sc0 + cc;
           float v = 0.f;
           for (int si = 0; si < a.n_segs; ++si) {
             const Seg sg = a.segs[si];
@@ -845,7 +848,16 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             const float cf = coef_src(sg.kind);
             if (cf != 0.f) v = fmaf(cf, DZ[e * ldz + sg.row + c - sg.col], v);
           }
-          a.desrc[(size_t)(k0 + e) * dx + c] = v;
+          a.desrc[(size_t)(k0 + e) * sw + cc] = v;
+        };
+        if (sw >= 32) {  // wide rows (hoisted first layer): a warp per edge, lanes along the row -- no division per item
+          for (int e = tid >> 5; e < ne; e += NW / 32)
+            for (int cc = tid & 31; cc < sw; cc += 32) src_cot(e, cc);
+        } else {
+          for (int item = tid; item < ne * sw; item += NW) {
+            const int e = item / sw;
+            src_cot(e, item - e * sw);
+          }
         }
         // destination side: sequential over the row's edges, carried across tiles through dxdst itself
         if (a.has_dst_side) {
