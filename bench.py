@@ -287,6 +287,42 @@ def roofline_block(workload, w, prof, K, paths, step_ms, peaks, edges_launch, no
     return out
 
 
+def ode_trajectory_c1(w, dt=0.05, nsteps=20, reps=20):
+    """Tsit5, fixed step, 20 steps = 120 right-hand sides (docs/src/tutorials/graph_node.md:53-66), forward + discrete adjoint:
+    the CUDA-graph-captured step built from the layer kernels (ode.GraphedRK) against the two persistent cluster kernels
+    (ode.PersistentRK: ngpde_edgeconv_ode_forward / _adjoint, ONE launch each)."""
+    from ngpde import ode
+    rk = ode.GraphedRK(w.layer, w.x, w.ps, w.st, dt, "tsit5")
+    prk = ode.PersistentRK(w.layer, w.x, w.ps, w.st, dt, "tsit5")
+    g = torch.ones_like(rk.u)
+    rhs = nsteps * 6
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    t_graph = timeit(lambda: (rk.solve(w.x, nsteps), rk.adjoint(g)))
+    t_pers = timeit(lambda: (prk.solve(w.x, nsteps), prk.adjoint(g)))
+    t_pers_fwd = timeit(lambda: prk.solve(w.x, nsteps))
+    uT = prk.solve(w.x, nsteps).clone()
+    uT2 = rk.solve(w.x, nsteps)
+    return {"method": "tsit5, dt 0.05, 20 steps (120 right-hand sides)", "rhs_per_trajectory": rhs,
+            "cuda_graph_step_path_us_per_rhs_fwd_adjoint": 1e3 * t_graph / rhs,
+            "persistent_kernels_us_per_rhs_fwd_adjoint": 1e3 * t_pers / rhs,
+            "persistent_kernels_us_per_rhs_fwd": 1e3 * t_pers_fwd / rhs,
+            "persistent_rhs_evals_per_sec_fwd_adjoint": rhs / (t_pers * 1e-3),
+            "launches_per_trajectory_persistent": 2,
+            "max_abs_diff_between_paths": float((uT - uT2).abs().max())}
+
+
 def strong_c4(args, rank, world, dev, peaks):
     """The north-star scaling configuration: ONE GNOConv graph of 1M nodes / ~16M radius edges, node-partitioned over
     the `world` ranks with a halo exchange per RHS, fwd + VJP per step, strong scaling; with a parity
@@ -620,6 +656,13 @@ def main():
             "sample": f"{ws.name}: {ws.n_nodes} nodes / {ws.n_edges} edges "
                       f"({'the full workload' if not sample_kw else 'reduced: ' + str(sample_kw)}), {n} fwd+bwd steps in {dt:.1f} s "
                       "(oracle: torch-CPU restatement of the unfused reference algorithm; Julia is not installed)"}
+
+    # ---- C1 is an ODE right-hand side on a graph that fits a thread-block cluster: the trajectory numbers ----
+    if args.workload == "c1" and rank == 0 and world == 1:
+        try:
+            line["ode_trajectory"] = ode_trajectory_c1(w)
+        except Exception as exc:  # noqa: BLE001
+            line["ode_trajectory"] = {"error": repr(exc)}
 
     # ---- the north-star scaling configuration rides on the default line: C4, 1M nodes, node-partitioned, with parity ----
     if args.workload == "c3" and not args.no_strong_c4:

@@ -38,6 +38,7 @@ include("graphs.jl")
 include("conv.jl")
 include("layers.jl")
 include("train.jl")
+include("ode.jl")
 include("dist.jl")
 
 # the reference's export list (src/NeuralGraphPDE.jl:27-33), unchanged
@@ -46,6 +47,7 @@ export ExplicitEdgeConv, GCNConv, VMHConv, MPPDEConv, GNOConv, SpectralConv
 export updategraph
 # what this back end adds
 export adam_step!, rprop_step!, mse_loss, logitcrossentropy_loss
+export solve_persistent, RkTableau, RK4, TSIT5
 export NodePartition, HaloExchange, partition_nodes, morton_order, halo_forward, halo_backward, allreduce_sum!
 
 end # module

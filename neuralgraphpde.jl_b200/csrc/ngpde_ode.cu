@@ -719,6 +719,12 @@ __device__ __forceinline__ void ode_layer_mma(const MlpDev& m, int l, const floa
   }
 }
 
+// Cluster barrier with release / acquire at cluster scope: what DSMEM stores need.  (cooperative_groups' cluster.sync() puts a
+// gpu-scope MEMBAR in front of it.)
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 template <int L>
 __global__ void __launch_bounds__(ODE_THREADS, 1) edgeconv_ode_fwd_mma_kernel(const __grid_constant__ OdeArgs a, const OdeMmaSmem Q) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -747,6 +753,12 @@ __global__ void __launch_bounds__(ODE_THREADS, 1) edgeconv_ode_fwd_mma_kernel(co
   for (int i = tid; i < nown; i += ODE_THREADS) {
     u0[i] = a.u[n0 * dx + i];
     a.traj[n0 * dx + i] = u0[i];
+  }
+  // stage-combination coefficients: cf[s][j] = dt a[s+1][j] (dt b[j] for the last stage), j <= s
+  __shared__ float cf[ODE_MAXS * ODE_MAXS];
+  if (tid < ODE_MAXS * ODE_MAXS) {
+    const int ss = tid / ODE_MAXS, j = tid % ODE_MAXS;
+    cf[tid] = (ss < a.S && j <= ss) ? a.dt * (ss + 1 == a.S ? a.b[j] : a.a[ss + 1][j]) : 0.f;
   }
   cluster.sync();
   int cur = 0;
@@ -794,10 +806,9 @@ __global__ void __launch_bounds__(ODE_THREADS, 1) edgeconv_ode_fwd_mma_kernel(co
         kst[(size_t)s * max_own + i] = acc;
         float nxt = u0[i];
         const bool last = s + 1 == a.S;
-        for (int j = 0; j <= s; ++j) {
-          const float cf = a.dt * (last ? a.b[j] : a.a[s + 1][j]);
-          if (cf != 0.f) nxt = fmaf(cf, kst[(size_t)j * max_own + i], nxt);
-        }
+#pragma unroll
+        for (int j = 0; j < ODE_MAXS; ++j)   // zero coefficients add exactly nothing
+          if (j <= s) nxt = fmaf(cf[s * ODE_MAXS + j], kst[(size_t)j * max_own + i], nxt);
         const int gi = n0 * dx + i;
         if (!last) {
           tr[(size_t)(s + 1) * nd + gi] = nxt;
@@ -809,7 +820,7 @@ __global__ void __launch_bounds__(ODE_THREADS, 1) edgeconv_ode_fwd_mma_kernel(co
         for (int r = 0; r < a.ncta; ++r) cluster.map_shared_rank(unext, r)[gi] = nxt;
       }
       ODE_PROF(1);
-      cluster.sync();
+      cluster_barrier();
       ODE_PROF(2);
       cur ^= 1;
     }
@@ -875,6 +886,13 @@ __global__ void __launch_bounds__(ODE_THREADS, 1) edgeconv_ode_bwd_mma_kernel(co
   {
     const int q0 = a.tptr[n0], q1 = a.tptr[n1];
     for (int q = q0 + tid; q < q1; q += ODE_THREADS) tinv[a.tpos[q]] = q;
+  }
+  // stage-cotangent coefficients: ca[sn][j] = dt a[j][sn] (j > sn), cb[sn] = dt b[sn]
+  __shared__ float ca[ODE_MAXS * ODE_MAXS], cb[ODE_MAXS];
+  if (tid < ODE_MAXS * ODE_MAXS) {
+    const int sn = tid / ODE_MAXS, j = tid % ODE_MAXS;
+    ca[tid] = (j < a.S && j > sn) ? a.dt * a.a[j][sn] : 0.f;
+    if (j == 0) cb[sn] = sn < a.S ? a.dt * a.b[sn] : 0.f;
   }
   int idx = a.n_steps * a.S - 1;
   for (int i = tid; i < nd; i += ODE_THREADS) cp_async4(ucur + i, a.traj + (size_t)idx * nd + i);
@@ -1030,7 +1048,7 @@ __global__ void __launch_bounds__(ODE_THREADS, 1) edgeconv_ode_bwd_mma_kernel(co
     }
     cp_async_wait_all();
     ODE_PROF(1);
-    cluster.sync();  // every CTA's source-side cotangents of this stage have landed; the next stage input is in place
+    cluster_barrier();  // every CTA's source-side cotangents of this stage have landed; the next stage input is in place
     ODE_PROF(3);
     // ---- owned nodes: ubar_s = destination side (CSR order) + source side (transpose order); next stage cotangent ----
     for (int i = tid; i < nown; i += ODE_THREADS) {
@@ -1048,11 +1066,10 @@ __global__ void __launch_bounds__(ODE_THREADS, 1) edgeconv_ode_bwd_mma_kernel(co
         sn = a.S - 1;
       }
       // kbar_sn = dt b_sn lam + dt sum_{j > sn} a_j,sn ubar_j   (the ubar of the step being entered: none yet when sn = S - 1)
-      float kv = a.dt * a.b[sn] * lam[i];
-      for (int j = sn + 1; j < a.S; ++j) {
-        const float cf = a.dt * a.a[j][sn];
-        if (cf != 0.f) kv = fmaf(cf, ub[(size_t)j * max_own + i], kv);
-      }
+      float kv = cb[sn] * lam[i];
+#pragma unroll
+      for (int j = 1; j < ODE_MAXS; ++j)   // zero coefficients (and stages that do not exist) add exactly nothing
+        if (j > sn && j < a.S) kv = fmaf(ca[sn * ODE_MAXS + j], ub[(size_t)j * max_own + i], kv);
       const int deg = rp[nl + 1] - rp[nl];
       if (a.aggr == NGPDE_AGGR_MEAN && deg > 0) kv = __fdiv_rn(kv, (float)deg);
       kb[i] = kv;

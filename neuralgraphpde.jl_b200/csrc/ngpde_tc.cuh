@@ -403,9 +403,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
           } else if (NODE) {
             if (valid) {
               float* o = out + (size_t)(k0 + row) * a.out_ld + c0;
+              if (c0 + 16 <= dout && (a.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < dout) o[j] = f[j];
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (c0 + j < dout) o[j] = f[j];
+              }
             }
           } else {
 #pragma unroll
