@@ -39,13 +39,14 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nc
 // dx[i][c] = dx_direct[i][c] + dxdst[i][c] + sum over out-edges of i (src-sorted, stable) of desrc[edge][c]
 __global__ void dx_combine_kernel(const float* __restrict__ dx_direct, const float* __restrict__ dxdst,
                                   const float* __restrict__ desrc, const int* __restrict__ tptr,
-                                  const int* __restrict__ tpos, int N, int dx, int src_c0, int src_w, float* __restrict__ out) {
+                                  const int* __restrict__ tpos, int N, int dx, int src_c0, int src_w, int dst_c0, int dst_w,
+                                  float* __restrict__ out) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)N * dx) return;
   const int i = (int)(idx / dx), c = (int)(idx - (size_t)i * dx);
   float s = 0.f;
   if (dx_direct) s = dx_direct[idx];
-  if (dxdst) s += dxdst[idx];
+  if (dxdst && c >= dst_c0 && c < dst_c0 + dst_w) s += dxdst[idx];  // columns outside have no destination side (never written)
   if (desrc && c >= src_c0 && c < src_c0 + src_w) {  // desrc is [E][src_w]: the x columns with a source-side use
     for (int q = tptr[i]; q < tptr[i + 1]; ++q) s += desrc[(size_t)tpos[q] * src_w + (c - src_c0)];
   }
@@ -1231,6 +1232,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       nhoist_args(p, reinterpret_cast<const float*>(ws + L.nhoist.off_q), &n);
       n.params = reinterpret_cast<const float*>(ws + L.nhoist.off_fin);
       n.part_stride = p.node_in.n_params;
+      n.skip_w0 = 1;
       n.dx_direct = ndq;   // only columns [0, n1) of a row are written: the cotangent is the same for both halves
       n.dmbar = nullptr;
       n.dx = 2 * p.nh_n1;
@@ -1261,7 +1263,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   }
 
   // ---- edge phase: dmbar -> (dxdst, desrc, dphi_params) ----
-  int src_c0_all = 0, src_w_all = desc->dx;
+  int src_c0_all = 0, src_w_all = desc->dx, dst_c0_all = 0, dst_w_all = desc->dx;
   {
     BwdArgs a{};
     const int te = L.tce.on ? TC_TILE : L.te_e;
@@ -1282,6 +1284,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       a.segs[1] = p.hsegs[1];
       a.mlp = p.phi_in;
       a.params = reinterpret_cast<const float*>(ws + L.hoist.off_fin);
+      a.skip_w0 = 1;
     }
     a.wt = wt_phi;
     a.contract = p.contract;
@@ -1300,7 +1303,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     a.desrc = desrc;
     a.dx = L.dxe;
     // x columns that receive source-side cotangents (the per-edge spill covers only these on the tensor-core path)
-    int src_c0 = 0, src_w = L.dxe;
+    int src_c0 = 0, src_w = L.dxe, dst_c0 = 0, dst_w = L.dxe;
     if (L.tce.on) {
       int lo = L.dxe, hi = 0;
       for (int i = 0; i < a.n_segs; ++i) {
@@ -1310,11 +1313,23 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
         hi = std::max(hi, sg.col + sg.width);
       }
       if (hi > lo) { src_c0 = lo; src_w = hi - lo; }
+      lo = L.dxe; hi = 0;
+      for (int i = 0; i < a.n_segs; ++i) {
+        const Seg& sg = a.segs[i];
+        if (sg.arr != ARR_X || !coef_dst_host(sg.kind)) continue;
+        lo = std::min(lo, sg.col);
+        hi = std::max(hi, sg.col + sg.width);
+      }
+      if (hi > lo) { dst_c0 = lo; dst_w = hi - lo; }
     }
+    a.dst_c0 = dst_c0;
+    a.dst_w = dst_w;
     a.src_c0 = src_c0;
     a.src_w = src_w;
     src_c0_all = src_c0;
     src_w_all = src_w;
+    dst_c0_all = dst_c0;
+    dst_w_all = dst_w;
     a.need_dz0 = (p.edge_need_dz0 || p.hoist) ? 1 : 0;
     a.store_last = L.se.store_last;
     a.has_dst_side = (p.edge_dst_side || p.hoist) ? 1 : 0;
@@ -1361,7 +1376,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       float* dfs = reinterpret_cast<float*>(ws + L.off_dfs);
       const size_t totq = (size_t)g->N * L.dxe;
       dx_combine_kernel<<<(unsigned)((totq + 255) / 256), 256, 0, st>>>(nullptr, dxdst, g->E > 0 ? desrc : nullptr, g->tptr, g->tpos,
-                                                                         (int)g->N, L.dxe, src_c0, src_w, dq);
+                                                                         (int)g->N, L.dxe, src_c0, src_w, dst_c0, dst_w, dq);
       (void)dpt; (void)dps;  // dPt / dPs are the two halves of dQ's rows, read in place
       const float* ft = reinterpret_cast<const float*>(ws + L.hoist.off_ft);
       const float* fs = reinterpret_cast<const float*>(ws + L.hoist.off_fs);
@@ -1380,7 +1395,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     const size_t total = (size_t)g->N * desc->dx;
     const bool has_src = (p.edge_need_dz0 || p.contract) && g->E > 0;
     dx_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dxdirect, dxdst, has_src ? desrc : nullptr,
-                                                                        g->tptr, g->tpos, (int)g->N, desc->dx, src_c0_all, src_w_all, io->dx);
+                                                                        g->tptr, g->tpos, (int)g->N, desc->dx, src_c0_all, src_w_all, dst_c0_all, dst_w_all, io->dx);
   }
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;

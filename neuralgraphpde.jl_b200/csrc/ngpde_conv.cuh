@@ -80,6 +80,8 @@ struct BwdArgs {
   int store_last;         // Z_L has to be recomputed (activation on the last layer, or max/min)
   int has_dst_side;
   int gout_ld;            // node phase, tensor-core kernels: leading dimension of gout_ptr (0: dout)
+  int skip_w0;            // tensor-core kernels: layer 0 is the identity of a hoisted first layer -- its weight gradient is not formed
+  int dst_c0, dst_w;      // likewise for the destination side: dxdst columns outside [dst_c0, dst_c0 + dst_w) are not written
   int src_c0, src_w;      // tensor-core edge kernels: x columns [src_c0, src_c0 + src_w) carry source-side cotangents; desrc is
                           // [E][src_w] (src_w == 0: all dx columns)
   int zoff[NGPDE_MAX_LAYERS + 1];

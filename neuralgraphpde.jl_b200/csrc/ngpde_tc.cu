@@ -236,8 +236,11 @@ int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base,
   a.dout = base.dout;
   a.gout_ptr = base.gout_ptr;
   a.gout_ld = base.gout_ld > 0 ? base.gout_ld : base.dout;
+  a.skip_w0 = base.skip_w0;
   a.src_c0 = base.src_w > 0 ? base.src_c0 : 0;
   a.src_w = base.src_w > 0 ? base.src_w : base.dx;
+  a.dst_c0 = base.dst_w > 0 ? base.dst_c0 : 0;
+  a.dst_w = base.dst_w > 0 ? base.dst_w : base.dx;
   a.dparams_partial = base.dparams_partial;
   a.dx_direct = base.dx_direct;
   a.dmbar = base.dmbar;

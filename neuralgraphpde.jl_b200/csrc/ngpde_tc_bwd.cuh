@@ -41,6 +41,8 @@ struct TcBwdArgs {
   const float* gout_ptr;   // edge: dmbar / dy [N][dout]; node: dy [N][gout_ld]
   int gout_ld;
   int src_c0, src_w;       // x columns with source-side cotangents; desrc is [E][src_w]
+  int dst_c0, dst_w;       // x columns with destination-side cotangents (the others of dxdst are not written)
+  int skip_w0;             // layer 0's weight gradient is not wanted (identity of a hoisted first layer): no staging, no MMAs
   float* dparams_partial;  // [gridDim.x][n_params]
   float* dx_direct;        // node phase
   float* dmbar;            // node phase
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   float* DZ = reinterpret_cast<float*>(smem + a.off_dz);  // edge phase: [128][Kd0 + 1]; later reused for the db exchange
   const int L = lay.L, Kd0 = lay.Kd[0];
   // edge phase: the gathered layer-0 input is parked in the (not yet used) dZ_0 tile instead of being gathered twice
-  const bool keep_z0 = !NODE && a.need_dz0 && L > 1;
+  const bool keep_z0 = !NODE && a.need_dz0 && L > 1 && !a.skip_w0;
 
   if (tid < 32) umma::tmem_alloc(&tmem_slot, a.tmem_cols);
   if (tid == 0) {
@@ -405,8 +407,8 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               ps ^= 1;
               umma::tc_fence_after();
               TCB_STAMP_ANY(34 + 4 * l);
-              tcb_issue_wgrad<ROWS>(lay, l, s_ghi, s_glo, s_zhi, s_zlo, tDwl, h);
-              umma::mma_commit(&bar_w);
+              if (!(a.skip_w0 && l == 0)) tcb_issue_wgrad<ROWS>(lay, l, s_ghi, s_glo, s_zhi, s_zlo, tDwl, h);
+              umma::mma_commit(&bar_w);  // (an empty batch completes with whatever was issued before it)
               TCB_STAMP_ANY(35 + 4 * l);
             }
           }
@@ -697,7 +699,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             mbar_wait_warp(&bar_w, ph_w, a.opt);  // the first half has been consumed
             ph_w ^= 1;
           }
-          if (FULL || (lq >> 1) == h) {
+          if ((FULL || (lq >> 1) == h) && !(a.skip_w0 && l == 0)) {
             const int r = row - ROWS * h;
             if (active) stage_chunk<ROWS>(st_ghi, st_glo, r, c0, g);
             // Z_l: the gathered input for l == 0, else the FP32 copy kept in TMEM by the recompute
@@ -850,17 +852,74 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           }
           a.desrc[(size_t)(k0 + e) * sw + cc] = v;
         };
-        if (sw >= 32) {  // wide rows (hoisted first layer): a warp per edge, lanes along the row -- no division per item
-          for (int e = tid >> 5; e < ne; e += NW / 32)
-            for (int cc = tid & 31; cc < sw; cc += 32) src_cot(e, cc);
+        // Wide rows (hoisted first layer: 64 columns per edge): the per-element walk over the segment table was the most
+        // expensive phase of the tile (11k of 37k cycles at C5).  A lane owns a column, decodes its (at most two) contributing
+        // segments ONCE, and then walks the edges: a load, one or two multiplies and a coalesced store per element.
+        auto decode = [&](int c, bool src_side, int& z0, float& f0, int& z1, float& f1) {
+          int n = 0;
+          z0 = z1 = 0;
+          f0 = f1 = 0.f;
+          for (int si = 0; si < a.n_segs; ++si) {
+            const Seg sg = a.segs[si];
+            if (sg.arr != ARR_X || c < sg.col || c >= sg.col + sg.width) continue;
+            const float cf = src_side ? coef_src(sg.kind) : coef_dst(sg.kind);
+            if (cf == 0.f) continue;
+            if (n == 0) { z0 = sg.row + c - sg.col; f0 = cf; } else { z1 = sg.row + c - sg.col; f1 = cf; }
+            ++n;
+          }
+          return n;
+        };
+        if (sw >= 32) {
+          for (int cc = tid & 31; cc < sw; cc += 32) {
+            int z0, z1;
+            float f0, f1;
+            const int n = decode(sc0 + cc, true, z0, f0, z1, f1);
+            if (n > 2) {
+              for (int e = tid >> 5; e < ne; e += NW / 32) src_cot(e, cc);
+              continue;
+            }
+            for (int e = tid >> 5; e < ne; e += NW / 32) {
+              float v = n > 0 ? fmaf(f0, DZ[e * ldz + z0], 0.f) : 0.f;
+              if (n > 1) v = fmaf(f1, DZ[e * ldz + z1], v);
+              a.desrc[(size_t)(k0 + e) * sw + cc] = v;
+            }
+          }
         } else {
           for (int item = tid; item < ne * sw; item += NW) {
             const int e = item / sw;
             src_cot(e, item - e * sw);
           }
         }
+        TCB_STAMP(28);
         // destination side: sequential over the row's edges, carried across tiles through dxdst itself
-        if (a.has_dst_side) {
+        if (a.has_dst_side && a.dst_w >= 32) {  // wide: a warp per destination row, lanes along the columns that have a destination side
+          for (int jj = tid >> 5; jj < n1 - n0; jj += NW / 32) {
+            const int j = n0 + jj;
+            const int r0 = a.tg.rowptr[j], r1 = a.tg.rowptr[j + 1];
+            const int lo = max(r0, k0), hi = min(r1, k0 + ne);
+            if (lo >= hi) continue;
+            for (int c = a.dst_c0 + (tid & 31); c < a.dst_c0 + a.dst_w; c += 32) {
+              int z0, z1;
+              float f0, f1;
+              const int n = decode(c, false, z0, f0, z1, f1);
+              float accv = (lo == r0) ? 0.f : a.dxdst[(size_t)j * dx + c];
+              if (n <= 2) {
+                if (n > 0) for (int e = lo; e < hi; ++e) accv = fmaf(f0, DZ[(e - k0) * ldz + z0], accv);
+                if (n > 1) for (int e = lo; e < hi; ++e) accv = fmaf(f1, DZ[(e - k0) * ldz + z1], accv);
+              } else {
+                for (int si = 0; si < a.n_segs; ++si) {
+                  const Seg sg = a.segs[si];
+                  if (sg.arr != ARR_X || c < sg.col || c >= sg.col + sg.width) continue;
+                  const float cf = coef_dst(sg.kind);
+                  if (cf == 0.f) continue;
+                  const float* gr = DZ + sg.row + c - sg.col;
+                  for (int e = lo; e < hi; ++e) accv = fmaf(cf, gr[(e - k0) * ldz], accv);
+                }
+              }
+              a.dxdst[(size_t)j * dx + c] = accv;
+            }
+          }
+        } else if (a.has_dst_side) {
           for (int item = tid; item < (n1 - n0) * dx; item += NW) {
             const int jj = item / dx, c = item - jj * dx;
             const int j = n0 + jj;
@@ -880,11 +939,13 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           }
         }
       }
+      TCB_STAMP(29);
       // layer 0's dW^T block: its weight-gradient batch ran under the scatter above
       mbar_wait_warp(&bar_w, ph_w, a.opt);
+      TCB_STAMP(30);
       ph_w ^= 1;
       umma::tc_fence_after();
-      collect_dw(0, tmem + a.c_dw0);
+      if (!a.skip_w0) collect_dw(0, tmem + a.c_dw0);
       umma::tc_fence_before();
       worker_sync();
       TCB_STAMP(27);

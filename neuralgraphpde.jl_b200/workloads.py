@@ -144,15 +144,15 @@ def _bytes(N, E, d_x, d_static, d_edata, d_out, n_params):
     return float(fwd), float(fwdbwd)
 
 
-def c1_edgeconv(device="cuda", side: int = 32, seed: int = 0) -> Workload:
+def c1_edgeconv(device="cuda", side: int = 32, seed: int = 0, hidden: int = 16) -> Workload:
     rng = np.random.default_rng(seed)
     s, t, pos = grid_edges(side, side, 4, rng)
     g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=side * side,
                  ndata={"x": torch.from_numpy(pos)}).to(device)
-    layer = ExplicitEdgeConv(_chain([4, 16, 16, 1], "tanh"), initialgraph=g, aggr="mean")
+    layer = ExplicitEdgeConv(_chain([4, hidden, hidden, 1], "tanh"), initialgraph=g, aggr="mean")
     ps, st = setup(rng, layer, device)
     N, E = g.num_nodes, g.num_edges
-    fe = _mlp_flops([(4, 16), (16, 16), (16, 1)])
+    fe = _mlp_flops([(4, hidden), (hidden, hidden), (hidden, 1)])
     bf, bb = _bytes(N, E, 1, 2, 0, 1, layer.parameterlength())
     return Workload("C1 ExplicitEdgeConv %dx%d grid-4 h16" % (side, side), layer, ps, st, _x(rng, 1, N, device), g, N, E,
                     float(E * fe), bf, bb, rhs_per_step=6, notes={"flops_edge_fwd": float(E * fe), "flops_node_fwd": 0.0})

@@ -76,11 +76,14 @@ def test_cuda_graph_step_and_adjoint(name, method, kw, dt, t1):
     assert torch.equal(uT, uT3) and torch.equal(g, unpad(dps3))
 
 
-@pytest.mark.parametrize("method,dt,t1,side", [("tsit5", 0.05, 1.0, 32), ("rk4", 0.05, 0.5, 17)])
-def test_persistent_kernel_integrator_and_adjoint(method, dt, t1, side):
+@pytest.mark.parametrize("method,dt,t1,side,hidden", [("tsit5", 0.05, 1.0, 32, 16),    # C1: tensor-core kernels, 16-CTA cluster
+                                                        ("rk4", 0.05, 0.5, 17, 16),     # ragged node ranges
+                                                        ("rk4", 0.05, 0.25, 9, 12),     # 81 nodes: the portable 8-CTA cluster, padded widths
+                                                        ("tsit5", 0.05, 0.25, 12, 24)])  # layers 17..32 wide: the FFMA kernels
+def test_persistent_kernel_integrator_and_adjoint(method, dt, t1, side, hidden):
     """One-launch integrator + one-launch adjoint (ode.PersistentRK, thread-block cluster) on the C1 model: trajectory and
     gradient against the float64 oracle (<= 1e-4) and against the CUDA-graph path built from the layer kernels."""
-    w = workloads.c1_edgeconv("cuda", side=side)
+    w = workloads.c1_edgeconv("cuda", side=side, hidden=hidden)
     nsteps = int(round(t1 / dt))
     prk = ode.PersistentRK(w.layer, w.x, w.ps, w.st, dt, method)
     uT = prk.solve(w.x, nsteps).clone()
