@@ -567,9 +567,11 @@ BwdSmem bwd_smem(const MlpDev& m, int contract, int gin, int gout, int aggr, boo
 
 template <class F>
 int pick_tile(F bytes_for, int* te_out, int* bytes_out) {
+  const char* cap = getenv("NGPDE_MAX_TE");  // developer switch: cap the FFMA engine's tile size (32 / 64 / 128)
+  const int tmax = cap ? (atoi(cap) <= 32 ? 0 : (atoi(cap) <= 64 ? 1 : 2)) : 2;
   for (int pass = 0; pass < 2; ++pass) {
     const int limit = pass == 0 ? kSmemTwoCtas : kSmemMax;
-    for (int t = 2; t >= 0; --t) {
+    for (int t = tmax; t >= 0; --t) {
       const int b = bytes_for(kTileSizes[t]);
       if (b <= limit) {
         *te_out = kTileSizes[t];
@@ -744,7 +746,8 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
   L->off_dmbar = off;     off = align256(off + (p.has_node ? sizeof(float) * g->N * p.dm : 0));
   L->off_dxdirect = off;  off = align256(off + (p.has_node ? sizeof(float) * g->N * d.dx : 0));
   L->off_dxdst = off;     off = align256(off + ((p.edge_dst_side || p.hoist) ? sizeof(float) * g->N * L->dxe : 0));
-  L->off_desrc = off;     off = align256(off + sizeof(float) * g->E * L->dxe);
+  // per-edge source-side cotangents: [E][dx], or [E][n1] for a hoisted first layer (only Q's source half has a source side)
+  L->off_desrc = off;     off = align256(off + sizeof(float) * g->E * (p.hoist ? p.h_n1 : d.dx));
   L->part_stride = p.hoist ? p.phi_in.n_params : p.phi.n_params;
   if (p.nhoist) {
     NGPDE_REQUIRE(L->tcn.on, "internal: hoisted node plan without a tensor-core node phase");

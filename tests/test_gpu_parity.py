@@ -764,6 +764,8 @@ def _wide_first_layer_case(family, aggr, dx, hidden, depth, seed=41, n=1200, e=1
     t[:(280 if aggr == "mean" else 130)] = 17
     s[:40] = 17           # ... that is also a busy source
     t[300:306] = n - 1
+    keep = (t != 5) & (t != 640)   # two isolated destinations (mean of nothing = 0)
+    s, t = s[keep], t[keep]
     g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"x": jl_rand(rng, 2, n)}).to(DEV)
     acts = ["tanh", "sigmoid", "elu"]
     din = 2 * dx + 2
@@ -804,3 +806,13 @@ def test_hoisted_first_layer_against_oracle_and_unhoisted(family, aggr, dx, hidd
     assert not torch.equal(y0, y1)
     errs = dict(y=relerr(y1, y0), dx=relerr(dx1, dx0), dp=relerr(dp1, dp0))
     assert all(v <= TOL for v in errs.values()), errs
+
+
+def test_hoisted_first_layer_on_an_edgeless_graph():
+    rng = np.random.default_rng(3)
+    z = torch.zeros(0, dtype=torch.int64)
+    n, dx, h = 37, 60, 32
+    g = GNNGraph(z, z.clone(), num_nodes=n, ndata={"x": jl_rand(rng, 2, n)}).to(DEV)
+    layer = VMHConv(Chain(Dense(2 * dx + 2, h, "tanh"), Dense(h, h)), Chain(Dense(dx + h, h, "tanh"), Dense(h, 3)), initialgraph=g, aggr="mean")
+    ps, st = setup(rng, layer, DEV)
+    check_layer(layer, jl_rand(rng, dx, n, DEV), ps, st, g)
