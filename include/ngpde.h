@@ -124,6 +124,11 @@ typedef struct {
   float* dx;               /* [N][dx] cotangent of x (overwritten)      */
   float* dphi_params;      /* flat, overwritten                         */
   float* dnode_params;     /* flat, overwritten                         */
+  /* optional (may be NULL; forward and backward): ngpde_conv_state_bytes(g, desc) bytes of caller-owned device memory,
+   * 16-byte aligned, in which the forward leaves what the backward would otherwise recompute (the hoisted first-layer
+   * projections).  The backward may be given it only after the matching forward call -- same graph,
+   * descriptor, x, parameters and static data -- and before anything else writes to it. */
+  void* state;
 } ngpde_conv_io;
 
 typedef struct ngpde_graph* ngpde_graph_t;
@@ -163,6 +168,8 @@ int ngpde_aggregate(ngpde_graph_t g, int32_t aggr, const float* x, int32_t d, co
  * ngpde_conv_workspace_bytes(g, desc, backward) bytes, 256-byte aligned (forward: prepared weight images of the
  * tensor-core path; backward: transposed weights, per-edge source gradients, per-CTA parameter-gradient partials). ---- */
 size_t ngpde_conv_workspace_bytes(ngpde_graph_t g, const ngpde_conv_desc* desc, int32_t backward);
+/* bytes of the optional ngpde_conv_io.state buffer (0: this descriptor keeps nothing between forward and backward) */
+size_t ngpde_conv_state_bytes(ngpde_graph_t g, const ngpde_conv_desc* desc);
 int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_conv_io* io, void* workspace,
                        size_t workspace_bytes, void* stream);
 int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc, const ngpde_conv_io* io, void* workspace,

@@ -71,6 +71,7 @@ struct ConvIO
     dx::CuPtr{Float32}
     dphi_params::CuPtr{Float32}
     dnode_params::CuPtr{Float32}
+    state::CuPtr{Cvoid}       # optional forward -> backward state (ngpde_conv_state_bytes); CU_NULL: the backward recomputes
 end
 
 struct GcnDesc

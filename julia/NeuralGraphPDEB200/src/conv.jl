@@ -20,7 +20,7 @@ function fused_conv(h::GraphHandle, desc::ConvDesc, x::CuMatrix{Float32}, snode,
     nb == 0 && check(-1)
     ws = workspace(nb)
     io = ConvIO(pointer(x), ptr(snode), ptr(edata), ptr(theta), pointer(phi), ptr(node), pointer(mbar), pointer(y),
-                CU_NULL, CU_NULL, CU_NULL, CU_NULL)
+                CU_NULL, CU_NULL, CU_NULL, CU_NULL, CU_NULL)
     GC.@preserve h x snode edata theta phi node mbar y ws conv_forward!(h.ptr, desc, io, ws)
     return y, mbar
 end
@@ -38,7 +38,7 @@ function ChainRulesCore.rrule(::typeof(fused_conv), h::GraphHandle, desc::ConvDe
         nb == 0 && check(-1)
         ws = workspace(nb)
         io = ConvIO(pointer(x), ptr(snode), ptr(edata), ptr(theta), pointer(phi), ptr(node), pointer(mbar), pointer(y),
-                    pointer(dyv), pointer(dx), pointer(dphi), ptr(dnode))
+                    pointer(dyv), pointer(dx), pointer(dphi), ptr(dnode), CU_NULL)
         GC.@preserve h x snode edata theta phi node mbar y dyv dx dphi dnode ws conv_backward!(h.ptr, desc, io, ws)
         # tangents for (x, phi, node); the graph, the static data and theta carry none (the reference wraps theta in
         # `@ignore_derivatives`, src/layers.jl:397, and `ndata` never enters `ps`)

@@ -35,7 +35,7 @@ EXPORTS = [
     "ngpde_halo_destroy", "ngpde_halo_forward", "ngpde_halo_backward", "ngpde_allreduce_sum", "ngpde_adam_step",
     "ngpde_rprop_step", "ngpde_loss_workspace_bytes", "ngpde_mse_loss", "ngpde_logit_cross_entropy",
     "ngpde_cuda_graph_kernel_nodes", "ngpde_peer_allreduce_sum", "ngpde_edgeconv_ode_workspace_bytes",
-    "ngpde_edgeconv_ode_forward", "ngpde_edgeconv_ode_adjoint",
+    "ngpde_edgeconv_ode_forward", "ngpde_edgeconv_ode_adjoint", "ngpde_conv_state_bytes",
 ]
 PA = {"bounds": 0, "halo_global": 1, "recv_counts": 2, "send_counts": 3, "send_local": 4, "s_local": 5, "t_local": 6,
       "edge_ids": 7, "seg_rows": 8, "seg_ptr": 9, "seg_pos": 10, "peer_recv_offset": 11}
@@ -56,7 +56,8 @@ class ConvDesc(C.Structure):
 class ConvIO(C.Structure):
     _fields_ = [("x", C.c_void_p), ("snode", C.c_void_p), ("edata", C.c_void_p), ("theta", C.c_void_p),
                 ("phi_params", C.c_void_p), ("node_params", C.c_void_p), ("mbar", C.c_void_p), ("y", C.c_void_p),
-                ("dy", C.c_void_p), ("dx", C.c_void_p), ("dphi_params", C.c_void_p), ("dnode_params", C.c_void_p)]
+                ("dy", C.c_void_p), ("dx", C.c_void_p), ("dphi_params", C.c_void_p), ("dnode_params", C.c_void_p),
+                ("state", C.c_void_p)]
 
 
 class GcnDesc(C.Structure):
@@ -98,6 +99,8 @@ def load() -> C.CDLL:
     lib.ngpde_aggregate.argtypes = [vp, i32, vp, i32, vp, vp, vp]
     lib.ngpde_conv_workspace_bytes.argtypes = [vp, C.POINTER(ConvDesc), i32]
     lib.ngpde_conv_workspace_bytes.restype = sz
+    lib.ngpde_conv_state_bytes.argtypes = [vp, C.POINTER(ConvDesc)]
+    lib.ngpde_conv_state_bytes.restype = sz
     conv_sig = [vp, C.POINTER(ConvDesc), C.POINTER(ConvIO), vp, sz, vp]
     for name in ("conv", "explicit_edge_conv", "vmh_conv", "mppde_conv", "gno_conv"):
         getattr(lib, f"ngpde_{name}_forward").argtypes = conv_sig

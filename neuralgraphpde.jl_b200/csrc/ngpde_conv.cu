@@ -957,6 +957,21 @@ struct FwdPlan {
   HoistWs hoist;
 };
 
+// layout of the optional ngpde_conv_io.state buffer: the hoisted projections and folded parameters, kept for the backward
+struct StatePlan {
+  HoistWs hoist;
+  NodeHoistWs nhoist;
+  size_t bytes = 0;
+};
+StatePlan state_plan(const Plan& p, int64_t N) {
+  StatePlan sp;
+  size_t off = 0;
+  if (p.hoist) off = hoist_ws(p, N, off, &sp.hoist);
+  if (p.nhoist) off = nhoist_ws(p, N, off, &sp.nhoist);
+  sp.bytes = off;
+  return sp;
+}
+
 FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin) {
   FwdPlan f;
   size_t off = 0;
@@ -1012,6 +1027,14 @@ extern "C" size_t ngpde_conv_workspace_bytes(ngpde_graph_t g, const ngpde_conv_d
   return L.total + 256;
 }
 
+extern "C" size_t ngpde_conv_state_bytes(ngpde_graph_t g, const ngpde_conv_desc* desc) {
+  if (!g || !desc) return 0;
+  Plan p;
+  if (make_plan(g, *desc, &p)) return 0;
+  const size_t b = state_plan(p, g->N).bytes;
+  return b ? b + 256 : 0;
+}
+
 extern "C" int ngpde_conv_kernel_paths(ngpde_graph_t g, const ngpde_conv_desc* desc, int32_t* paths) {
   NGPDE_REQUIRE(g && desc && paths, "null argument");
   Plan p;
@@ -1041,6 +1064,13 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
     return NGPDE_ERR_WORKSPACE;
   }
   char* fws = static_cast<char*>(workspace);
+  // the hoisted projections live in io->state when the caller provides it (the backward then reuses them), else in the workspace
+  const StatePlan sp = state_plan(p, g->N);
+  const bool keep = io->state != nullptr && sp.bytes > 0;
+  NGPDE_REQUIRE(!keep || aligned16(io->state), "io.state must be 16-byte aligned");
+  char* hbase = keep ? static_cast<char*>(io->state) : fws;
+  const HoistWs& hw = keep ? sp.hoist : fp.hoist;
+  const NodeHoistWs& nhw = keep ? sp.nhoist : fp.nhoist;
 
   // ---- edge phase ----
   int te = 0, smem = 0;
@@ -1072,14 +1102,14 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
     if (p.hoist) {
       // first layer hoisted to the nodes; the edge kernel runs the inner problem on Q (Plan::hoist)
       NGPDE_REQUIRE(fp.edge.on, "internal: hoisted plan without a tensor-core edge phase");
-      if (int rc = hoist_forward(g, *desc, p, *io, fws, fp.hoist, st)) return rc;
-      a.arr[ARR_X] = reinterpret_cast<const float*>(fws + fp.hoist.off_q);
+      if (int rc = hoist_forward(g, *desc, p, *io, hbase, hw, st)) return rc;
+      a.arr[ARR_X] = reinterpret_cast<const float*>(hbase + hw.off_q);
       a.ld[ARR_X] = 2 * p.h_n1;
       a.n_segs = 2;
       a.segs[0] = p.hsegs[0];
       a.segs[1] = p.hsegs[1];
       a.mlp = p.phi_in;
-      a.params = reinterpret_cast<const float*>(fws + fp.hoist.off_fin);
+      a.params = reinterpret_cast<const float*>(hbase + hw.off_fin);
       a.tg.unit_ptr = g->units[2];
       a.tg.n_units = g->n_units[2];
       if (int rc = launch_fwd_tc(false, g->num_sms, fp.edge, p.phi_in, a.params, a, reinterpret_cast<float*>(fws + fp.edge.ws_off), st))
@@ -1130,9 +1160,9 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
     ProfScope prof(NGPDE_PROF_FWD_NODE, st);
     if (p.nhoist) {
       NGPDE_REQUIRE(fp.node.on, "internal: hoisted node plan without a tensor-core node phase");
-      if (int rc = nhoist_forward(g, *desc, p, *io, fws, fp.nhoist, st)) return rc;
-      nhoist_args(p, reinterpret_cast<const float*>(fws + fp.nhoist.off_q), &n);
-      n.params = reinterpret_cast<const float*>(fws + fp.nhoist.off_fin);
+      if (int rc = nhoist_forward(g, *desc, p, *io, hbase, nhw, st)) return rc;
+      nhoist_args(p, reinterpret_cast<const float*>(hbase + nhw.off_q), &n);
+      n.params = reinterpret_cast<const float*>(hbase + nhw.off_fin);
       n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
       if (int rc = launch_fwd_tc(true, g->num_sms, fp.node, p.node_in, n.params, n, reinterpret_cast<float*>(fws + fp.node.ws_off), st))
         return rc;
@@ -1168,6 +1198,13 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   if (g->N == 0) return NGPDE_OK;
   char* ws = static_cast<char*>(workspace);
   NGPDE_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
+  // hoisted projections: left in io->state by the forward, or recomputed here
+  const StatePlan sp = state_plan(p, g->N);
+  const bool kept = io->state != nullptr && sp.bytes > 0;
+  NGPDE_REQUIRE(!kept || aligned16(io->state), "io.state must be 16-byte aligned");
+  char* hbase = kept ? static_cast<char*>(io->state) : ws;
+  const HoistWs& hw = kept ? sp.hoist : L.hoist;
+  const NodeHoistWs& nhw = kept ? sp.nhoist : L.nhoist;
   float* wt_phi = reinterpret_cast<float*>(ws + L.off_wt_phi);
   float* wt_node = reinterpret_cast<float*>(ws + L.off_wt_node);
   float* dmbar = p.has_node ? reinterpret_cast<float*>(ws + L.off_dmbar) : nullptr;
@@ -1226,14 +1263,16 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       // first layer of gamma hoisted (Plan::nhoist): inner backward on Q' gives g = d(U + V); the two projections' backward
       // then produce exactly what this phase owes: dx_direct (from U = x Wx + b1) and dmbar (from V = mbar Wm)
       ProfScope prof(NGPDE_PROF_BWD_NODE, st);
-      if (int rc = nhoist_forward(g, *desc, p, *io, ws, L.nhoist, st)) return rc;
+      if (!kept) {
+        if (int rc = nhoist_forward(g, *desc, p, *io, ws, L.nhoist, st)) return rc;
+      }
       float* ndq = reinterpret_cast<float*>(ws + L.off_ndq);
       float* ng = reinterpret_cast<float*>(ws + L.off_ng);
       float* ndfu = reinterpret_cast<float*>(ws + L.off_ndfu);
       float* ndfv = reinterpret_cast<float*>(ws + L.off_ndfv);
       float* ndfin = reinterpret_cast<float*>(ws + L.off_ndfin);
-      nhoist_args(p, reinterpret_cast<const float*>(ws + L.nhoist.off_q), &n);
-      n.params = reinterpret_cast<const float*>(ws + L.nhoist.off_fin);
+      nhoist_args(p, reinterpret_cast<const float*>(hbase + nhw.off_q), &n);
+      n.params = reinterpret_cast<const float*>(hbase + nhw.off_fin);
       n.part_stride = p.node_in.n_params;
       n.skip_w0 = 1;
       n.dx_direct = ndq;   // only columns [0, n1) of a row are written: the cotangent is the same for both halves
@@ -1244,8 +1283,8 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       const int Pin = p.node_in.n_params;
       reduce_partials_kernel<<<(Pin + 255) / 256, 256, 0, st>>>(part_node, L.grid_n, Pin, ndfin);
       (void)ng;  // the projections' backward reads the first n1 columns of dQ' in place (strided cotangent)
-      const float* fu = reinterpret_cast<const float*>(ws + L.nhoist.off_fu);
-      const float* fv = reinterpret_cast<const float*>(ws + L.nhoist.off_fv);
+      const float* fu = reinterpret_cast<const float*>(hbase + nhw.off_fu);
+      const float* fv = reinterpret_cast<const float*>(hbase + nhw.off_fv);
       const int ldq = 2 * p.nh_n1;
       if (int rc = node_mlp_backward(g, p.mlp_u, fu, io->x, ndq, dxdirect, ndfu, ws + L.off_nnodews, L.nnodews_bytes, st, nullptr, 0, ldq)) return rc;
       if (int rc = node_mlp_backward(g, p.mlp_v, fv, io->mbar, ndq, dmbar, ndfv, ws + L.off_nnodews, L.nnodews_bytes, st, nullptr, 0, ldq)) return rc;
@@ -1279,14 +1318,16 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     a.mlp = p.phi;
     a.params = io->phi_params;
     if (p.hoist) {  // the inner problem on Q (Plan::hoist); its forward part is recomputed here
-      if (int rc = hoist_forward(g, *desc, p, *io, ws, L.hoist, st)) return rc;
-      a.arr[ARR_X] = reinterpret_cast<const float*>(ws + L.hoist.off_q);
+      if (!kept) {
+        if (int rc = hoist_forward(g, *desc, p, *io, ws, L.hoist, st)) return rc;
+      }
+      a.arr[ARR_X] = reinterpret_cast<const float*>(hbase + hw.off_q);
       a.ld[ARR_X] = 2 * p.h_n1;
       a.n_segs = 2;
       a.segs[0] = p.hsegs[0];
       a.segs[1] = p.hsegs[1];
       a.mlp = p.phi_in;
-      a.params = reinterpret_cast<const float*>(ws + L.hoist.off_fin);
+      a.params = reinterpret_cast<const float*>(hbase + hw.off_fin);
       a.skip_w0 = 1;
     }
     a.wt = wt_phi;
@@ -1381,8 +1422,8 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       dx_combine_kernel<<<(unsigned)((totq + 255) / 256), 256, 0, st>>>(nullptr, dxdst, g->E > 0 ? desrc : nullptr, g->tptr, g->tpos,
                                                                          (int)g->N, L.dxe, src_c0, src_w, dst_c0, dst_w, dq);
       (void)dpt; (void)dps;  // dPt / dPs are the two halves of dQ's rows, read in place
-      const float* ft = reinterpret_cast<const float*>(ws + L.hoist.off_ft);
-      const float* fs = reinterpret_cast<const float*>(ws + L.hoist.off_fs);
+      const float* ft = reinterpret_cast<const float*>(hbase + hw.off_ft);
+      const float* fs = reinterpret_cast<const float*>(hbase + hw.off_fs);
       if (int rc = node_mlp_backward(g, p.mlp_t, ft, io->x, dq, dxt, dft, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds, L.dxe)) return rc;
       if (int rc = node_mlp_backward(g, p.mlp_s, fs, io->x, dq + p.h_n1, dxs, dfs, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds, L.dxe)) return rc;
       hoist_unfold_kernel<<<32, 256, 0, st>>>(hoist_map(*desc, p), dft, dfs, dphi_target, p.phi.dims[0], io->dphi_params);

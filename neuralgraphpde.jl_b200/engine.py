@@ -65,10 +65,15 @@ class RhsRunner:
         else:
             self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
             self.ws_fwd = torch.empty(int(nbytes_f), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            nstate = self.lib.ngpde_conv_state_bytes(self.handle, C.byref(self.desc))
+        # forward -> backward state (hoisted first-layer projections): private to this runner, like mbar
+        self.state = torch.empty(int(nstate), dtype=torch.uint8, device=dev) if nstate else None
         p = ops._ptr
         self.io = _lib.ConvIO(x=p(self.x), snode=p(self.snode), edata=p(self.edata), theta=p(self.theta),
                               phi_params=p(self.phi), node_params=p(self.node), mbar=p(self.mbar), y=p(self.y),
-                              dy=p(self.dy), dx=p(self.dx), dphi_params=p(self.dphi), dnode_params=p(self.dnode))
+                              dy=p(self.dy), dx=p(self.dx), dphi_params=p(self.dphi), dnode_params=p(self.dnode),
+                              state=p(self.state))
         fam = ops._FAMILY_FN[self.desc.family]
         self._fwd = getattr(self.lib, f"ngpde_{fam}_forward")
         self._bwd = getattr(self.lib, f"ngpde_{fam}_backward")

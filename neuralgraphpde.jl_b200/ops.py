@@ -69,8 +69,13 @@ class ConvFunction(torch.autograd.Function):
         has_node = desc.node.n_layers > 0
         mbar = torch.empty((N, dm), dtype=torch.float32, device=dev)
         y = torch.empty((N, dy), dtype=torch.float32, device=dev) if has_node else mbar
+        with torch.cuda.device(dev):
+            nstate = lib.ngpde_conv_state_bytes(handle, C.byref(desc))
+        # what the backward would otherwise recompute (hoisted first-layer projections): kept alive with the autograd node
+        state = torch.empty(int(nstate), dtype=torch.uint8, device=dev) if nstate else None
         io = _lib.ConvIO(x=_ptr(x), snode=_ptr(snode), edata=_ptr(edata), theta=_ptr(theta),
-                         phi_params=_ptr(phi_params), node_params=_ptr(node_params), mbar=_ptr(mbar), y=_ptr(y))
+                         phi_params=_ptr(phi_params), node_params=_ptr(node_params), mbar=_ptr(mbar), y=_ptr(y),
+                         state=_ptr(state))
         with torch.cuda.device(dev):
             nbytes = lib.ngpde_conv_workspace_bytes(handle, C.byref(desc), 0)
             if nbytes == 0:
@@ -82,6 +87,7 @@ class ConvFunction(torch.autograd.Function):
         ctx.save_for_backward(x, phi_params, node_params if node_params is not None else x.new_empty(0), mbar)
         ctx.handle, ctx.desc = handle, desc
         ctx.static = (snode, edata, theta)
+        ctx.state = state
         ctx.has_node = has_node
         return y
 
@@ -104,7 +110,7 @@ class ConvFunction(torch.autograd.Function):
             io = _lib.ConvIO(x=_ptr(x), snode=_ptr(snode), edata=_ptr(edata), theta=_ptr(theta),
                              phi_params=_ptr(phi_params), node_params=_ptr(node_params) if ctx.has_node else None,
                              mbar=_ptr(mbar), y=None if not ctx.has_node else _ptr(mbar), dy=_ptr(gy), dx=_ptr(dx),
-                             dphi_params=_ptr(dphi), dnode_params=_ptr(dnode))
+                             dphi_params=_ptr(dphi), dnode_params=_ptr(dnode), state=_ptr(ctx.state))
             fn = getattr(lib, f"ngpde_{_FAMILY_FN[desc.family]}_backward")
             _lib.check(fn(handle, C.byref(desc), C.byref(io), ws.data_ptr(), ws.numel(), _stream(dev)))
         LAUNCHES["count"] += (8 if ctx.has_node else 5) + (4 if _factored(lib, handle, desc) else 0)

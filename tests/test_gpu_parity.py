@@ -806,6 +806,18 @@ def test_hoisted_first_layer_against_oracle_and_unhoisted(family, aggr, dx, hidd
     assert not torch.equal(y0, y1)
     errs = dict(y=relerr(y1, y0), dx=relerr(dx1, dx0), dp=relerr(dp1, dp0))
     assert all(v <= TOL for v in errs.values()), errs
+    # the optional forward -> backward state buffer (ngpde_conv_io.state) only saves the recomputation: same bits without it
+    # (what a binder that passes NULL, e.g. the Julia package, gets)
+    assert r.state is not None
+    r.dy.copy_(dy.T)
+    r.forward(); r.backward()
+    torch.cuda.synchronize()
+    kept = (r.y.clone(), r.dx.clone(), r.dparams.clone())
+    r.io.state = None
+    r.forward(); r.backward()
+    torch.cuda.synchronize()
+    assert torch.equal(kept[0], r.y) and torch.equal(kept[1], r.dx) and torch.equal(kept[2], r.dparams)
+    assert torch.equal(kept[0].T, y1) and torch.equal(kept[1].T, dx1)
 
 
 def test_hoisted_first_layer_on_an_edgeless_graph():

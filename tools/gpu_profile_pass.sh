@@ -20,5 +20,12 @@ for wl in c5 c2 c1; do
   timeout 200 python bench.py --workload $wl --no-cpu-baseline > $out/${tag}_bench_${wl}.json 2>/dev/null
   python tools/show_bench.py $out/${tag}_bench_${wl}.json
 done
+timeout 200 python tools/ode_bench.py > $out/${tag}_ode_bench.log 2>&1
+tail -4 $out/${tag}_ode_bench.log
+timeout 200 python tools/tcb_phases_c5.py > $out/${tag}_phases_c5.log 2>&1
+timeout 300 ncu --set full --clock-control none -k regex:'edgeconv_ode' -c 2 -f -o $out/${tag}_ode_full \
+    python tools/ode_bench.py > /dev/null 2> $out/${tag}_ncu_ode.err
+timeout 400 ncu --set full --clock-control none -k regex:'mp_(fwd|bwd)_tc_kernel' -s 16 -c 8 -f -o $out/${tag}_c5_full \
+    python bench.py --workload c5 --graphs 64 --steps 2 --warmup 2 --no-cpu-baseline > /dev/null 2> $out/${tag}_ncu_c5.err
 sha256sum neuralgraphpde.jl_b200/libngpde.so > $out/${tag}_lib.sha256
 ls -la $out/${tag}_*
