@@ -1110,6 +1110,7 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
       a.segs[1] = p.hsegs[1];
       a.mlp = p.phi_in;
       a.params = reinterpret_cast<const float*>(hbase + hw.off_fin);
+      a.skip_l0 = 1;
       a.tg.unit_ptr = g->units[2];
       a.tg.n_units = g->n_units[2];
       if (int rc = launch_fwd_tc(false, g->num_sms, fp.edge, p.phi_in, a.params, a, reinterpret_cast<float*>(fws + fp.edge.ws_off), st))
@@ -1163,6 +1164,7 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
       if (int rc = nhoist_forward(g, *desc, p, *io, hbase, nhw, st)) return rc;
       nhoist_args(p, reinterpret_cast<const float*>(hbase + nhw.off_q), &n);
       n.params = reinterpret_cast<const float*>(hbase + nhw.off_fin);
+      n.skip_l0 = 1;
       n.tg.n_units = (int)((g->N + TC_TILE - 1) / TC_TILE);
       if (int rc = launch_fwd_tc(true, g->num_sms, fp.node, p.node_in, n.params, n, reinterpret_cast<float*>(fws + fp.node.ws_off), st))
         return rc;
@@ -1368,6 +1370,9 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     }
     a.dst_c0 = dst_c0;
     a.dst_w = dst_w;
+    // hoisted input: x' columns [n1, 2 n1) <- input rows [0, n1) through ONE source-kind segment, so an edge's desrc row is its
+    // dZ_0 row (needs 16-byte aligned rows: n1 % 4 == 0, which hoisting requires anyway)
+    a.direct_src = (p.hoist && L.tce.on && src_w == p.h_n1 && src_c0 == p.h_n1 && (p.h_n1 & 15) == 0) ? 1 : 0;
     a.src_c0 = src_c0;
     a.src_w = src_w;
     src_c0_all = src_c0;

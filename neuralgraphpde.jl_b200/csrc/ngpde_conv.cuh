@@ -51,6 +51,8 @@ struct FwdArgs {
   int dout;             // rows of the result tile
   float* out;           // edge phase: mbar [N][dout]; node phase: y [N][dout]
   int out_ld;           // node phase, tensor-core kernels: leading dimension of `out` (0: dout)
+  int skip_l0;          // tensor-core kernels: layer 0 is the identity of a hoisted first layer -- its activation is applied to the
+                        // gathered input directly, no MMAs
   const float* addend;  // node phase (GNO): [N][dout] added before the last activation
   int offA, offB, offW, offH;  // shared-memory float offsets
 };
@@ -80,6 +82,8 @@ struct BwdArgs {
   int store_last;         // Z_L has to be recomputed (activation on the last layer, or max/min)
   int has_dst_side;
   int gout_ld;            // node phase, tensor-core kernels: leading dimension of gout_ptr (0: dout)
+  int direct_src;         // tensor-core edge kernel, hoisted input: the source-side cotangent row of an edge IS its dZ_0 row (one SRC
+                          // segment over all input rows): written from registers, no pass over the shared-memory tile
   int skip_w0;            // tensor-core kernels: layer 0 is the identity of a hoisted first layer -- its weight gradient is not formed
   int dst_c0, dst_w;      // likewise for the destination side: dxdst columns outside [dst_c0, dst_c0 + dst_w) are not written
   int src_c0, src_w;      // tensor-core edge kernels: x columns [src_c0, src_c0 + src_w) carry source-side cotangents; desrc is

@@ -203,6 +203,7 @@ int launch_fwd_tc_t(int num_sms, const TcPhase& t, const MlpDev& mlp, const floa
   a.dout = base.dout;
   a.out = base.out;
   a.out_ld = base.out_ld > 0 ? base.out_ld : base.dout;
+  a.skip_l0 = base.skip_l0;
   a.off_cols = t.off_cols;
   a.off_groups = t.off_groups;
   a.group_bytes = t.group_bytes;
@@ -237,6 +238,7 @@ int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base,
   a.gout_ptr = base.gout_ptr;
   a.gout_ld = base.gout_ld > 0 ? base.gout_ld : base.dout;
   a.skip_w0 = base.skip_w0;
+  a.direct_src = base.direct_src;
   a.src_c0 = base.src_w > 0 ? base.src_c0 : 0;
   a.src_w = base.src_w > 0 ? base.src_w : base.dx;
   a.dst_c0 = base.dst_w > 0 ? base.dst_c0 : 0;

@@ -37,6 +37,7 @@ struct TcFwdArgs {
   int dout;
   float* out;           // edge phase: mbar [N][dout]; node phase: y [N][out_ld]
   int out_ld;
+  int skip_l0;          // layer 0 = identity (hoisted first layer): activation at the gather, the layer loop starts at 1
   int off_cols;         // byte offsets into dynamic shared memory: column table, per-group regions
   int off_groups;
   int group_bytes;
@@ -219,6 +220,33 @@ __device__ __forceinline__ void tc_act16(int act, float (&f)[16]) {
   }
 }
 
+// the same for the 8-value chunks of the gather (hoisted first layer: the activation is applied to the gathered input)
+__device__ __forceinline__ void tc_act8(int act, float (&f)[8]) {
+  switch (act) {
+    case NGPDE_ACT_IDENTITY: break;
+    case NGPDE_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      break;
+    case NGPDE_ACT_TANH:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = tc_tanh(f[j]);
+      break;
+    case NGPDE_ACT_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __fdividef(1.f, 1.f + expf(-f[j]));
+      break;
+    case NGPDE_ACT_SWISH:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.f + expf(-f[j]));
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = tc_act_slow(act, f[j]);
+      break;
+  }
+}
+
 __device__ __forceinline__ void tc_split16(const float (&f)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -298,6 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
   const uint32_t wblk_smem = umma::smem_u32(wblk);
   uint32_t phase = 0;
   const int L = lay.L, Kd0 = lay.Kd[0], gdiv = a.tg.gdiv;
+  const bool skip0 = a.skip_l0 && L > 1 && lay.Np[0] == Kd0;
   const float ident = aggr == NGPDE_AGGR_MAX ? -INFINITY : (aggr == NGPDE_AGGR_MIN ? INFINITY : 0.f);
 
   for (int unit = blockIdx.x * TC_GROUPS + grp; unit < a.tg.n_units; unit += gridDim.x * TC_GROUPS) {
@@ -354,6 +383,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
             for (int j = 0; j < 8; ++j) vv[j] = valid ? tc_gather_col(cols[c0 + j], s, d, p, pg) : 0.f;
           }
         }
+        if (skip0) tc_act8(a.act[0], vv);  // identity first layer: these ARE layer 1's input columns
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float v = vv[j];
@@ -369,7 +399,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
       umma::tc_fence_before();
       group_bar(grp);
 
-      for (int l = 0; l < L; ++l) {
+      for (int l = skip0 ? 1 : 0; l < L; ++l) {
         if (gwarp == 0) {
           // one elected lane issues the MMAs (elect.sync keeps the operands in uniform registers: no R2UR waterfall per
           // MMA) and waits for their completion; everybody else parks on barriers (a spinning try_wait loop in 255

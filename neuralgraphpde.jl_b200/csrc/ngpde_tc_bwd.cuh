@@ -42,6 +42,7 @@ struct TcBwdArgs {
   int gout_ld;
   int src_c0, src_w;       // x columns with source-side cotangents; desrc is [E][src_w]
   int dst_c0, dst_w;       // x columns with destination-side cotangents (the others of dxdst are not written)
+  int direct_src;          // source-side cotangent row = dZ_0 row (hoisted input): stored from registers
   int skip_w0;             // layer 0's weight gradient is not wanted (identity of a hoisted first layer): no staging, no MMAs
   float* dparams_partial;  // [gridDim.x][n_params]
   float* dx_direct;        // node phase
@@ -269,6 +270,11 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   const int L = lay.L, Kd0 = lay.Kd[0];
   // edge phase: the gathered layer-0 input is parked in the (not yet used) dZ_0 tile instead of being gathered twice
   const bool keep_z0 = !NODE && a.need_dz0 && L > 1 && !a.skip_w0;
+  // layer 0 is the identity of a hoisted first layer (skip_w0) and a thread's 16-column chunk of G_0 is its chunk of dZ_0:
+  // dZ_0 = G_0 needs no input-gradient MMAs at all
+  const bool id0 = a.skip_w0 && L > 1 && Kd0 <= 64 && lay.Np[0] == Kd0;
+  // ... and no recompute MMAs either: Z_1 = act_0(gathered input), when the columns a thread gathers are its own chunk
+  const bool id0r = id0 && (NODE || (Kd0 >> 2) == 16);
 
   if (tid < 32) umma::tmem_alloc(&tmem_slot, a.tmem_cols);
   if (tid == 0) {
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           kend = a.tg.rowptr[a.tg.unit_ptr[unit + 1]];
         }
         for (int k0 = kbeg; k0 < kend; k0 += TC_TILE) {
-          for (int l = 0; l < L - 1; ++l) {  // recompute
+          for (int l = id0r ? 1 : 0; l < L - 1; ++l) {  // recompute
             const int nmma = 3 * (lay.Kd[l] / 8);
             umma::mbar_wait(&bar_fg, pf);
             pf ^= 1;
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             pd ^= 1;
           }
           for (int l = L - 1; l >= 0; --l) {
-            const bool do_dgrad = l > 0 || a.need_dz0;
+            const bool do_dgrad = (l > 0 || a.need_dz0) && !(id0 && l == 0);
             const uint32_t tDl = (l == 0) ? tmem + a.c_d0 : tD;
             const uint32_t tDwl = (l == 0) ? tmem + a.c_dw0 : tDw + ((l & 1) ? a.dw_alt : 0);
             const bool swapped = streaming && (l == a.stream_a || l == a.stream_b);
@@ -485,7 +491,52 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       if (!NODE && aggr == NGPDE_AGGR_MEAN && valid) rdeg = __frcp_rn((float)(a.tg.rowptr[d + 1] - a.tg.rowptr[d]));
 
       // ---- 1. forward recompute: Z_1 .. Z_{L-1} (two issuing warps, accumulators tD and tDw, bias added here) ----
-      if (L > 1) {
+      if (L > 1 && id0r) {
+        // identity first layer (hoisted): Z_1 = act_0(gathered input) for this thread's chunk -- no MMAs, no A operand for layer 0
+        if (c0 < Kd0) {
+          float z[16];
+          if (NODE) {
+            const TcChunk ch = chunks[c0 >> 4];
+            if (ch.base != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) z[j] = 0.f;
+              if (valid) tc_load_chunk<4>(ch, d, 0, z);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) z[j] = valid ? tc_gather_col(cols[c0 + j], s, d, p, pg) : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const TcCol t0 = cols[c0 + 4 * i];
+              float v4[4];
+              if ((t0.kind & TC_KIND_VEC4) && t0.kind > 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v4[j] = 0.f;
+                if (valid) tc_gather_dps4(t0, s, d, v4);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v4[j] = valid ? tc_gather_col(cols[c0 + 4 * i + j], s, d, p, pg) : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) z[4 * i + j] = v4[j];
+            }
+          }
+          tc_act16(a.act[0], z);
+          uint32_t v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(z[j]);
+          umma::tmem_st16(tmem + a.c_zs[1] + lane_addr + c0, v);
+          if (L > 2) {
+            uint32_t lo[16];
+            tc_split16(z, v, lo);
+            umma::tmem_st16(tAhi + lane_addr + c0, v);
+            umma::tmem_st16(tAlo + lane_addr + c0, lo);
+          }
+        }
+        umma::tmem_wait_st();
+        if (L > 2) arrive(&bar_fg);
+      } else if (L > 1) {
         if (NODE) {
           // node phase: whole 16-column chunks (vector loads where the chunk is an aligned run of one array)
           for (int cc = c0; cc < Kd0; cc += 64) {
@@ -532,8 +583,10 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         }
         umma::tmem_wait_st();
         arrive(&bar_fg);
+      }
+      if (L > 1) {
 #pragma unroll 1
-        for (int l = 0; l < L - 1; ++l) {
+        for (int l = id0r ? 1 : 0; l < L - 1; ++l) {
           const int Np = lay.Np[l];
           // bias row of the weight image (row Kd, unswizzled because Kd % 4 == 0): hi + lo.  Loaded BEFORE the wait: a
           // shared-memory load issued while the MMAs stream their operands takes hundreds of cycles
@@ -657,7 +710,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       for (int l = L - 1; l >= 0; --l) {
         const int Np = lay.Np[l], Kd = lay.Kd[l];
         const bool active = c0 < Np;
-        const bool do_dgrad = l > 0 || a.need_dz0;
+        const bool do_dgrad = (l > 0 || a.need_dz0) && !(id0 && l == 0);
         const uint32_t tDl = (l == 0) ? tmem + a.c_d0 : tD;
         // with two dW^T accumulators (dw_alt) a layer's block is collected two layers later, off the critical path; with one
         // it has to be collected before the next layer's weight-gradient batch is issued
@@ -807,8 +860,13 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             // ---- 4. dZ_0 back to its sources ----
             for (int cc = c0; cc < Kd0; cc += 64) {
               uint32_t v[16];
-              umma::tmem_ld16(tDl + lane_addr + cc, v);
-              umma::tmem_wait_ld();
+              if (id0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(g[j]);
+              } else {
+                umma::tmem_ld16(tDl + lane_addr + cc, v);
+                umma::tmem_wait_ld();
+              }
               if (NODE) {
                 const TcChunk dch = dchunks[cc >> 4];
                 if (valid && dch.base != nullptr) {
@@ -827,6 +885,13 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) DZ[row * (Kd0 + 1) + cc + j] = __uint_as_float(v[j]);
+                if (a.direct_src && valid) {  // desrc[k0 + row][cc .. cc + 16): this thread's registers
+                  float4* o = reinterpret_cast<float4*>(a.desrc + (size_t)(k0 + row) * a.src_w + cc);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    o[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                       __uint_as_float(v[4 * j + 3]));
+                }
               }
             }
           }
@@ -869,7 +934,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           }
           return n;
         };
-        if (sw >= 32) {
+        if (a.direct_src) {
+          // already stored from the registers that held dZ_0 (step 4)
+        } else if (sw >= 32) {
           for (int cc = tid & 31; cc < sw; cc += 32) {
             int z0, z1;
             float f0, f1;
