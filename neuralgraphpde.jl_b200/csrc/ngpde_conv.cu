@@ -155,6 +155,75 @@ __global__ void nhoist_unfold_kernel(NodeHoistMap h, const float* __restrict__ d
   }
 }
 
+// Weighted column sums over the node axis in two fixed-order stages: out[j][c] = sum_n S[n][j] dq[n][c] for j < ds, and
+// out[ds][c] = sum_n dq[n][c]  (the weight-gradient rows of the static node columns and the bias gradient of a hoisted first
+// layer: the dense part goes through the GEMM engine, these few rows do not deserve one).  ds <= 7.
+__global__ void __launch_bounds__(256) wcolsum_stage1_kernel(const float* __restrict__ dq, int ld, int C, const float* __restrict__ S, int lds,
+                                                              int ds, long long N, int rows_per_block, float* __restrict__ partial) {
+  // thread = (4 columns, row slice): the block's rows are dealt round-robin to the slices, whose sums are then added in slice
+  // order through shared memory (fixed order: deterministic)
+  extern __shared__ float4 sm4[];  // [slices][ds + 1][C / 4]
+  const int c4n = C >> 2, slices = blockDim.x / c4n;
+  const int c4 = threadIdx.x % c4n, slice = threadIdx.x / c4n;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(N, r0 + rows_per_block);
+  float4 acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (slice < slices) {
+    for (long long r = r0 + slice; r < r1; r += slices) {
+      const float4 v = *reinterpret_cast<const float4*>(dq + (size_t)r * ld + 4 * c4);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        if (j < ds) {
+          const float w = S[(size_t)r * lds + j];
+          acc[j].x = fmaf(w, v.x, acc[j].x); acc[j].y = fmaf(w, v.y, acc[j].y);
+          acc[j].z = fmaf(w, v.z, acc[j].z); acc[j].w = fmaf(w, v.w, acc[j].w);
+        }
+      }
+      acc[7].x += v.x; acc[7].y += v.y; acc[7].z += v.z; acc[7].w += v.w;
+    }
+    for (int j = 0; j <= ds; ++j) sm4[(slice * (ds + 1) + j) * c4n + c4] = j < ds ? acc[j] : acc[7];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (ds + 1) * c4n; i += blockDim.x) {
+    float4 t = sm4[i];
+    for (int sl = 1; sl < slices; ++sl) {
+      const float4 u = sm4[sl * (ds + 1) * c4n + i];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    reinterpret_cast<float4*>(partial + (size_t)blockIdx.x * (ds + 1) * C)[i] = t;
+  }
+}
+// out2[g][p] = sum over the `group` partials of group g, in order (first level of a two-level fixed-order reduction)
+__global__ void reduce_groups_kernel(const float* __restrict__ partial, int n, int P, int group, float* __restrict__ out2) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+  if (p >= P) return;
+  const int c0 = g * group, c1 = min(n, c0 + group);
+  float s = 0.f;
+  for (int c = c0; c < c1; ++c) s += partial[(size_t)c * P + p];
+  out2[(size_t)g * P + p] = s;
+}
+// [hdin][n1] | [hdin][n1] -> [hdin][2 n1]
+__global__ void hoist_cat_kernel(const float* __restrict__ ft, const float* __restrict__ fs, int rows, int n1, float* __restrict__ fcat) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 2 * n1) return;
+  const int r = i / (2 * n1), c = i - r * 2 * n1;
+  fcat[i] = c < n1 ? ft[r * n1 + c] : fs[r * n1 + c - n1];
+}
+// dense rows [dx][2 n1] (GEMM) + static / bias rows [(ds + 1)][2 n1] (weighted column sums) -> the (Wt, b1 | Ws) gradient layout
+__global__ void hoist_repack_kernel(const float* __restrict__ dwx, const float* __restrict__ dsmall, int dx, int ds, int n1,
+                                    float* __restrict__ dft, float* __restrict__ dfs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, hdin = dx + ds;
+  if (i < hdin * n1) {
+    const int k = i / n1, c = i - k * n1;
+    const float* src = k < dx ? dwx + (size_t)k * 2 * n1 : dsmall + (size_t)(k - dx) * 2 * n1;
+    dft[i] = src[c];
+    dfs[i] = src[n1 + c];
+  } else if (i < hdin * n1 + n1) {
+    dft[i] = dsmall[(size_t)ds * 2 * n1 + (i - hdin * n1)];
+  }
+}
+
 // q[n] = [a[n]; b[n]]  (rows of `w` floats, w % 4 == 0) and its inverse
 __global__ void hoist_join_kernel(const float4* __restrict__ a, const float4* __restrict__ b, size_t rows, int w4, float4* __restrict__ q) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -688,6 +757,45 @@ void nhoist_args(const Plan& p, const float* q, Args* n) {
   n->mlp = p.node_in;
 }
 
+// ---- the hoisted projections' backward as dense GEMMs over the node axis (tcgen05 3xTF32 engine of the factored GNOConv) ----
+constexpr int kWcsRows = 1024;  // rows per block of the weighted column sums
+int outer_gemm_splits(int M, int N, int64_t n_nodes, int num_sms) {
+  const int tiles = ((M + 127) / 128) * ((N + 63) / 64);
+  int sp = std::max(1, (2 * num_sms) / std::max(1, tiles));
+  while (sp > 1 && n_nodes / sp < 512) --sp;
+  return std::min(sp, 512);
+}
+// out[M][N] = A' B, A stored [n][M] (lda), B stored [n][N] (ldb): split over the node axis, slices added in order
+int node_outer_gemm(const float* A, int lda, int M, const float* B, int ldb, int N, int64_t n_nodes, int num_sms, float* part,
+                    float* out, cudaStream_t st) {
+  const int sp = outer_gemm_splits(M, N, n_nodes, num_sms);
+  if (int rc = gno_gemm(A, lda, true, B, ldb, true, part, N, M, N, n_nodes, sp, nullptr, st)) return rc;
+  const int P = M * N;
+  reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part, sp, P, out);
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+// out[(ds + 1)][C]: rows j < ds = sum_n S[n][j] dq[n][:], row ds = column sums of dq.  C % 4 == 0, C <= 1024, rows 16-byte aligned.
+// `part` holds wcs_part_floats(...) floats.
+size_t wcs_part_floats(int64_t n_nodes, int C, int ds) {
+  const size_t nblk = (size_t)((n_nodes + kWcsRows - 1) / kWcsRows) + 1;
+  return (nblk + (nblk + 63) / 64 + 1) * (size_t)(ds + 1) * C;
+}
+int weighted_colsums(const float* dq, int ld, int C, const float* S, int lds, int ds, int64_t n_nodes, float* part, float* out,
+                     cudaStream_t st) {
+  const int nblk = std::max(1, (int)((n_nodes + kWcsRows - 1) / kWcsRows));
+  const int c4n = C / 4, slices = std::max(1, 256 / c4n);
+  const size_t smem = sizeof(float4) * (size_t)slices * (ds + 1) * c4n;
+  wcolsum_stage1_kernel<<<nblk, slices * c4n, smem, st>>>(dq, ld, C, S, lds, ds, (long long)n_nodes, kWcsRows, part);
+  const int P = (ds + 1) * C;
+  const int ngroups = (nblk + 63) / 64;
+  float* part2 = part + (size_t)nblk * P;
+  reduce_groups_kernel<<<dim3((P + 127) / 128, ngroups), 128, 0, st>>>(part, nblk, P, 64, part2);
+  reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part2, ngroups, P, out);
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
 struct BwdLayout {
   int te_e, smem_e, grid_e;
   int te_n, smem_n, grid_n;
@@ -704,6 +812,9 @@ struct BwdLayout {
   size_t off_dq = 0, off_dpt = 0, off_dps = 0, off_dxt = 0, off_dxs = 0, off_dft = 0, off_dfs = 0, off_dfin = 0, off_nodews = 0,
          nodews_bytes = 0;
   int dxe = 0;  // width of the array the edge phase differentiates: dx, or 2 n1 when hoisted
+  // GEMM form of the projections' backward (when the widths allow it)
+  bool hgemm = false, nhgemm = false;
+  size_t off_fcat = 0, off_dwx = 0, off_dsmall = 0, off_gpart = 0, off_wpart = 0;
 };
 
 int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, BwdLayout* L) {
@@ -795,6 +906,17 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
     L->off_DM = off;     off = align256(off + sizeof(float) * (size_t)g->N * d.gno_out);
     L->off_dBpart = off; off = align256(off + sizeof(float) * (size_t)L->gno_splits * R * d.gno_out);
     L->off_B = off;      off = align256(off + sizeof(float) * R * d.gno_out);
+  }
+  if (p.hoist || p.nhoist) {
+    L->hgemm = p.hoist && (d.dx & 3) == 0 && p.ds <= 7;
+    L->nhgemm = p.nhoist && (d.dx & 3) == 0 && (p.dm & 3) == 0;
+    const int n1m = std::max(p.hoist ? p.h_n1 : 0, p.nhoist ? p.nh_n1 : 0);
+    const int mm = std::max(d.dx, p.dm);
+    L->off_fcat = off;   off = align256(off + sizeof(float) * (size_t)(d.dx + p.ds) * 2 * n1m);
+    L->off_dwx = off;    off = align256(off + sizeof(float) * (size_t)mm * 2 * n1m);
+    L->off_dsmall = off; off = align256(off + sizeof(float) * 8 * 2 * n1m);
+    L->off_gpart = off;  off = align256(off + sizeof(float) * (size_t)outer_gemm_splits(mm, 2 * n1m, g->N, g->num_sms) * mm * 2 * n1m * 2);
+    L->off_wpart = off;  off = align256(off + sizeof(float) * wcs_part_floats(g->N, 2 * n1m, 7));
   }
   L->off_part_phi = off;  off = align256(off + sizeof(float) * (size_t)L->grid_e * L->part_stride);
   L->off_part_node = off; off = align256(off + sizeof(float) * (size_t)L->grid_n * (p.nhoist ? p.node_in.n_params : p.node.n_params));
@@ -894,6 +1016,11 @@ int node_bwd_layout(const ngpde_graph* g, const MlpDev& mlp, NodeBwdLayout* L) {
 }
 }  // namespace
 
+bool node_mlp_backward_fuses_act(const ngpde_graph* g, const MlpDev& mlp) {
+  NodeBwdLayout L;
+  return node_bwd_layout(g, mlp, &L) == NGPDE_OK && L.tc.on;
+}
+
 size_t node_mlp_backward_ws(const ngpde_graph* g, const MlpDev& mlp) {
   NodeBwdLayout L;
   if (node_bwd_layout(g, mlp, &L)) return 0;
@@ -903,7 +1030,7 @@ size_t node_mlp_backward_ws(const ngpde_graph* g, const MlpDev& mlp) {
 // dy -> dx (may be nullptr... it is always produced here), dparams
 int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, const float* dy,
                       float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st, const float* snode, int ds,
-                      int dy_ld) {
+                      int dy_ld, const float* yact, int yact_kind) {
   NodeBwdLayout L;
   if (int rc = node_bwd_layout(g, mlp, &L)) return rc;
   if (ws_bytes < L.total) {
@@ -932,6 +1059,9 @@ int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* para
   std::memcpy(n.zoff, L.s.zoff, sizeof(n.zoff));
   n.offG0 = L.s.offG0; n.offG1 = L.s.offG1; n.offW = L.s.offW;
   n.gout_ld = dy_ld;
+  NGPDE_REQUIRE(yact == nullptr || L.tc.on, "internal: fused act'(y) needs the tensor-core node kernel");
+  n.yact = yact;
+  n.yact_kind = yact_kind;
   if (L.tc.on) {
     if (int rc = launch_bwd_tc(true, L.tc, mlp, n, reinterpret_cast<float*>(ws + L.tc.ws_off), st)) return rc;
   } else {
@@ -1288,8 +1418,20 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       const float* fu = reinterpret_cast<const float*>(hbase + nhw.off_fu);
       const float* fv = reinterpret_cast<const float*>(hbase + nhw.off_fv);
       const int ldq = 2 * p.nh_n1;
-      if (int rc = node_mlp_backward(g, p.mlp_u, fu, io->x, ndq, dxdirect, ndfu, ws + L.off_nnodews, L.nnodews_bytes, st, nullptr, 0, ldq)) return rc;
-      if (int rc = node_mlp_backward(g, p.mlp_v, fv, io->mbar, ndq, dmbar, ndfv, ws + L.off_nnodews, L.nnodews_bytes, st, nullptr, 0, ldq)) return rc;
+      if (L.nhgemm && aligned16(io->x) && aligned16(io->mbar)) {
+        // GEMM form: dx_direct = g Wx', dmbar = g Wm', dWx = x' g, dWm = mbar' g (split-K, slices in order), db1 = column sums of g
+        const int n1 = p.nh_n1;
+        float* gpart = reinterpret_cast<float*>(ws + L.off_gpart);
+        float* wpart = reinterpret_cast<float*>(ws + L.off_wpart);
+        if (int rc = gno_gemm(ndq, ldq, false, fu, n1, false, dxdirect, desc->dx, g->N, desc->dx, n1, 1, nullptr, st)) return rc;
+        if (int rc = gno_gemm(ndq, ldq, false, fv, n1, false, dmbar, p.dm, g->N, p.dm, n1, 1, nullptr, st)) return rc;
+        if (int rc = node_outer_gemm(io->x, desc->dx, desc->dx, ndq, ldq, n1, g->N, g->num_sms, gpart, ndfu, st)) return rc;
+        if (int rc = node_outer_gemm(io->mbar, p.dm, p.dm, ndq, ldq, n1, g->N, g->num_sms, gpart, ndfv, st)) return rc;
+        if (int rc = weighted_colsums(ndq, ldq, n1, nullptr, 0, 0, g->N, wpart, ndfu + (size_t)desc->dx * n1, st)) return rc;
+      } else {
+        if (int rc = node_mlp_backward(g, p.mlp_u, fu, io->x, ndq, dxdirect, ndfu, ws + L.off_nnodews, L.nnodews_bytes, st, nullptr, 0, ldq)) return rc;
+        if (int rc = node_mlp_backward(g, p.mlp_v, fv, io->mbar, ndq, dmbar, ndfv, ws + L.off_nnodews, L.nnodews_bytes, st, nullptr, 0, ldq)) return rc;
+      }
       nhoist_unfold_kernel<<<32, 256, 0, st>>>(nhoist_map(*desc, p), ndfu, ndfv, ndfin, io->dnode_params);
     } else {
       {
@@ -1429,10 +1571,28 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       (void)dpt; (void)dps;  // dPt / dPs are the two halves of dQ's rows, read in place
       const float* ft = reinterpret_cast<const float*>(hbase + hw.off_ft);
       const float* fs = reinterpret_cast<const float*>(hbase + hw.off_fs);
-      if (int rc = node_mlp_backward(g, p.mlp_t, ft, io->x, dq, dxt, dft, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds, L.dxe)) return rc;
-      if (int rc = node_mlp_backward(g, p.mlp_s, fs, io->x, dq + p.h_n1, dxs, dfs, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds, L.dxe)) return rc;
-      hoist_unfold_kernel<<<32, 256, 0, st>>>(hoist_map(*desc, p), dft, dfs, dphi_target, p.phi.dims[0], io->dphi_params);
       const size_t total = (size_t)g->N * desc->dx;
+      if (L.hgemm && aligned16(io->x) && (p.ds == 0 || io->snode != nullptr)) {
+        // dense GEMMs over the node axis: dx_h = dQ [Wt | Ws]_x' (one GEMM for both projections), d[Wt | Ws]_x = x' dQ (split-K,
+        // slices added in order); the static rows and the bias through two-stage weighted column sums
+        const int n1 = p.h_n1, hdin = desc->dx + p.ds;
+        float* fcat = reinterpret_cast<float*>(ws + L.off_fcat);
+        float* dwx = reinterpret_cast<float*>(ws + L.off_dwx);
+        float* dsmall = reinterpret_cast<float*>(ws + L.off_dsmall);
+        float* gpart = reinterpret_cast<float*>(ws + L.off_gpart);
+        float* wpart = reinterpret_cast<float*>(ws + L.off_wpart);
+        hoist_cat_kernel<<<(hdin * 2 * n1 + 255) / 256, 256, 0, st>>>(ft, fs, hdin, n1, fcat);
+        if (int rc = gno_gemm(dq, L.dxe, false, fcat, 2 * n1, false, dxt, desc->dx, g->N, desc->dx, 2 * n1, 1, nullptr, st)) return rc;
+        if (int rc = node_outer_gemm(io->x, desc->dx, desc->dx, dq, L.dxe, 2 * n1, g->N, g->num_sms, gpart, dwx, st)) return rc;
+        if (int rc = weighted_colsums(dq, L.dxe, 2 * n1, io->snode, p.ds, p.ds, g->N, wpart, dsmall, st)) return rc;
+        hoist_repack_kernel<<<(hdin * n1 + n1 + 255) / 256, 256, 0, st>>>(dwx, dsmall, desc->dx, p.ds, n1, dft, dfs);
+        hoist_unfold_kernel<<<32, 256, 0, st>>>(hoist_map(*desc, p), dft, dfs, dphi_target, p.phi.dims[0], io->dphi_params);
+        NGPDE_CUDA_TRY(cudaMemsetAsync(dxs, 0, sizeof(float) * total, st));
+      } else {
+        if (int rc = node_mlp_backward(g, p.mlp_t, ft, io->x, dq, dxt, dft, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds, L.dxe)) return rc;
+        if (int rc = node_mlp_backward(g, p.mlp_s, fs, io->x, dq + p.h_n1, dxs, dfs, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds, L.dxe)) return rc;
+        hoist_unfold_kernel<<<32, 256, 0, st>>>(hoist_map(*desc, p), dft, dfs, dphi_target, p.phi.dims[0], io->dphi_params);
+      }
       add3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dxdirect, dxt, dxs, total, io->dx);
       NGPDE_CUDA_TRY(cudaGetLastError());
       return NGPDE_OK;

@@ -82,6 +82,8 @@ struct BwdArgs {
   int store_last;         // Z_L has to be recomputed (activation on the last layer, or max/min)
   int has_dst_side;
   int gout_ld;            // node phase, tensor-core kernels: leading dimension of gout_ptr (0: dout)
+  const float* yact;      // node phase, tensor-core kernels: when set, the cotangent is multiplied by act'(y) on load, y = yact [N][dout]
+  int yact_kind;          //   (an activation that follows the MLP's identity last layer: GCNConv's out >= in branch)
   int direct_src;         // tensor-core edge kernel, hoisted input: the source-side cotangent row of an edge IS its dZ_0 row (one SRC
                           // segment over all input rows): written from registers, no pass over the shared-memory tile
   int skip_w0;            // tensor-core kernels: layer 0 is the identity of a hoisted first layer -- its weight gradient is not formed
@@ -115,6 +117,8 @@ int node_mlp_forward(const ngpde_graph* g, const MlpDev& mlp, const float* param
 size_t node_mlp_backward_ws(const ngpde_graph* g, const MlpDev& mlp);
 int node_mlp_backward(const ngpde_graph* g, const MlpDev& mlp, const float* params, const float* x, const float* dy,
                       float* dx, float* dparams, void* workspace, size_t ws_bytes, cudaStream_t st, const float* snode = nullptr,
-                      int ds = 0, int dy_ld = 0);
+                      int ds = 0, int dy_ld = 0, const float* yact = nullptr, int yact_kind = 0);
+// true when node_mlp_backward runs on the tensor-core kernel, which can apply act'(y) to the cotangent on load (`yact`)
+bool node_mlp_backward_fuses_act(const ngpde_graph* g, const MlpDev& mlp);
 
 }  // namespace ngpde

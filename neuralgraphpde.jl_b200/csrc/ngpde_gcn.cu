@@ -542,15 +542,20 @@ extern "C" int ngpde_gcn_conv_backward(ngpde_graph_t g, const ngpde_gcn_desc* de
                   "GCNConv expects bias to follow weight in the flat parameter vector (and dbias to follow dweight)");
     if (int rc = launch_gcn_aggregate(N, desc->in_chs, L.colptr, nullptr, L.rowval, val, c, x, agg, st)) return rc;
     const float* dp = dy;
+    const float* yact = nullptr;
     if (gcn_bwd_act(desc->act) != desc->act) {
       NGPDE_REQUIRE(y != nullptr, "GCNConv backward needs the forward output y");
-      const size_t total = (size_t)N * desc->out_chs;
-      float* tmp3 = reinterpret_cast<float*>(ws + w.off_tmp3);
-      act_grad_y_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, dy, desc->act, total, tmp3);
-      dp = tmp3;
       m.act[0] = NGPDE_ACT_IDENTITY;
+      if (node_mlp_backward_fuses_act(g, m)) {
+        yact = y;  // the tensor-core Dense backward multiplies the cotangent by act'(y) as it loads it
+      } else {
+        const size_t total = (size_t)N * desc->out_chs;
+        float* tmp3 = reinterpret_cast<float*>(ws + w.off_tmp3);
+        act_grad_y_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, dy, desc->act, total, tmp3);
+        dp = tmp3;
+      }
     }
-    if (int rc = node_mlp_backward(g, m, weight, agg, dp, tmp, dweight, mlp_ws, mlp_ws_bytes, st)) return rc;
+    if (int rc = node_mlp_backward(g, m, weight, agg, dp, tmp, dweight, mlp_ws, mlp_ws_bytes, st, nullptr, 0, 0, yact, desc->act)) return rc;
     if (int rc = launch_gcn_aggregate(N, desc->in_chs, L.tptr, L.tpos, L.colidx, val, c, tmp, dx, st)) return rc;
   }
   NGPDE_CUDA_TRY(cudaGetLastError());

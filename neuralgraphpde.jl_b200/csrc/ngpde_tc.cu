@@ -238,6 +238,8 @@ int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base,
   a.gout_ptr = base.gout_ptr;
   a.gout_ld = base.gout_ld > 0 ? base.gout_ld : base.dout;
   a.skip_w0 = base.skip_w0;
+  a.yact = base.yact;
+  a.yact_kind = base.yact_kind;
   a.direct_src = base.direct_src;
   a.src_c0 = base.src_w > 0 ? base.src_c0 : 0;
   a.src_w = base.src_w > 0 ? base.src_w : base.dx;

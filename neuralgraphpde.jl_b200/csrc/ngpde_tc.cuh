@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mp_fwd_tc_kernel(const __grid_c
           if (valid) tc_load_chunk<2>(ch, d, c0 & 15, vv);
         } else {
           const TcCol t0 = cols[c0], t4 = cols[c0 + 4];
-          if (!NODE && (t0.kind & TC_KIND_VEC4) && (t4.kind & TC_KIND_VEC4) && t0.kind > 0 && t4.kind > 0) {
+          if ((t0.kind & TC_KIND_VEC4) && (t4.kind & TC_KIND_VEC4) && t0.kind > 0 && t4.kind > 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) vv[j] = 0.f;
             if (valid) {

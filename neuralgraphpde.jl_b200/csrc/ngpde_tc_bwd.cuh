@@ -40,6 +40,8 @@ struct TcBwdArgs {
   int dout;                // width of the MLP output (= N[L-1])
   const float* gout_ptr;   // edge: dmbar / dy [N][dout]; node: dy [N][gout_ld]
   int gout_ld;
+  const float* yact;       // node phase: cotangent *= act'(y) on load (y [N][dout]); NULL: off
+  int yact_kind;
   int src_c0, src_w;       // x columns with source-side cotangents; desrc is [E][src_w]
   int dst_c0, dst_w;       // x columns with destination-side cotangents (the others of dxdst are not written)
   int direct_src;          // source-side cotangent row = dZ_0 row (hoisted input): stored from registers
@@ -495,16 +497,11 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         // identity first layer (hoisted): Z_1 = act_0(gathered input) for this thread's chunk -- no MMAs, no A operand for layer 0
         if (c0 < Kd0) {
           float z[16];
-          if (NODE) {
-            const TcChunk ch = chunks[c0 >> 4];
-            if (ch.base != nullptr) {
+          const TcChunk ch = NODE ? chunks[c0 >> 4] : TcChunk{nullptr, 0};
+          if (NODE && ch.base != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) z[j] = 0.f;
-              if (valid) tc_load_chunk<4>(ch, d, 0, z);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) z[j] = valid ? tc_gather_col(cols[c0 + j], s, d, p, pg) : 0.f;
-            }
+            for (int j = 0; j < 16; ++j) z[j] = 0.f;
+            if (valid) tc_load_chunk<4>(ch, d, 0, z);
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -658,6 +655,12 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           if (!NODE && aggr == NGPDE_AGGR_MEAN) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) g[j] *= rdeg;
+          }
+          if (NODE && a.yact != nullptr) {  // an activation behind the MLP (GCNConv): dP = dy * act'(y)
+            const float* yp = a.yact + (size_t)(k0 + row) * dout + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < dout) g[j] *= act_grad_y(a.yact_kind, yp[j]);
           }
         }
       }
