@@ -239,10 +239,10 @@ __global__ void hoist_split_kernel(const float4* __restrict__ q, size_t rows, in
   const int c = (int)(i - r * 2 * w4);
   if (c < w4) a[r * w4 + c] = q[i]; else b[r * w4 + c - w4] = q[i];
 }
-// out = a + b + c (a may be NULL)
+// out = a + b + c (a and c may be NULL)
 __global__ void add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, size_t n, float* __restrict__ out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (a ? a[i] : 0.f) + b[i] + c[i];
+  if (i < n) out[i] = (a ? a[i] : 0.f) + b[i] + (c ? c[i] : 0.f);
 }
 
 namespace {
@@ -1587,7 +1587,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
         if (int rc = weighted_colsums(dq, L.dxe, 2 * n1, io->snode, p.ds, p.ds, g->N, wpart, dsmall, st)) return rc;
         hoist_repack_kernel<<<(hdin * n1 + n1 + 255) / 256, 256, 0, st>>>(dwx, dsmall, desc->dx, p.ds, n1, dft, dfs);
         hoist_unfold_kernel<<<32, 256, 0, st>>>(hoist_map(*desc, p), dft, dfs, dphi_target, p.phi.dims[0], io->dphi_params);
-        NGPDE_CUDA_TRY(cudaMemsetAsync(dxs, 0, sizeof(float) * total, st));
+        dxs = nullptr;  // both projections' input gradients came out of the one GEMM
       } else {
         if (int rc = node_mlp_backward(g, p.mlp_t, ft, io->x, dq, dxt, dft, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds, L.dxe)) return rc;
         if (int rc = node_mlp_backward(g, p.mlp_s, fs, io->x, dq + p.h_n1, dxs, dfs, ws + L.off_nodews, L.nodews_bytes, st, io->snode, p.ds, L.dxe)) return rc;

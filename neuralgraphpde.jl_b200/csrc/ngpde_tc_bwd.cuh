@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             if (swapped) pr ^= 1;
             const int gz = (lay.Kd[l] + 31) >> 5;
             const uint32_t s_zhi = umma::smem_u32(st_base), s_zlo = s_zhi + 4u * gz * ROWS * 32;
-            for (int h = 0; h < NH; ++h) {
+            for (int h = 0; h < ((id0 && l == 0) ? 0 : NH); ++h) {  // identity layer 0: no weight-gradient batch, no hand-off
               umma::mbar_wait(&bar_fs, ps);
               ps ^= 1;
               umma::tc_fence_after();
@@ -658,9 +658,18 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           }
           if (NODE && a.yact != nullptr) {  // an activation behind the MLP (GCNConv): dP = dy * act'(y)
             const float* yp = a.yact + (size_t)(k0 + row) * dout + c0;
+            if ((dout & 3) == 0 && c0 + 16 <= dout && (reinterpret_cast<uintptr_t>(a.yact) & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c0 + j < dout) g[j] *= act_grad_y(a.yact_kind, yp[j]);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(yp + j);
+                g[j] *= act_grad_y(a.yact_kind, t.x); g[j + 1] *= act_grad_y(a.yact_kind, t.y);
+                g[j + 2] *= act_grad_y(a.yact_kind, t.z); g[j + 3] *= act_grad_y(a.yact_kind, t.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < dout) g[j] *= act_grad_y(a.yact_kind, yp[j]);
+            }
           }
         }
       }
@@ -738,19 +747,22 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         // one this layer's weight-gradient batch will overwrite)
         if (defer && l + 2 <= L - 1) collect_dw(l + 2, tDw + (((l + 2) & 1) ? a.dw_alt : 0));
         // (C) the previous layer's weight-gradient batch has drained the staging buffer
-        if (l < L - 1) {
+        // identity layer 0 (hoisted): nothing is staged and no batch is issued for it, so layer 1's batch is only waited for
+        // (and its dW^T block collected) at the end of the tile, under the cotangent scatter
+        const bool lazy0 = id0 && l == 0;
+        if (l < L - 1 && !lazy0) {
           mbar_wait_warp(&bar_w, ph_w, a.opt);
           ph_w ^= 1;
           umma::tc_fence_after();
           if (!defer) collect_dw(l + 1, tDw);
         }
-        float cy[2];
-        tcb_colsum_b(cw, lane, cy);
+        float cy[2] = {0.f, 0.f};
+        if (!lazy0) tcb_colsum_b(cw, lane, cy);
         TCB_STAMP(4 + 6 * l);
         // (D) stage G_{l+1} and Z_l as MN-major hi/lo images -- the whole tile at once (FULL), or rows 0..63 and then, once
         // that batch has drained the buffer, rows 64..127 -- while the input-gradient MMAs run
 #pragma unroll 1
-        for (int h = 0; h < NH; ++h) {
+        for (int h = 0; h < (lazy0 ? 0 : NH); ++h) {
           if (h == 1) {
             mbar_wait_warp(&bar_w, ph_w, a.opt);  // the first half has been consumed
             ph_w ^= 1;
@@ -857,7 +869,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               for (int j = 0; j < 16; ++j) g[j] = 0.f;
             }
           }
-          tcb_colsum_a(g, lane, cw);
+          if (!(id0 && l == 1)) tcb_colsum_a(g, lane, cw);  // (the identity layer has no bias)
         } else {
           if (a.need_dz0) {
             // ---- 4. dZ_0 back to its sources ----
@@ -899,7 +911,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             }
           }
           // layer 1's block (deferred); layer 0's closes the tile, after the scatter below (its MMAs are still running)
-          if (a.dw_alt > 0 && L > 1) collect_dw(1, tDw + a.dw_alt);
+          if (a.dw_alt > 0 && L > 1 && !id0) collect_dw(1, tDw + a.dw_alt);
         }
         umma::tc_fence_before();
       }
@@ -1011,11 +1023,12 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       }
       TCB_STAMP(29);
       // layer 0's dW^T block: its weight-gradient batch ran under the scatter above
-      mbar_wait_warp(&bar_w, ph_w, a.opt);
+      mbar_wait_warp(&bar_w, ph_w, a.opt);  // id0: layer 1's last batch (layer 0 issued none), else layer 0's
       TCB_STAMP(30);
       ph_w ^= 1;
       umma::tc_fence_after();
-      if (!a.skip_w0) collect_dw(0, tmem + a.c_dw0);
+      if (id0) collect_dw(1, a.dw_alt > 0 ? tDw + a.dw_alt : tDw);
+      else if (!a.skip_w0) collect_dw(0, tmem + a.c_dw0);
       umma::tc_fence_before();
       worker_sync();
       TCB_STAMP(27);
