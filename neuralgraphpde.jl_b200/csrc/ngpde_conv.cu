@@ -245,6 +245,29 @@ __global__ void add3_kernel(const float* __restrict__ a, const float* __restrict
   if (i < n) out[i] = (a ? a[i] : 0.f) + b[i] + (c ? c[i] : 0.f);
 }
 
+// the same with four columns per thread (dx, src_c0, src_w, dst_c0, dst_w all multiples of 4; 16-byte aligned arrays): the hoisted
+// dQ rows are 128 floats wide and the scalar kernel above spent its time issuing loads
+__global__ void dx_combine4_kernel(const float4* __restrict__ dx_direct, const float4* __restrict__ dxdst, const float4* __restrict__ desrc,
+                                   const int* __restrict__ tptr, const int* __restrict__ tpos, int N, int dx4, int src_c04, int src_w4,
+                                   int dst_c04, int dst_w4, float4* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * dx4) return;
+  const int i = (int)(idx / dx4), c = (int)(idx - (size_t)i * dx4);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (dx_direct) s = dx_direct[idx];
+  if (dxdst && c >= dst_c04 && c < dst_c04 + dst_w4) {
+    const float4 t = dxdst[idx];
+    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+  }
+  if (desrc && c >= src_c04 && c < src_c04 + src_w4) {
+    for (int q = tptr[i]; q < tptr[i + 1]; ++q) {
+      const float4 t = __ldg(desrc + (size_t)tpos[q] * src_w4 + (c - src_c04));
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+  }
+  out[idx] = s;
+}
+
 namespace {
 
 // ---- optional per-kernel timing (ngpde_profile_*): CUDA events recorded on the launching stream around the four
@@ -1566,8 +1589,14 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
       float* dft = reinterpret_cast<float*>(ws + L.off_dft);
       float* dfs = reinterpret_cast<float*>(ws + L.off_dfs);
       const size_t totq = (size_t)g->N * L.dxe;
-      dx_combine_kernel<<<(unsigned)((totq + 255) / 256), 256, 0, st>>>(nullptr, dxdst, g->E > 0 ? desrc : nullptr, g->tptr, g->tpos,
-                                                                         (int)g->N, L.dxe, src_c0, src_w, dst_c0, dst_w, dq);
+      if (((L.dxe | src_c0 | src_w | dst_c0 | dst_w) & 3) == 0) {
+        dx_combine4_kernel<<<(unsigned)((totq / 4 + 255) / 256), 256, 0, st>>>(
+            nullptr, reinterpret_cast<const float4*>(dxdst), g->E > 0 ? reinterpret_cast<const float4*>(desrc) : nullptr, g->tptr, g->tpos,
+            (int)g->N, L.dxe / 4, src_c0 / 4, src_w / 4, dst_c0 / 4, dst_w / 4, reinterpret_cast<float4*>(dq));
+      } else {
+        dx_combine_kernel<<<(unsigned)((totq + 255) / 256), 256, 0, st>>>(nullptr, dxdst, g->E > 0 ? desrc : nullptr, g->tptr, g->tpos,
+                                                                           (int)g->N, L.dxe, src_c0, src_w, dst_c0, dst_w, dq);
+      }
       (void)dpt; (void)dps;  // dPt / dPs are the two halves of dQ's rows, read in place
       const float* ft = reinterpret_cast<const float*>(hbase + hw.off_ft);
       const float* fs = reinterpret_cast<const float*>(hbase + hw.off_fs);

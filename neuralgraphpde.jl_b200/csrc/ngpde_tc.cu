@@ -260,13 +260,17 @@ int launch_bwd_tc_t(const TcBwdPhase& t, const MlpDev& mlp, const BwdArgs& base,
   a.stream_a = t.stream_a; a.stream_b = t.stream_b;
   a.dbg = (NODE != (getenv("NGPDE_TCB_DBG_NODE") != nullptr)) ? nullptr : g_tcb_dbg;
   { const char* e = getenv("NGPDE_TCB_OPT"); a.opt = e ? atoi(e) : 0; }
-  if (t.full) {
-    NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_bwd_tc_kernel<NODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
-    mp_bwd_tc_kernel<NODE, true><<<t.grid, TCB_THREADS, t.smem, st>>>(a);
-  } else {
-    NGPDE_CUDA_TRY(cudaFuncSetAttribute(mp_bwd_tc_kernel<NODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
-    mp_bwd_tc_kernel<NODE, false><<<t.grid, TCB_THREADS, t.smem, st>>>(a);
-  }
+  // the extended variant only where its extras are needed (hoisted first layers, wide cotangent rows, GCNConv's fused act')
+  const bool ext = a.skip_w0 || a.direct_src || a.yact != nullptr || (!NODE && a.need_dz0 && (a.src_w >= 32 || a.dst_w >= 32));
+  auto go = [&](auto kernel) -> int {
+    NGPDE_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t.smem));
+    kernel<<<t.grid, TCB_THREADS, t.smem, st>>>(a);
+    return NGPDE_OK;
+  };
+  int rc;
+  if (t.full) rc = ext ? go(mp_bwd_tc_kernel<NODE, true, true>) : go(mp_bwd_tc_kernel<NODE, true, false>);
+  else rc = ext ? go(mp_bwd_tc_kernel<NODE, false, true>) : go(mp_bwd_tc_kernel<NODE, false, false>);
+  if (rc) return rc;
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;
 }

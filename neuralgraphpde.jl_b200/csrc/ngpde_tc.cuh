@@ -164,9 +164,10 @@ __device__ __forceinline__ void tc_load_chunk(const TcChunk ch, int r, int first
   }
 }
 
+template <bool SUMMED = true>  // SUMMED = false: a kernel variant that never sees summed (hoisted) columns leaves the branch out
 __device__ __forceinline__ float tc_gather_col(const TcCol t, int s, int d, int p, int pg) {
   if (t.kind < 0) return 0.f;
-  if ((t.kind & TC_KIND_MASK) == TC_KIND_DPS)
+  if (SUMMED && (t.kind & TC_KIND_MASK) == TC_KIND_DPS)
     return __ldg(t.base + (size_t)d * t.ld) + __ldg(t.base + (size_t)s * t.ld + (t.kind >> TC_KIND_SHIFT));
   const int i0 = (t.kind == SEG_SRC || t.kind == SEG_SMD) ? s : (t.kind == SEG_EDGE ? p : (t.kind == SEG_GRAPH ? pg : d));
   float v = t.base[(size_t)i0 * t.ld];

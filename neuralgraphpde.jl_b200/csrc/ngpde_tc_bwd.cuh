@@ -245,7 +245,10 @@ __device__ __forceinline__ float tcb_colsum_c(const float (&y)[2], int lane) {
 // FULL: the weight-gradient operands of a layer are staged for the whole 128-row tile at once (all 16 warps, all four
 // schedulers busy, one MMA batch of K = 128 per layer) instead of in two 64-row halves.  The 128 KB staging buffer only
 // fits next to the weight images when two of them share a slot (stream_a / stream_b).
-template <bool NODE, bool FULL>
+// EXT: the variant with everything the hoisted first layers (and GCNConv's fused act') added -- identity layer 0 without MMAs,
+// summed gather, wide cotangent scatter, act'(y) on the cotangent load.  The plain variant does not even contain that code: the
+// kernel is instruction-cache sensitive, and carrying it cost the C3 edge backward 8 % (0.698 -> 0.758 ms).
+template <bool NODE, bool FULL, bool EXT>
 __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_constant__ TcBwdArgs a) {
   constexpr int NW = TCB_WORKERS;  // worker threads
   constexpr int ROWS = FULL ? TC_TILE : TCB_HALF;  // rows of one staged image
@@ -271,10 +274,12 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
   float* DZ = reinterpret_cast<float*>(smem + a.off_dz);  // edge phase: [128][Kd0 + 1]; later reused for the db exchange
   const int L = lay.L, Kd0 = lay.Kd[0];
   // edge phase: the gathered layer-0 input is parked in the (not yet used) dZ_0 tile instead of being gathered twice
-  const bool keep_z0 = !NODE && a.need_dz0 && L > 1 && !a.skip_w0;
+  const bool skip_w0 = EXT && a.skip_w0;
+  const bool direct_src = EXT && a.direct_src;
+  const bool keep_z0 = !NODE && a.need_dz0 && L > 1 && !skip_w0;
   // layer 0 is the identity of a hoisted first layer (skip_w0) and a thread's 16-column chunk of G_0 is its chunk of dZ_0:
   // dZ_0 = G_0 needs no input-gradient MMAs at all
-  const bool id0 = a.skip_w0 && L > 1 && Kd0 <= 64 && lay.Np[0] == Kd0;
+  const bool id0 = skip_w0 && L > 1 && Kd0 <= 64 && lay.Np[0] == Kd0;
   // ... and no recompute MMAs either: Z_1 = act_0(gathered input), when the columns a thread gathers are its own chunk
   const bool id0r = id0 && (NODE || (Kd0 >> 2) == 16);
 
@@ -415,7 +420,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               ps ^= 1;
               umma::tc_fence_after();
               TCB_STAMP_ANY(34 + 4 * l);
-              if (!(a.skip_w0 && l == 0)) tcb_issue_wgrad<ROWS>(lay, l, s_ghi, s_glo, s_zhi, s_zlo, tDwl, h);
+              if (!(skip_w0 && l == 0)) tcb_issue_wgrad<ROWS>(lay, l, s_ghi, s_glo, s_zhi, s_zlo, tDwl, h);
               umma::mma_commit(&bar_w);  // (an empty batch completes with whatever was issued before it)
               TCB_STAMP_ANY(35 + 4 * l);
             }
@@ -507,13 +512,13 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             for (int i = 0; i < 4; ++i) {
               const TcCol t0 = cols[c0 + 4 * i];
               float v4[4];
-              if ((t0.kind & TC_KIND_VEC4) && t0.kind > 0) {
+              if (EXT && (t0.kind & TC_KIND_VEC4) && t0.kind > 0) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v4[j] = 0.f;
                 if (valid) tc_gather_dps4(t0, s, d, v4);
               } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v4[j] = valid ? tc_gather_col(cols[c0 + 4 * i + j], s, d, p, pg) : 0.f;
+                for (int j = 0; j < 4; ++j) v4[j] = valid ? tc_gather_col<EXT>(cols[c0 + 4 * i + j], s, d, p, pg) : 0.f;
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j) z[4 * i + j] = v4[j];
@@ -545,7 +550,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               if (valid) tc_load_chunk<4>(ch, d, 0, v);
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+              for (int j = 0; j < 16; ++j) v[j] = valid ? tc_gather_col<EXT>(cols[cc + j], s, d, p, pg) : 0.f;
             }
             uint32_t hi[16], lo[16];
             tc_split16(v, hi, lo);
@@ -559,13 +564,13 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           uint32_t hi[4], lo[4];
           float v4[4];
           const TcCol t0 = cols[cc];
-          if ((t0.kind & TC_KIND_VEC4) && t0.kind > 0) {
+          if (EXT && (t0.kind & TC_KIND_VEC4) && t0.kind > 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) v4[j] = 0.f;
             if (valid) tc_gather_dps4(t0, s, d, v4);
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v4[j] = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+            for (int j = 0; j < 4; ++j) v4[j] = valid ? tc_gather_col<EXT>(cols[cc + j], s, d, p, pg) : 0.f;
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -656,7 +661,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 16; ++j) g[j] *= rdeg;
           }
-          if (NODE && a.yact != nullptr) {  // an activation behind the MLP (GCNConv): dP = dy * act'(y)
+          if (EXT && NODE && a.yact != nullptr) {  // an activation behind the MLP (GCNConv): dP = dy * act'(y)
             const float* yp = a.yact + (size_t)(k0 + row) * dout + c0;
             if ((dout & 3) == 0 && c0 + 16 <= dout && (reinterpret_cast<uintptr_t>(a.yact) & 15) == 0) {
 #pragma unroll
@@ -767,7 +772,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             mbar_wait_warp(&bar_w, ph_w, a.opt);  // the first half has been consumed
             ph_w ^= 1;
           }
-          if ((FULL || (lq >> 1) == h) && !(a.skip_w0 && l == 0)) {
+          if ((FULL || (lq >> 1) == h) && !(skip_w0 && l == 0)) {
             const int r = row - ROWS * h;
             if (active) stage_chunk<ROWS>(st_ghi, st_glo, r, c0, g);
             // Z_l: the gathered input for l == 0, else the FP32 copy kept in TMEM by the recompute
@@ -785,7 +790,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
                     if (valid) tc_load_chunk<4>(ch, d, 0, z);
                   } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) z[j] = valid ? tc_gather_col(cols[cc + j], s, d, p, pg) : 0.f;
+                    for (int j = 0; j < 16; ++j) z[j] = valid ? tc_gather_col<EXT>(cols[cc + j], s, d, p, pg) : 0.f;
                   }
                 }
               } else {
@@ -900,7 +905,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) DZ[row * (Kd0 + 1) + cc + j] = __uint_as_float(v[j]);
-                if (a.direct_src && valid) {  // desrc[k0 + row][cc .. cc + 16): this thread's registers
+                if (direct_src && valid) {  // desrc[k0 + row][cc .. cc + 16): this thread's registers
                   float4* o = reinterpret_cast<float4*>(a.desrc + (size_t)(k0 + row) * a.src_w + cc);
 #pragma unroll
                   for (int j = 0; j < 4; ++j)
@@ -949,9 +954,9 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
           }
           return n;
         };
-        if (a.direct_src) {
+        if (direct_src) {
           // already stored from the registers that held dZ_0 (step 4)
-        } else if (sw >= 32) {
+        } else if (EXT && sw >= 32) {
           for (int cc = tid & 31; cc < sw; cc += 32) {
             int z0, z1;
             float f0, f1;
@@ -974,7 +979,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
         }
         TCB_STAMP(28);
         // destination side: sequential over the row's edges, carried across tiles through dxdst itself
-        if (a.has_dst_side && a.dst_w >= 32) {  // wide: a warp per destination row, lanes along the columns that have a destination side
+        if (EXT && a.has_dst_side && a.dst_w >= 32) {  // wide: a warp per destination row, lanes along the columns that have a destination side
           for (int jj = tid >> 5; jj < n1 - n0; jj += NW / 32) {
             const int j = n0 + jj;
             const int r0 = a.tg.rowptr[j], r1 = a.tg.rowptr[j + 1];
@@ -1028,7 +1033,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
       ph_w ^= 1;
       umma::tc_fence_after();
       if (id0) collect_dw(1, a.dw_alt > 0 ? tDw + a.dw_alt : tDw);
-      else if (!a.skip_w0) collect_dw(0, tmem + a.c_dw0);
+      else if (!skip_w0) collect_dw(0, tmem + a.c_dw0);
       umma::tc_fence_before();
       worker_sync();
       TCB_STAMP(27);
