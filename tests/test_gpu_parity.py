@@ -781,7 +781,8 @@ def _wide_first_layer_case(family, aggr, dx, hidden, depth, seed=41, n=1200, e=1
 
 @pytest.mark.parametrize("family,aggr,dx,hidden,depth", [("vmh", "mean", 64, 64, 2),   # the C5 VMHConv shape: phi 130 => 64 => 64
                                                          ("vmh", "+", 47, 32, 3),      # odd input width, narrower hidden layers
-                                                         ("edge", "mean", 50, 64, 3)])  # ExplicitEdgeConv: [h_i; h_j; pos_j - pos_i]
+                                                         ("edge", "mean", 50, 64, 3),   # ExplicitEdgeConv: [h_i; h_j; pos_j - pos_i]
+                                                         ("edge", "+", 44, 48, 3)])     # n1 = 48: identity layer recomputed by MMAs (its chunks are not the gather's), GEMM projections
 def test_hoisted_first_layer_against_oracle_and_unhoisted(family, aggr, dx, hidden, depth):
     from ngpde import engine
     layer, x, ps, st, g = _wide_first_layer_case(family, aggr, dx, hidden, depth)
