@@ -181,16 +181,28 @@ struct TcDst {
   int ld;
 };
 
+#ifdef NGPDE_TCB_STAMPS
+#define TCB_DIAG 1
+#else
+#define TCB_DIAG 0
+#endif
+
 // One lane per warp polls the mbarrier, the others park on __syncwarp: 512 threads spinning on mbarrier.try_wait slow the
 // MMA-issuing lanes down by 2x and more (measured with the phase stamps).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int opt) {
   if ((threadIdx.x & 31) == 0) {
-    if (opt & 2) umma::mbar_wait(bar, parity);
+    if (TCB_DIAG && (opt & 2)) umma::mbar_wait(bar, parity);
     else umma::mbar_spin(bar, parity);  // test_wait poll: try_wait may suspend the lane and wake it ~200 cycles late
   }
   __syncwarp();
 }
 
+// Phase stamps and the polling diagnostics are a DEVELOPER build (-DNGPDE_TCB_STAMPS, tools/tcb_phases*.py): the two dozen
+// predicated stamp sites cost the C3 edge backward 2 % (0.703 -> 0.689 ms), so the shipped kernel does not contain them.
+#ifndef NGPDE_TCB_STAMPS
+#define TCB_STAMP(slot) do { } while (0)
+#define TCB_STAMP_ANY(slot) do { } while (0)
+#else
 #define TCB_STAMP(slot)                                                                          \
   do {                                                                                           \
     if (a.dbg != nullptr && blockIdx.x == 0 && tid == TCB_STAMP_TID && dbg_tile < 8) a.dbg[dbg_tile * 64 + (slot)] = clock64(); \
@@ -199,6 +211,7 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
   do {                                                                                           \
     if (a.dbg != nullptr && blockIdx.x == 0 && dbg_tile < 8) a.dbg[dbg_tile * 64 + (slot)] = clock64(); \
   } while (0)
+#endif
 constexpr int TCB_STAMP_TID = 160;  // warp 5 (rows 32..63, chunk 1): a worker that never issues MMAs
 
 // column sums of a 16-value chunk over the 32 rows of a warp (fixed butterfly order): afterwards every lane holds the
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
               tcb_issue_dgrad(lay, l, wblk_smem + 4u * a.woff[l], tDl, tAhi, tAlo);
               umma::mma_commit(&bar_d);
               TCB_STAMP_ANY(33 + 4 * l);
-              if (a.opt & 4) {  // diagnosis: when does this batch really complete?  (bar_d parity as the workers track it)
+              if (TCB_DIAG && (a.opt & 4)) {  // diagnosis: when does this batch really complete?  (bar_d parity as the workers track it)
                 umma::mbar_spin(&bar_d, pd);
                 TCB_STAMP_ANY(48 + l);
               }
@@ -820,7 +833,7 @@ __global__ void __launch_bounds__(TCB_THREADS, 1) mp_bwd_tc_kernel(const __grid_
             // warps is not served until they end (measured: tools/tcb_phases.py)
             TCB_STAMP(52 + l);
             if (do_dgrad) {
-              if (a.dbg != nullptr && blockIdx.x == 0 && dbg_tile < 8) {  // diagnosis: poll vs warp re-convergence
+              if (TCB_DIAG && a.dbg != nullptr && blockIdx.x == 0 && dbg_tile < 8) {  // diagnosis: poll vs warp re-convergence
                 if (lane == 0) {
                   umma::mbar_spin(&bar_d, ph_d);
                   if (tid == TCB_STAMP_TID) a.dbg[dbg_tile * 64 + 56 + l] = clock64();

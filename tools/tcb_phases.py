@@ -1,5 +1,8 @@
 """Phase timing of the tensor-core edge-phase backward (clock64 stamps of CTA 0, thread 64), C3 workload."""
 import os, sys
+# needs the developer build with the stamps compiled in:
+#   NGPDE_BUILD_TAG=stamps NGPDE_EXTRA_FLAGS=-DNGPDE_TCB_STAMPS python neuralgraphpde.jl_b200/build.py
+os.environ.setdefault("NGPDE_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "neuralgraphpde.jl_b200", "libngpde_stamps.so"))
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch

@@ -1,6 +1,9 @@
 """Phase timing of the tensor-core edge-phase backward on the HOISTED C5 VMHConv shape (inner MLP: identity 64x64 + 64 => 64,
 dx' = 128): clock64 stamps of CTA 0, worker warp 5."""
 import os, sys
+# needs the developer build with the stamps compiled in:
+#   NGPDE_BUILD_TAG=stamps NGPDE_EXTRA_FLAGS=-DNGPDE_TCB_STAMPS python neuralgraphpde.jl_b200/build.py
+os.environ.setdefault("NGPDE_LIB_PATH", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "neuralgraphpde.jl_b200", "libngpde_stamps.so"))
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
