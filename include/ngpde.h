@@ -46,8 +46,11 @@ enum {
 };
 
 /* aggregation operators of propagate(..., aggr) -- NNlib.scatter semantics: sequential in stored edge
- * order per destination; identity 0 / 0 / -Inf / +Inf for isolated nodes; mean = sum / float(count). */
-enum { NGPDE_AGGR_SUM = 0, NGPDE_AGGR_MEAN = 1, NGPDE_AGGR_MAX = 2, NGPDE_AGGR_MIN = 3 };
+ * order per destination; identity 0 / 0 / -Inf / +Inf / 1 for isolated nodes; mean = sum / float(count).
+ * NGPDE_AGGR_PROD is `aggr = *` (/root/reference/src/layers.jl:49,257,348,441); its pullback is NNlib's
+ * product of the OTHER messages of the destination (never a division by the message: zeros are exact).
+ * It runs on the FFMA kernels only; the persistent ODE kernels and the factored GNOConv take + and mean. */
+enum { NGPDE_AGGR_SUM = 0, NGPDE_AGGR_MEAN = 1, NGPDE_AGGR_MAX = 2, NGPDE_AGGR_MIN = 3, NGPDE_AGGR_PROD = 4 };
 
 /* layer families (/root/reference/src/layers.jl) */
 enum {

@@ -16,7 +16,7 @@ cuda_stream() = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)   # calls 
 
 # ---- enums (include/ngpde.h) ----
 const ACT_IDENTITY, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_SWISH, ACT_GELU, ACT_SOFTPLUS, ACT_ELU, ACT_LEAKYRELU = Int32.(0:8)
-const AGGR_SUM, AGGR_MEAN, AGGR_MAX, AGGR_MIN = Int32.(0:3)
+const AGGR_SUM, AGGR_MEAN, AGGR_MAX, AGGR_MIN, AGGR_PROD = Int32.(0:4)
 const FAM_EDGECONV, FAM_VMH, FAM_MPPDE, FAM_GNO = Int32.(0:3)
 const IDX_I32, IDX_I64 = Int32(0), Int32(1)
 const MAX_LAYERS = 8
@@ -26,13 +26,13 @@ const ACT = IdDict{Any, Int32}(identity => ACT_IDENTITY, NNlib.relu => ACT_RELU,
                                NNlib.tanh_fast => ACT_TANH, NNlib.sigmoid => ACT_SIGMOID, NNlib.sigmoid_fast => ACT_SIGMOID,
                                NNlib.swish => ACT_SWISH, NNlib.gelu => ACT_GELU, NNlib.softplus => ACT_SOFTPLUS,
                                NNlib.elu => ACT_ELU, NNlib.leakyrelu => ACT_LEAKYRELU)
-const AGGR = IdDict{Any, Int32}((+) => AGGR_SUM, mean => AGGR_MEAN, max => AGGR_MAX, min => AGGR_MIN)
+const AGGR = IdDict{Any, Int32}((+) => AGGR_SUM, mean => AGGR_MEAN, max => AGGR_MAX, min => AGGR_MIN, (*) => AGGR_PROD)
 
 act_code(f) = get(ACT, f) do
     throw(ArgumentError("activation $f has no fused kernel branch; supported: $(collect(keys(ACT)))"))
 end
 aggr_code(f) = get(AGGR, f) do
-    throw(ArgumentError("aggregation $f is not supported by the fused kernels (+, mean, max, min)"))
+    throw(ArgumentError("aggregation $f is not supported by the fused kernels (+, *, mean, max, min)"))
 end
 
 # ---- struct mirrors ----

@@ -92,3 +92,43 @@ function (l::GCNConv)(x::CuF32Mat, ps, st::NamedTuple, edge_weight::Union{Nothin
     y = fused_gcn(handle(g), desc, x, params, edge_weight, gw)
     return y, st
 end
+
+# ---- SpectralConv: u'_i = 1/2 sum_j cos((x_i - x_j) n / 2) cot((x_i - x_j) / 2) u_j        reference src/layers.jl:652-662 ----
+# The per-edge coefficient is static (a function of st.graph.edata.e and n only): it is evaluated once per graph in the precision
+# `e` is stored in, rounded to Float32 and cached; the call is one pass of the ordered aggregate kernel.  The pullback w.r.t. u is
+# the same kernel on the transposed graph (edges kept in their stored order, so the coefficient vector is shared).
+const SPECTRAL_COEF = IdDict{Any, CuVector{Float32}}()
+function spectral_coef(l::SpectralConv, g::GNNGraph)
+    get!(SPECTRAL_COEF, g.edata.e) do
+        e = Float64.(vec(Array(g.edata.e)))
+        CuVector{Float32}(Float32.(cos.(e .* l.n ./ 2) .* cot.(e ./ 2) ./ 2))
+    end
+end
+
+function weighted_sum(h::GraphHandle, ht::GraphHandle, x::CuF32Mat, w::CuVector{Float32})
+    y = similar(x)
+    aggregate!(h.ptr, AGGR_SUM, x, Int32(size(x, 1)), w, y)
+    return y
+end
+
+function ChainRulesCore.rrule(::typeof(weighted_sum), h::GraphHandle, ht::GraphHandle, x::CuF32Mat, w::CuVector{Float32})
+    y = weighted_sum(h, ht, x, w)
+    function weighted_sum_pullback(dy)
+        dx = similar(x)
+        aggregate!(ht.ptr, AGGR_SUM, CuMatrix{Float32}(unthunk(dy)), Int32(size(x, 1)), w, dx)
+        return NoTangent(), NoTangent(), NoTangent(), dx, NoTangent()
+    end
+    return y, weighted_sum_pullback
+end
+
+function (l::SpectralConv)(x::CuF32Mat, ps, st::NamedTuple)
+    g = st.graph
+    s, t = edge_index(g)
+    gt = GNNGraph(t, s; num_nodes = g.num_nodes)          # reversed edges, same stored order (its handle is cached like any other)
+    return weighted_sum(handle(g), handle(gt), x, spectral_coef(l, g)), st
+end
+
+function (l::SpectralConv)(x::CuVector{Float32}, ps, st::NamedTuple)
+    y, st = l(reshape(x, 1, :), ps, st)
+    return vec(y), st
+end

@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import NgpdeError
 from .graph import GNNGraph, add_self_loops, batch, copy, from_rowmajor, rand_graph, rowmajor
 from .layers import (AbstractGNNContainerLayer, AbstractGNNLayer, ExplicitEdgeConv, GCNConv, GNOConv, MPPDEConv,
-                     VMHConv, initialgraph, propagate_copy_xj, wrapgraph)
+                     SpectralConv, VMHConv, initialgraph, propagate_copy_xj, wrapgraph)
 from .lux import (NT, Chain, ComponentArray, Dense, flat_params, glorot_normal, glorot_uniform, julia_array, merge,
                   ones32, setup, zeros32)
 from .utils import drop, updategraph
@@ -16,6 +16,6 @@ from . import distributed, losses, optim, partition
 
 __all__ = [
     "AbstractGNNLayer", "AbstractGNNContainerLayer", "ExplicitEdgeConv", "GCNConv", "VMHConv", "MPPDEConv", "GNOConv",
-    "updategraph", "GNNGraph", "rand_graph", "batch", "add_self_loops", "copy", "Dense", "Chain", "setup", "NT",
+    "SpectralConv", "updategraph", "GNNGraph", "rand_graph", "batch", "add_self_loops", "copy", "Dense", "Chain", "setup", "NT",
     "ComponentArray", "NgpdeError",
 ]

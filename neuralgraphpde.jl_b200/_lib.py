@@ -15,7 +15,7 @@ MAX_LAYERS = 8
 # enums of include/ngpde.h
 ACT = {"identity": 0, "relu": 1, "tanh": 2, "sigmoid": 3, "swish": 4, "gelu": 5, "softplus": 6, "elu": 7,
        "leakyrelu": 8}
-AGGR = {"+": 0, "sum": 0, "mean": 1, "max": 2, "min": 3}
+AGGR = {"+": 0, "sum": 0, "mean": 1, "max": 2, "min": 3, "*": 4, "prod": 4}
 FAMILY = {"explicit_edge_conv": 0, "vmh_conv": 1, "mppde_conv": 2, "gno_conv": 3}
 IDX_I32, IDX_I64 = 0, 1
 GA = {"rowptr": 0, "src": 1, "dst": 2, "perm": 3, "tptr": 4, "tpos": 5, "units32": 6, "units64": 7, "units128": 8,

@@ -28,6 +28,38 @@ __global__ void transpose_weights_kernel(const float* __restrict__ params, float
 }
 
 // dparams[p] = sum over CTAs of partial[cta][p], in ascending CTA order (deterministic)
+// aggr = * (layers.jl:49,257,348,441): cotangent of message k of destination n = dmbar[n] * product of the OTHER messages of n
+// ([DEP] NNlib's pullback of scatter(*, ...): `prod(j -> src[i, j], inds)` over the destination's other edges in ascending
+// order).  Up to 16 in-edges the product is that left fold exactly; longer rows use prefix x suffix products (O(deg)).
+// One thread per (destination, channel); `msg` = the recomputed messages [E][d] in CSR order, `suf` scratch of the same size.
+__global__ void prod_cotangent_kernel(int N, int d, const int* __restrict__ rowptr, const float* __restrict__ msg,
+                                      const float* __restrict__ dmbar, float* __restrict__ suf, float* __restrict__ gedge) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * d) return;
+  const int n = (int)(idx / d), c = (int)(idx - (long long)n * d);
+  const int r0 = rowptr[n], r1 = rowptr[n + 1];
+  const float g = dmbar[idx];
+  if (r1 - r0 <= 16) {
+    for (int k = r0; k < r1; ++k) {
+      float acc = 1.f;
+      for (int j = r0; j < r1; ++j)
+        if (j != k) acc = __fmul_rn(acc, msg[(size_t)j * d + c]);
+      gedge[(size_t)k * d + c] = __fmul_rn(g, acc);
+    }
+    return;
+  }
+  float run = 1.f;
+  for (int k = r1 - 1; k >= r0; --k) {
+    suf[(size_t)k * d + c] = run;
+    run = __fmul_rn(msg[(size_t)k * d + c], run);
+  }
+  run = 1.f;
+  for (int k = r0; k < r1; ++k) {
+    gedge[(size_t)k * d + c] = __fmul_rn(g, __fmul_rn(run, suf[(size_t)k * d + c]));
+    run = __fmul_rn(run, msg[(size_t)k * d + c]);
+  }
+}
+
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int ncta, int P, float* __restrict__ out) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
@@ -485,7 +517,7 @@ int make_plan(const ngpde_graph* g, const ngpde_conv_desc& d, Plan* p) {
   NGPDE_REQUIRE(g != nullptr, "null graph handle");
   NGPDE_REQUIRE(d.dx > 0, "dx must be positive");
   NGPDE_REQUIRE(d.dhs >= 0 && d.dpos >= 0 && d.de >= 0 && d.dtheta >= 0, "negative feature width");
-  NGPDE_REQUIRE(d.aggr >= NGPDE_AGGR_SUM && d.aggr <= NGPDE_AGGR_MIN, "unknown aggregation %d", d.aggr);
+  NGPDE_REQUIRE(d.aggr >= NGPDE_AGGR_SUM && d.aggr <= NGPDE_AGGR_PROD, "unknown aggregation %d", d.aggr);
   if (int rc = make_mlp(d.phi, &p->phi, "phi")) return rc;
   if (int rc = make_mlp(d.node, &p->node, "node")) return rc;
   NGPDE_REQUIRE(p->phi.L >= 1, "phi needs at least one Dense layer");
@@ -825,6 +857,9 @@ struct BwdLayout {
   BwdSmem se, sn;
   TcBwdPhase tce, tcn;  // tensor-core variants of the two phases (when eligible)
   size_t off_wt_phi, off_wt_node, off_dmbar, off_dxdirect, off_dxdst, off_desrc, off_part_phi, off_part_node, total;
+  // aggr = *: recomputed messages, suffix products, per-edge message cotangents ([E][dm] each) + the forward kernel's tile
+  size_t off_msg = 0, off_suf = 0, off_gedge = 0;
+  int te_f = 0, smem_f = 0;
   // factored GNO
   size_t off_S = 0, off_T = 0, off_DM = 0, off_dBpart = 0, off_B = 0;
   int part_stride = 0, gno_splits = 1;
@@ -883,6 +918,15 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
   // per-edge source-side cotangents: [E][dx], or [E][n1] for a hoisted first layer (only Q's source half has a source side)
   L->off_desrc = off;     off = align256(off + sizeof(float) * g->E * (p.hoist ? p.h_n1 : d.dx));
   L->part_stride = p.hoist ? p.phi_in.n_params : p.phi.n_params;
+  if (d.aggr == NGPDE_AGGR_PROD) {
+    NGPDE_REQUIRE(!L->tce.on && !p.hoist && p.contract != 2, "internal: aggr = * runs on the FFMA kernels");
+    if (int rc = pick_tile([&](int t) { return 4 * fwd_smem(p.phi, p.contract, d.gno_in, d.gno_out, t, p.gno_Ka).floats; },
+                           &L->te_f, &L->smem_f))
+      return rc;
+    L->off_msg = off;   off = align256(off + sizeof(float) * g->E * p.dm);
+    L->off_suf = off;   off = align256(off + sizeof(float) * g->E * p.dm);
+    L->off_gedge = off; off = align256(off + sizeof(float) * g->E * p.dm);
+  }
   if (p.nhoist) {
     NGPDE_REQUIRE(L->tcn.on, "internal: hoisted node plan without a tensor-core node phase");
     off = nhoist_ws(p, g->N, off, &L->nhoist);
@@ -1557,6 +1601,34 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
         if (int rc = gno_dm_scale(dmbar, g->rowptr, desc->aggr == NGPDE_AGGR_MEAN, g->N, desc->gno_out, gDM, st)) return rc;
         if (int rc = gno_gemm(gDM, desc->gno_out, false, gB, desc->gno_out, false, gT, gR, g->N, gR, desc->gno_out, 1, nullptr, st))
           return rc;
+      }
+      if (desc->aggr == NGPDE_AGGR_PROD) {
+        // the messages once more (forward kernel, nothing aggregated), then their cotangents: dmbar x product of the others
+        float* msg = reinterpret_cast<float*>(ws + L.off_msg);
+        float* gedge = reinterpret_cast<float*>(ws + L.off_gedge);
+        const FwdSmem fs = fwd_smem(p.phi, p.contract, desc->gno_in, desc->gno_out, L.te_f, p.gno_Ka);
+        FwdArgs f{};
+        const int tf = tile_index(L.te_f);
+        f.tg = TileGraph{g->rowptr, g->src, g->dst, g->perm, g->units[tf], g->n_units[tf], (int)g->N, a.tg.gdiv};
+        fill_arrays(g, *desc, p, *io, f.arr, f.ld);
+        f.n_segs = p.n_esegs;
+        std::memcpy(f.segs, p.esegs, sizeof(p.esegs));
+        f.mlp = p.phi;
+        f.params = io->phi_params;
+        f.contract = p.contract;
+        f.gin = desc->gno_in;
+        f.gout = desc->gno_out;
+        f.aggr = desc->aggr;
+        f.dout = p.dm;
+        f.msg_out = msg;
+        f.offA = fs.offA; f.offB = fs.offB; f.offW = fs.offW; f.offH = fs.offH; f.offZt = fs.offZt;
+        f.gno_Ka = p.gno_Ka;
+        if (int rc = launch_fwd_edge(L.te_f, f, L.smem_f, g->num_sms, st)) return rc;
+        const long long tot = (long long)g->N * p.dm;
+        prod_cotangent_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>((int)g->N, p.dm, g->rowptr, msg, a.gout_ptr,
+                                                                             reinterpret_cast<float*>(ws + L.off_suf), gedge);
+        NGPDE_CUDA_TRY(cudaGetLastError());
+        a.gedge = gedge;
       }
       if (L.tce.on) {
         a.tg.unit_ptr = g->units[2];

@@ -54,6 +54,8 @@ struct FwdArgs {
   int skip_l0;          // tensor-core kernels: layer 0 is the identity of a hoisted first layer -- its activation is applied to the
                         // gathered input directly, no MMAs
   const float* addend;  // node phase (GNO): [N][dout] added before the last activation
+  float* msg_out;       // edge phase, aggr = *: when set the per-edge messages are written here ([E][dout], CSR order) and nothing is
+                        // aggregated (the backward's product-of-others pass reads them)
   int offA, offB, offW, offH;  // shared-memory float offsets
 };
 
@@ -71,6 +73,7 @@ struct BwdArgs {
   int dout;
   const float* gout_ptr;  // edge phase: dmbar [N][dout]; node phase: dy [N][dout]
   const float* fwd_out;   // edge phase: mbar (max/min mask)
+  const float* gedge;     // edge phase, aggr = *: per-edge message cotangents [E][dout] in CSR order (replace the gather of gout_ptr)
   const float* addend;    // node phase (GNO)
   float* dparams_partial; // [gridDim.x][n_params], zero-initialised
   float* dx_direct;       // node phase: [N][dx]

@@ -11,7 +11,7 @@
 namespace ngpde {
 
 __device__ __forceinline__ float aggr_identity(int aggr) {
-  return aggr == NGPDE_AGGR_MAX ? -INFINITY : (aggr == NGPDE_AGGR_MIN ? INFINITY : 0.f);
+  return aggr == NGPDE_AGGR_MAX ? -INFINITY : (aggr == NGPDE_AGGR_MIN ? INFINITY : (aggr == NGPDE_AGGR_PROD ? 1.f : 0.f));
 }
 
 template <int TE>
@@ -130,6 +130,8 @@ __device__ __forceinline__ void aggregate_tile(const float* __restrict__ M, int 
       for (int e = lo; e < hi; ++e) acc = fmaxf(acc, m[e]);
     } else if (aggr == NGPDE_AGGR_MIN) {
       for (int e = lo; e < hi; ++e) acc = fminf(acc, m[e]);
+    } else if (aggr == NGPDE_AGGR_PROD) {
+      for (int e = lo; e < hi; ++e) acc = __fmul_rn(acc, m[e]);
     } else {
       for (int e = lo; e < hi; ++e) acc = __fadd_rn(acc, m[e]);
       if (aggr == NGPDE_AGGR_MEAN && hi == r1) acc = __fdiv_rn(acc, (float)(r1 - r0));
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(NT) mp_fwd_kernel(const FwdArgs a) {
       const float ident = aggr_identity(a.aggr);
       if (a.contract == 2) {
         gno_zero_isolated(a.tg.rowptr, n0, n1, (size_t)a.gno_Ka * a.gin, a.gno_S);
-      } else {
+      } else if (a.msg_out == nullptr) {
         for (int item = tid; item < (n1 - n0) * a.dout; item += NT) {
           const int jj = item / a.dout;
           if (a.tg.rowptr[n0 + jj] == a.tg.rowptr[n0 + jj + 1]) a.out[(size_t)n0 * a.dout + item] = ident;
@@ -268,6 +270,12 @@ __global__ void __launch_bounds__(NT) mp_fwd_kernel(const FwdArgs a) {
           const int e = item / d, c = item - e * d;
           a.out[(size_t)(k0 + e) * d + c] = cur[c * C::LD + e];
         }
+      } else if (a.msg_out != nullptr) {
+        const int d = a.dout;
+        for (int item = tid; item < ne * d; item += NT) {
+          const int e = item / d, c = item - e * d;
+          a.msg_out[(size_t)(k0 + e) * d + c] = cur[c * C::LD + e];
+        }
       } else {
         aggregate_tile<TE>(cur, a.dout, a.aggr, a.tg.rowptr, n0, n1, k0, ne, a.out);
       }
@@ -348,7 +356,7 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
               v = a.gout_ptr[(size_t)(k0 + e) * d + c];
             } else {
               const int dn = s_dst[e];
-              v = a.gout_ptr[(size_t)dn * d + c];
+              v = a.gedge != nullptr ? a.gedge[(size_t)(k0 + e) * d + c] : a.gout_ptr[(size_t)dn * d + c];
               if (a.aggr == NGPDE_AGGR_MEAN) {
                 v = __fdiv_rn(v, (float)(a.tg.rowptr[dn + 1] - a.tg.rowptr[dn]));
               } else if (a.aggr == NGPDE_AGGR_MAX || a.aggr == NGPDE_AGGR_MIN) {
@@ -424,7 +432,7 @@ __global__ void __launch_bounds__(NT) mp_bwd_kernel(const BwdArgs a) {
           float v = 0.f;
           if (e < ne) {
             const int dn = s_dst[e];
-            v = a.gout_ptr[(size_t)dn * a.gout + c];
+            v = a.gedge != nullptr ? a.gedge[(size_t)(k0 + e) * a.gout + c] : a.gout_ptr[(size_t)dn * a.gout + c];
             if (a.aggr == NGPDE_AGGR_MEAN) v = __fdiv_rn(v, (float)(a.tg.rowptr[dn + 1] - a.tg.rowptr[dn]));
           }
           DM[c * C::LD + e] = v;

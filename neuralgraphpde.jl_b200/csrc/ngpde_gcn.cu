@@ -331,12 +331,13 @@ __global__ void aggregate_kernel(int N, int d, int aggr, const int* __restrict__
   if (idx >= (long long)N * d) return;
   const int r = (int)(idx / d), c = (int)(idx - (long long)r * d);
   const int q0 = rowptr[r], q1 = rowptr[r + 1];
-  float acc = aggr == NGPDE_AGGR_MAX ? -INFINITY : (aggr == NGPDE_AGGR_MIN ? INFINITY : 0.f);
+  float acc = aggr == NGPDE_AGGR_MAX ? -INFINITY : (aggr == NGPDE_AGGR_MIN ? INFINITY : (aggr == NGPDE_AGGR_PROD ? 1.f : 0.f));
   for (int q = q0; q < q1; ++q) {
     float v = x[(size_t)src[q] * d + c];
     if (w) v = __fmul_rn(w[perm[q]], v);
     if (aggr == NGPDE_AGGR_MAX) acc = fmaxf(acc, v);
     else if (aggr == NGPDE_AGGR_MIN) acc = fminf(acc, v);
+    else if (aggr == NGPDE_AGGR_PROD) acc = __fmul_rn(acc, v);
     else acc = __fadd_rn(acc, v);
   }
   if (aggr == NGPDE_AGGR_MEAN && q1 > q0) acc = __fdiv_rn(acc, (float)(q1 - q0));
@@ -565,7 +566,7 @@ extern "C" int ngpde_gcn_conv_backward(ngpde_graph_t g, const ngpde_gcn_desc* de
 extern "C" int ngpde_aggregate(ngpde_graph_t g, int32_t aggr, const float* x, int32_t d, const float* w, float* out,
                                void* stream) {
   NGPDE_REQUIRE(g && x && out && d > 0, "bad argument");
-  NGPDE_REQUIRE(aggr >= NGPDE_AGGR_SUM && aggr <= NGPDE_AGGR_MIN, "unknown aggregation %d", aggr);
+  NGPDE_REQUIRE(aggr >= NGPDE_AGGR_SUM && aggr <= NGPDE_AGGR_PROD, "unknown aggregation %d", aggr);
   if (g->N == 0) return NGPDE_OK;
   const long long total = (long long)g->N * d;
   aggregate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -143,6 +143,14 @@ class GNNGraph:
             self.w = w
         self._cache: Dict = {}
 
+    def transposed(self) -> "GNNGraph":
+        """The graph with every edge reversed, edges in the same stored order (cached; topology only)."""
+        gt = self._cache.get("transposed")
+        if gt is None:
+            gt = GNNGraph(self.t, self.s, num_nodes=self.num_nodes, num_graphs=self.num_graphs)
+            self._cache["transposed"] = gt
+        return gt
+
     # --- GNNGraph fields ---
     @property
     def s(self) -> Tensor:

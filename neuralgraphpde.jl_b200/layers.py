@@ -8,6 +8,7 @@ Julia shapes `(features, items)`, stored column-major.
 """
 from __future__ import annotations
 
+import math
 from typing import Callable, Dict, Optional, Sequence, Union
 
 import torch
@@ -41,9 +42,9 @@ def wrapgraph(g: Union[GNNGraph, Callable[[], GNNGraph]]) -> Callable[[], GNNGra
 def _aggr_name(aggr) -> str:
     if callable(aggr):
         aggr = {torch.mean: "mean", torch.sum: "+", sum: "+", max: "max", min: "min", torch.max: "max",
-                torch.min: "min"}.get(aggr, getattr(aggr, "__name__", str(aggr)))
+                torch.min: "min", torch.prod: "*"}.get(aggr, getattr(aggr, "__name__", str(aggr)))
     if aggr not in _lib.AGGR:
-        raise ValueError(f"unsupported aggregation {aggr!r}; supported: +, mean, max, min")
+        raise ValueError(f"unsupported aggregation {aggr!r}; supported: +, *, mean, max, min")
     return aggr
 
 
@@ -305,6 +306,58 @@ class GCNConv(AbstractGNNLayer):
     def __repr__(self):
         a = "" if self.activation == "identity" else f", {self.activation}"
         return f"GCNConv({self.in_chs} => {self.out_chs}{a})"
+
+
+class SpectralConv(AbstractGNNLayer):
+    """Fourier differentiation of a periodic function sampled on 2 pi j / n, j = 1..n (layers.jl:549-662):
+    u'_i = 1/2 sum_j cos((x_i - x_j) n / 2) cot((x_i - x_j) / 2) u_j as `propagate(message, g, +)` over the complete digraph
+    whose `edata.e` is x[t] - x[s].  No parameters.  The per-edge coefficient `cos(e n / 2) cot(e / 2) / 2` is static: it is
+    evaluated once per graph in the precision `e` is stored in (Float64, as the reference builds it, layers.jl:642-646),
+    rounded to float32 and cached; the call is one pass of the ordered aggregate kernel (and, in the backward, one pass over
+    the transposed graph).  The reference would promote a Float32 input to Float64 through the Float64 `e`; this path
+    computes in float32 (INTEGRATION.md)."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+        self.initialgraph = None
+
+    def initialstates(self, rng) -> NT:
+        n = self.n
+        ii = torch.arange(n).repeat_interleave(n)
+        jj = torch.arange(n).repeat(n)
+        keep = ii != jj
+        s, t = ii[keep], jj[keep]  # Graphs.edges(complete_digraph(n)): source-major, ascending target
+        x = torch.linspace(0.0, 2.0 * math.pi, n + 1, dtype=torch.float64)[1:]
+        return NT(graph=GNNGraph(s, t, num_nodes=n, edata=(x[t] - x[s]).reshape(1, -1)))
+
+    def initialparameters(self, rng, device="cpu") -> NT:
+        return NT()
+
+    def parameterlength(self) -> int:
+        return 0
+
+    def _coef(self, g: GNNGraph, dev) -> Tensor:
+        e = g.edata["e"]
+        key = ("spectral_coef", self.n, e.data_ptr(), e._version, str(dev))
+        hit = g._cache.get("spectral_coef")
+        if hit is None or hit[0] != key or hit[1] is not e:
+            ed = e.reshape(-1).to(torch.float64)
+            c = torch.cos(ed * self.n / 2) * (1.0 / torch.tan(ed / 2)) / 2  # layers.jl:654
+            hit = (key, e, c.to(torch.float32).to(dev).contiguous())
+            g._cache["spectral_coef"] = hit
+        return hit[2]
+
+    def __call__(self, x: Tensor, ps, st):
+        g: GNNGraph = st["graph"]
+        vec = x.dim() == 1  # layers.jl:659-662
+        x2 = x.reshape(1, -1) if vec else x
+        x_rm = rowmajor(x2)
+        _check_nodes(x_rm, g)
+        y = from_rowmajor(ops.WeightedSumFunction.apply(x_rm, g, self._coef(g, x.device)))
+        return (y.reshape(-1) if vec else y), st
+
+    def __repr__(self):
+        return f"SpectralConv({self.n})"
 
 
 def propagate_copy_xj(g: GNNGraph, aggr, x: Tensor, e: Optional[Tensor] = None) -> Tensor:

@@ -184,6 +184,22 @@ def aggregate(handle, aggr: str, x_rm: Tensor, w: Optional[Tensor] = None) -> Te
     return out
 
 
+class WeightedSumFunction(torch.autograd.Function):
+    """y = propagate(e_mul_xj, g, +; xj = x, e = w) with a static per-edge weight (SpectralConv, layers.jl:652-657), on the
+    ordered aggregate kernel.  The pullback w.r.t. x is the same kernel on the transposed graph (edges kept in their stored
+    order, so `w` is shared): dx_j = sum over the out-edges k of j, ascending k, of w_k dy_t(k)."""
+
+    @staticmethod
+    def forward(ctx, x_rm: Tensor, g, w: Tensor):
+        ctx.g, ctx.w = g, w
+        return aggregate(g.handle(x_rm.device), "+", x_rm, w)
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        gt = ctx.g.transposed()
+        return aggregate(gt.handle(gy.device), "+", gy.contiguous(), ctx.w), None, None
+
+
 def axpy_stages(out: Tensor, u: Optional[Tensor], ks, coefs) -> Tensor:
     """out = u + sum_i coefs[i] * ks[i]  (one fused kernel; ODE stage glue).  u = None stands for zeros; out may alias u."""
     lib = _lib.load()

@@ -199,6 +199,28 @@ def _ordered_reduce(op: str, src: Tensor, idx: np.ndarray, n: int) -> Tensor:
     return dst
 
 
+def _prod_of_others(src: Tensor, idx: np.ndarray, n: int) -> Tensor:
+    """po[:, k] = product of src[:, j] over the other positions j != k with idx[j] == idx[k], j ascending (left fold from
+    the first factor; 1 when there is none).  Vectorised by rounds like _ordered_reduce: round r multiplies in the r-th
+    member of every group for all members except that one."""
+    po = torch.ones_like(src)
+    if len(idx) == 0:
+        return po
+    rank = _rank_within_group(idx, n)
+    order = np.argsort(idx, kind="stable")
+    counts = np.bincount(idx, minlength=n)
+    starts = np.cumsum(counts) - counts
+    for r in range(int(rank.max()) + 1):
+        has = counts[idx] > r                      # positions whose group has an r-th member
+        sel = np.nonzero(has & (rank != r))[0]
+        if len(sel) == 0:
+            continue
+        member = order[starts[idx[sel]] + r]       # position of the r-th member of each selected position's group
+        sel_t = torch.from_numpy(sel)
+        po[:, sel_t] = po[:, sel_t] * src[:, torch.from_numpy(member)]
+    return po
+
+
 class _Scatter(torch.autograd.Function):
     """[DEP] NNlib.scatter(op, src, idx; dstsize=(D, n)) and its ChainRules pullback w.r.t. src."""
 
@@ -229,9 +251,10 @@ class _Scatter(torch.autograd.Function):
         elif op in ("max", "min"):
             idx_t, s, out = ctx.saved_tensors
             g = (s == out.index_select(1, idx_t)).to(gout.dtype) * gout.index_select(1, idx_t)
-        else:  # "*": product of the others
+        else:  # "*": NNlib's ∇scatter_src for * -- gather(Δ, idx)[:, k] * prod(j -> src[:, j], others of idx[k]), the
+            # others taken in ascending edge order (a left fold); never a division by src (zeros are exact)
             idx_t, s, out = ctx.saved_tensors
-            g = gout.index_select(1, idx_t) * out.index_select(1, idx_t) / s
+            g = gout.index_select(1, idx_t) * _prod_of_others(s, idx_t.numpy(), out.shape[1])
         return g, None, None, None
 
 

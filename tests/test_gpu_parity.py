@@ -110,7 +110,7 @@ def test_graph_create_rejects_bad_indices():
 # aggregation order: bit-exact against NNlib.scatter's sequential loop
 # ------------------------------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("aggr", ["+", "mean", "max", "min"])
+@pytest.mark.parametrize("aggr", ["+", "mean", "max", "min", "*"])
 @pytest.mark.parametrize("d", [1, 3, 64])
 def test_aggregate_bit_exact(aggr, d):
     rng = np.random.default_rng(7)
@@ -142,6 +142,30 @@ def test_spectralconv_known_answer_on_cuda():
         assert torch.equal(got, orc.spectral_conv(f(xs), og, n))  # and bit-exact with the oracle's float32 run
 
 
+def test_spectral_conv_layer_known_answer_and_pullback():
+    # the reference's own test, through the product layer: /root/reference/test/runtests.jl:153-162 (vector input,
+    # layers.jl:659-662), then a (3, n) matrix input with its pullback against the oracle
+    n = 100
+    layer = ngpde.SpectralConv(n)
+    ps, st = setup(0, layer, DEV)
+    assert len(ps) == 0 and st["graph"].num_edges == n * (n - 1)
+    xs = torch.from_numpy(np.linspace(0.0, 2.0 * math.pi, n + 1)[1:]).float()
+    for f, ans in ((torch.sin, torch.cos), (torch.cos, lambda v: -torch.sin(v))):
+        y, st2 = layer(f(xs).to(DEV), ps, st)
+        assert st2 is st and y.shape == (n,)
+        assert ((y.cpu() - ans(xs)) ** 2).sum().item() < 1e-3
+    rng = np.random.default_rng(3)
+    x = jl_rand(rng, 3, n, DEV).requires_grad_(True)
+    y, _ = layer(x, ps, st)
+    dy = torch.from_numpy(rng.standard_normal((3, n)).astype(np.float32)).to(DEV)
+    (dx,) = torch.autograd.grad(y, x, dy)
+    og = orc.spectral_graph(n, torch.float64)
+    xo = x.detach().cpu().double().requires_grad_(True)
+    yo = orc.spectral_conv(xo, og, n)
+    (dxo,) = torch.autograd.grad(yo, xo, dy.cpu().double())
+    assert relerr(y.detach(), yo.detach()) <= TOL and relerr(dx, dxo) <= TOL
+
+
 @pytest.mark.parametrize("tensor_cores", [0, 1])
 def test_fused_kernel_aggregation_order_bit_exact(tensor_cores):
     # phi = a 0/1 selection matrix without bias: messages are exact copies of gathered inputs, so the fused kernel's
@@ -155,7 +179,7 @@ def test_fused_kernel_aggregation_order_bit_exact(tensor_cores):
     q = (lambda v: torch.round(v * 256) / 256) if tensor_cores else (lambda v: v)
     pos = q(jl_rand(rng, 2, n))
     ngpde._lib.set_option(ngpde._lib.OPT_TENSOR_CORES, tensor_cores)
-    for aggr in ("+", "mean", "max", "min"):
+    for aggr in ("+", "mean", "max", "min") + (() if tensor_cores else ("*",)):
         g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"x": pos}).to(DEV)
         layer = ExplicitEdgeConv(Dense(8, 3, bias=False), initialgraph=g, aggr=aggr)
         ps, st = setup(0, layer, DEV)
@@ -264,6 +288,49 @@ def test_explicit_edge_conv_extra_node_fields_and_isolated_nodes():
     layer = ExplicitEdgeConv(Chain(Dense(3 + 2 + 3 + 2 + 2, 20, "gelu"), Dense(20, 6, "sigmoid")), initialgraph=g, aggr="max")
     ps, st = setup(rng, layer, DEV)
     check_layer(layer, jl_rand(rng, 3, 70, DEV), ps, st, g)
+
+
+def _prod_graph(rng, n, long_rows=(), **kw):
+    """in-degree 1..4 for most nodes, `long_rows` = in-degrees of a few long rows, the last two nodes isolated"""
+    t = np.concatenate([np.repeat(np.arange(n - 2), rng.integers(1, 5, n - 2))] + [np.full(d, 3 + 7 * i) for i, d in enumerate(long_rows)])
+    rng.shuffle(t)
+    s = rng.integers(0, n, len(t))
+    return GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, **kw)
+
+
+@pytest.mark.parametrize("last_act,long_rows", [("softplus", (20, 150)), ("relu", (18,)), ("tanh", ())])
+def test_explicit_edge_conv_prod_aggregation(last_act, long_rows):
+    # aggr = * (layers.jl:49): mbar = product of the messages (1 for an isolated node), pullback = dmbar x the product of the
+    # destination's OTHER messages -- exact zeros (relu) included; rows of 18 / 20 / 150 in-edges take the prefix x suffix
+    # form and span FFMA tiles
+    rng = np.random.default_rng(31)
+    n = 90
+    g = _prod_graph(rng, n, long_rows, ndata={"x": jl_rand(rng, 2, n)}).to(DEV)
+    layer = ExplicitEdgeConv(Chain(Dense(3 + 3 + 2, 12, "tanh"), Dense(12, 5, last_act)), initialgraph=g, aggr="*")
+    ps, st = setup(rng, layer, DEV)
+    x = jl_rand(rng, 3, n, DEV)
+    y, _ = layer(x, ps, st)
+    assert torch.equal(y[:, -2:].cpu(), torch.ones(5, 2))
+    check_layer(layer, x, ps, st, g)
+
+
+def test_prod_aggregation_other_layers():
+    rng = np.random.default_rng(32)
+    n = 64
+    g = _prod_graph(rng, n, (40,), ndata={"x": jl_rand(rng, 2, n)}).to(DEV)
+    layer = VMHConv(Chain(Dense(4 + 4 + 2, 16, "swish"), Dense(16, 6, "sigmoid")), Chain(Dense(4 + 6, 8, "tanh"), Dense(8, 3)),
+                    initialgraph=g, aggr="*")
+    ps, st = setup(rng, layer, DEV)
+    check_layer(layer, jl_rand(rng, 4, n, DEV), ps, st, g)
+    e = g.num_edges
+    g2 = _prod_graph(rng, n, (), ndata={"x": jl_rand(rng, 2, n)}).to(DEV)
+    g2 = GNNGraph(g2.s, g2.t, num_nodes=n, ndata={"x": jl_rand(rng, 2, n)}, edata={"e": jl_rand(rng, 3, g2.num_edges)}).to(DEV)
+    layer = GNOConv((6, 4), Chain(Dense(7, 16, "tanh"), Dense(16, 24, "tanh")), "swish", initialgraph=g2, aggr="*")
+    ps, st = setup(rng, layer, DEV)
+    check_layer(layer, jl_rand(rng, 6, n, DEV), ps, st, g2)
+    w = workloads.c2_mppde(DEV, n_per=17, n_graphs=5, hidden=24)
+    layer = MPPDEConv(w.layer.ϕ, w.layer.ψ, initialgraph=w.graph, aggr="*")
+    check_layer(layer, w.x, w.ps, w.st, w.graph)
 
 
 @pytest.mark.parametrize("side,hidden", [(24, 64), (9, 16)])

@@ -82,6 +82,28 @@ def test_scatter_pullbacks_match_autograd_of_dense_formulation():
         assert torch.allclose(g1, g2, atol=1e-12)
 
 
+def test_prod_scatter_pullback_is_product_of_others():
+    # [DEP] NNlib's pullback of scatter(*, src, idx): gather(dy, idx)[:, k] * prod of the OTHER sources of idx[k], ascending
+    # (a left fold) -- checked against the literal loop, with an exact zero among the sources (no division by src)
+    rng = np.random.default_rng(2)
+    n, e, d = 7, 30, 2
+    idx = rng.integers(0, n - 1, e)
+    src_np = rng.standard_normal((d, e)).astype(np.float32)
+    src_np[:, 4] = 0.0
+    src = torch.from_numpy(src_np).requires_grad_(True)
+    dy = torch.from_numpy(rng.standard_normal((d, n)).astype(np.float32))
+    (got,) = torch.autograd.grad(orc.scatter("*", src, idx, n), src, dy)
+    ref = np.zeros((d, e), dtype=np.float32)
+    for k in range(e):
+        acc = None
+        for j in range(e):
+            if j != k and idx[j] == idx[k]:
+                acc = src_np[:, j].copy() if acc is None else acc * src_np[:, j]
+        ref[:, k] = dy[:, idx[k]].numpy() * (np.ones(d, dtype=np.float32) if acc is None else acc)
+    assert np.array_equal(got.numpy(), ref)
+    assert np.isfinite(got.numpy()).all()
+
+
 def test_csr_and_transpose_layouts():
     rng = np.random.default_rng(2)
     n, e = 11, 60
