@@ -264,7 +264,7 @@ def roofline_block(workload, w, prof, K, paths, step_ms, peaks, edges_launch, no
         "pipe": ("tcgen05 3xTF32 (fp32-accurate split: 3 TF32 MMAs per product; peak = bf16 peak / 6)" if on_tc else
                  "fp32 FFMA (fp32-accurate; tolerance 1e-5 excludes plain TF32/BF16)"),
         "pipe_peak_tflops": pipe_peak, "pipe_frac": ach_tflops / pipe_peak,
-        "kernel_paths": {k: {1: "tcgen05", 0: "ffma", 2: "factored (ffma + fp32 gemm)", -1: "none"}[v] for k, v in paths.items()},
+        "kernel_paths": {k: {1: "tcgen05", 0: "ffma", 2: "factored (ffma + fp32 gemm)", 3: "tcgen05 GEMM per Dense layer", -1: "none"}[v] for k, v in paths.items()},
         "avg_launch_ms": dom_ms, "algorithmic_flops_per_launch": alg_flops,
         "units_per_launch": {"edges": int(edges_launch), "nodes": int(nodes_launch)},
         "share_of_step_kernel_time": (prof[dom][0] / K) / step_kernel_ms if step_kernel_ms else None,

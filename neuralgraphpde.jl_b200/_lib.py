@@ -152,6 +152,7 @@ def load() -> C.CDLL:
 OPT_TENSOR_CORES = 0
 OPT_GNO_FACTORED = 1
 OPT_HOIST = 3
+OPT_LAYERED = 4
 
 
 def set_option(option: int, value: int) -> None:

@@ -7,6 +7,7 @@
 
 #include "ngpde_conv_launch.cuh"
 #include "ngpde_gno_tile.cuh"
+#include "ngpde_layered.cuh"
 #include "ngpde_tc_layout.cuh"
 #include "ngpde_gno.cuh"
 
@@ -387,8 +388,12 @@ struct Plan {
   bool nhoist = false;
   MlpDev node_in{}, mlp_u{}, mlp_v{};
   int nh_n1 = 0, nh_row_x = 0, nh_row_m = 0;
+  // Layer-by-layer evaluation on the tcgen05 GEMM (ngpde_layered.cuh): MLPs with a layer wider than the fused tensor-core
+  // kernels take (outputs > 64), + / mean aggregation, enough edges to fill the GEMM grid
+  bool layered = false;
 };
-bool g_hoist = true;  // NGPDE_OPT_HOIST
+bool g_hoist = true;    // NGPDE_OPT_HOIST
+bool g_layered = true;  // NGPDE_OPT_LAYERED
 
 void push_seg(Seg* segs, int* n, int* row, int kind, int arr, int col, int width) {
   if (width <= 0) return;
@@ -607,6 +612,13 @@ int make_plan(const ngpde_graph* g, const ngpde_conv_desc& d, Plan* p) {
   }
   plan_hoist(d, p);
   plan_nhoist(d, p);
+  {
+    int widest = 0;
+    for (int l = 1; l <= p->phi.L; ++l) widest = std::max(widest, p->phi.dims[l]);
+    p->layered = g_layered && tc_get_enabled() && !p->contract && !p->hoist && !p->nhoist && widest > 64 && g->E >= 8192 &&
+                 (d.aggr == NGPDE_AGGR_SUM || d.aggr == NGPDE_AGGR_MEAN) && layered::eligible(p->phi) &&
+                 (!p->has_node || layered::eligible(p->node));
+  }
   return NGPDE_OK;
 }
 
@@ -860,6 +872,8 @@ struct BwdLayout {
   // aggr = *: recomputed messages, suffix products, per-edge message cotangents ([E][dm] each) + the forward kernel's tile
   size_t off_msg = 0, off_suf = 0, off_gedge = 0;
   int te_f = 0, smem_f = 0;
+  layered::Ws lye, lyn;  // Plan::layered
+  size_t off_layered = 0;
   // factored GNO
   size_t off_S = 0, off_T = 0, off_DM = 0, off_dBpart = 0, off_B = 0;
   int part_stride = 0, gno_splits = 1;
@@ -878,6 +892,27 @@ struct BwdLayout {
 int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, BwdLayout* L) {
   L->te_e = 0; L->smem_e = 0; L->grid_e = 0;
   L->dxe = p.hoist ? 2 * p.h_n1 : d.dx;
+  if (p.layered) {
+    L->te_n = 0; L->smem_n = 0; L->grid_n = 0;
+    L->tce = TcBwdPhase{};
+    L->tcn = TcBwdPhase{};
+    size_t off = 0;
+    L->off_wt_phi = L->off_wt_node = L->off_dxdst = L->off_desrc = 0;
+    L->off_dmbar = off;     off = align256(off + (p.has_node ? sizeof(float) * g->N * p.dm : 0));
+    L->off_dxdirect = off;  off = align256(off + (p.has_node ? sizeof(float) * g->N * d.dx : 0));
+    // sized for a call without io.state: kept buffers (recomputed here) followed by the scratch, per phase, sharing the region
+    layered::plan_kept(layered::make_phase(p.phi), g->E, off, &L->lye);
+    layered::plan_scratch(layered::make_phase(p.phi), g->E, true, true, g->num_sms, L->lye.kept_end, &L->lye);
+    if (p.has_node) {
+      layered::plan_kept(layered::make_phase(p.node), g->N, off, &L->lyn);
+      layered::plan_scratch(layered::make_phase(p.node), g->N, true, true, g->num_sms, L->lyn.kept_end, &L->lyn);
+    }
+    L->off_layered = off;
+    off = std::max(L->lye.end, L->lyn.end);
+    L->off_part_phi = L->off_part_node = off;
+    L->total = off;
+    return NGPDE_OK;
+  }
   if (tc_bwd_make(p.hoist ? p.phi_in : p.phi, p.contract, false, false, d.aggr, p.hoist || p.edge_need_dz0, &L->tce)) {
     L->tce.grid = std::max(1, std::min(g->n_units[2], g->num_sms));
     L->grid_e = L->tce.grid;
@@ -1152,26 +1187,44 @@ struct FwdPlan {
   size_t ws_bytes = 0;
   size_t off_S = 0, off_B = 0;
   HoistWs hoist;
+  layered::Ws lye, lyn;  // Plan::layered
 };
 
 // layout of the optional ngpde_conv_io.state buffer: the hoisted projections and folded parameters, kept for the backward
 struct StatePlan {
   HoistWs hoist;
   NodeHoistWs nhoist;
+  layered::Ws lye, lyn;  // Plan::layered: the kept activations of both phases (up to 8 GiB; beyond that the backward recomputes)
   size_t bytes = 0;
 };
-StatePlan state_plan(const Plan& p, int64_t N) {
+StatePlan state_plan(const Plan& p, int64_t N, int64_t E = 0) {
   StatePlan sp;
   size_t off = 0;
+  if (p.layered) {
+    layered::plan_kept(layered::make_phase(p.phi), E, 0, &sp.lye);
+    off = sp.lye.kept_end;
+    if (p.has_node) {
+      layered::plan_kept(layered::make_phase(p.node), N, off, &sp.lyn);
+      off = sp.lyn.kept_end;
+    }
+    sp.bytes = off <= (size_t(8) << 30) ? off : 0;
+    return sp;
+  }
   if (p.hoist) off = hoist_ws(p, N, off, &sp.hoist);
   if (p.nhoist) off = nhoist_ws(p, N, off, &sp.nhoist);
   sp.bytes = off;
   return sp;
 }
 
-FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin) {
+FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin, int64_t E = 0) {
   FwdPlan f;
   size_t off = 0;
+  if (p.layered) {  // the two phases run one after the other: they share the region (sized for a call without io.state)
+    layered::plan_scratch(layered::make_phase(p.phi), E, false, false, 1, 0, &f.lye);
+    if (p.has_node) layered::plan_scratch(layered::make_phase(p.node), N, false, false, 1, 0, &f.lyn);
+    f.ws_bytes = std::max(f.lye.end, f.lyn.end);
+    return f;
+  }
   if (p.hoist) off = hoist_ws(p, N, off, &f.hoist);
   const MlpDev& ephi = p.hoist ? p.phi_in : p.phi;
   // max/min: the backward's tie mask compares recomputed messages with the forward's bit for bit, so both must run
@@ -1202,6 +1255,101 @@ FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin) {
   return f;
 }
 
+
+// ---- Plan::layered: every Dense layer as one tcgen05 GEMM over all edges / nodes (ngpde_layered.cuh) ----
+layered::Gather layered_gather(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, const ngpde_conv_io& io, bool node) {
+  layered::Gather ga{};
+  fill_arrays(g, d, p, io, ga.arr, ga.ld);
+  ga.n_segs = node ? p.n_nsegs : p.n_esegs;
+  std::memcpy(ga.segs, node ? p.nsegs : p.esegs, sizeof(p.esegs));
+  ga.src = node ? nullptr : g->src;
+  ga.dst = node ? nullptr : g->dst;
+  ga.perm = node ? nullptr : g->perm;
+  ga.gdiv = (int)std::max<int64_t>(1, (node ? g->N : g->E) / std::max<int64_t>(1, g->G));
+  return ga;
+}
+
+int layered_forward(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, const ngpde_conv_io& io, const FwdPlan& fp,
+                    char* ws, cudaStream_t st) {
+  NGPDE_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
+  NGPDE_REQUIRE(aligned16(io.mbar) && (!p.has_node || aligned16(io.y)), "layered evaluation: mbar and y must be 16-byte aligned");
+  // with io.state the activations the backward needs are kept there (ngpde_conv_state_bytes), else nothing is kept
+  const StatePlan sp = state_plan(p, g->N, g->E);
+  const bool keep = io.state != nullptr && sp.bytes > 0;
+  NGPDE_REQUIRE(!keep || aligned16(io.state), "io.state must be 16-byte aligned");
+  char* kbase = keep ? static_cast<char*>(io.state) : ws;
+  {
+    ProfScope prof(NGPDE_PROF_FWD_EDGE, st);
+    const layered::Phase ph = layered::make_phase(p.phi);
+    layered::Ws w = keep ? sp.lye : fp.lye;
+    if (keep) layered::plan_scratch(ph, g->E, false, true, 1, 0, &w);
+    const float* msg = nullptr;
+    if (int rc = layered::run_forward(ph, w, kbase, ws, layered_gather(g, d, p, io, false), g->E, io.phi_params, keep, nullptr, &msg, st))
+      return rc;
+    const long long tot = (long long)g->N * p.dm;
+    layered::aggregate_rows_kernel<<<layered::blocks(tot, 256), 256, 0, st>>>((int)g->N, p.dm, d.aggr == NGPDE_AGGR_MEAN, g->rowptr,
+                                                                              msg, io.mbar);
+  }
+  if (p.has_node) {
+    ProfScope prof(NGPDE_PROF_FWD_NODE, st);
+    const layered::Phase ph = layered::make_phase(p.node);
+    layered::Ws w = keep ? sp.lyn : fp.lyn;
+    if (keep) layered::plan_scratch(ph, g->N, false, true, 1, 0, &w);
+    if (int rc = layered::run_forward(ph, w, kbase, ws, layered_gather(g, d, p, io, true), g->N, io.node_params, keep, io.y, nullptr, st))
+      return rc;
+  }
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
+int layered_backward(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, const ngpde_conv_io& io, const BwdLayout& L,
+                     char* ws, cudaStream_t st) {
+  float* dmbar = p.has_node ? reinterpret_cast<float*>(ws + L.off_dmbar) : nullptr;
+  float* dxdirect = p.has_node ? reinterpret_cast<float*>(ws + L.off_dxdirect) : nullptr;
+  // the forward's activations: left in io.state by the forward call, or recomputed here into the workspace
+  const StatePlan sp = state_plan(p, g->N, g->E);
+  const bool kept = io.state != nullptr && sp.bytes > 0;
+  NGPDE_REQUIRE(!kept || aligned16(io.state), "io.state must be 16-byte aligned");
+  char* kbase = kept ? static_cast<char*>(io.state) : ws;
+  if (p.has_node) {
+    ProfScope prof(NGPDE_PROF_BWD_NODE, st);
+    const layered::Phase ph = layered::make_phase(p.node);
+    const layered::Gather ga = layered_gather(g, d, p, io, true);
+    layered::Ws w = L.lyn;
+    if (kept) { w = sp.lyn; layered::plan_scratch(ph, g->N, true, true, g->num_sms, L.off_layered, &w); }
+    else if (int rc = layered::run_forward(ph, w, kbase, ws, ga, g->N, io.node_params, true, nullptr, nullptr, st)) return rc;
+    const float* dz0 = nullptr;
+    if (int rc = layered::run_backward(ph, w, kbase, ws, g->N, io.dy, nullptr, nullptr, true, g->num_sms, io.dnode_params, &dz0, st))
+      return rc;
+    const long long tot = (long long)g->N * (d.dx + p.dm);
+    layered::node_split_kernel<<<layered::blocks(tot, 256), 256, 0, st>>>(ga, (int)g->N, d.dx, p.dm, ph.ld[0], dz0, dxdirect, dmbar);
+  }
+  {
+    ProfScope prof(NGPDE_PROF_BWD_EDGE, st);
+    const layered::Phase ph = layered::make_phase(p.phi);
+    const layered::Gather ga = layered_gather(g, d, p, io, false);
+    layered::Ws w = L.lye;
+    if (kept) { w = sp.lye; layered::plan_scratch(ph, g->E, true, true, g->num_sms, L.off_layered, &w); }
+    else if (int rc = layered::run_forward(ph, w, kbase, ws, ga, g->E, io.phi_params, true, nullptr, nullptr, st)) return rc;
+    const float* dz0 = nullptr;
+    if (int rc = layered::run_backward(ph, w, kbase, ws, g->E, p.has_node ? dmbar : io.dy, g->dst,
+                                       d.aggr == NGPDE_AGGR_MEAN ? g->rowptr : nullptr, p.edge_need_dz0, g->num_sms,
+                                       io.dphi_params, &dz0, st))
+      return rc;
+    const long long tot = (long long)g->N * d.dx;
+    if (p.edge_need_dz0) {
+      layered::edge_dx_kernel<<<layered::blocks(tot, 256), 256, 0, st>>>(ga, (int)g->N, d.dx, ph.ld[0], g->rowptr, g->tptr, g->tpos, dz0,
+                                                                         dxdirect, io.dx);
+    } else if (dxdirect) {
+      NGPDE_CUDA_TRY(cudaMemcpyAsync(io.dx, dxdirect, sizeof(float) * tot, cudaMemcpyDeviceToDevice, st));
+    } else {
+      NGPDE_CUDA_TRY(cudaMemsetAsync(io.dx, 0, sizeof(float) * tot, st));
+    }
+  }
+  NGPDE_CUDA_TRY(cudaGetLastError());
+  return NGPDE_OK;
+}
+
 }  // namespace
 
 extern "C" int ngpde_set_option(int32_t option, int32_t value) {
@@ -1210,6 +1358,7 @@ extern "C" int ngpde_set_option(int32_t option, int32_t value) {
     case NGPDE_OPT_GNO_FACTORED: g_gno_factored = value != 0; return NGPDE_OK;
     case NGPDE_OPT_DEBUG_SKIP: g_debug_skip = value; return NGPDE_OK;
     case NGPDE_OPT_HOIST: g_hoist = value != 0; return NGPDE_OK;
+    case NGPDE_OPT_LAYERED: g_layered = value != 0; return NGPDE_OK;
     default: set_error("unknown option %d", option); return NGPDE_ERR_INVALID;
   }
 }
@@ -1218,7 +1367,7 @@ extern "C" size_t ngpde_conv_workspace_bytes(ngpde_graph_t g, const ngpde_conv_d
   if (!g || !desc) return 0;
   Plan p;
   if (make_plan(g, *desc, &p)) return 0;
-  if (!backward) return fwd_plan(p, desc->aggr, g->N, desc->gno_in).ws_bytes + 256;
+  if (!backward) return fwd_plan(p, desc->aggr, g->N, desc->gno_in, g->E).ws_bytes + 256;
   BwdLayout L;
   if (bwd_layout(g, *desc, p, &L)) return 0;
   return L.total + 256;
@@ -1228,7 +1377,7 @@ extern "C" size_t ngpde_conv_state_bytes(ngpde_graph_t g, const ngpde_conv_desc*
   if (!g || !desc) return 0;
   Plan p;
   if (make_plan(g, *desc, &p)) return 0;
-  const size_t b = state_plan(p, g->N).bytes;
+  const size_t b = state_plan(p, g->N, g->E).bytes;
   return b ? b + 256 : 0;
 }
 
@@ -1236,9 +1385,14 @@ extern "C" int ngpde_conv_kernel_paths(ngpde_graph_t g, const ngpde_conv_desc* d
   NGPDE_REQUIRE(g && desc && paths, "null argument");
   Plan p;
   if (int rc = make_plan(g, *desc, &p)) return rc;
-  const FwdPlan fp = fwd_plan(p, desc->aggr, g->N, desc->gno_in);
+  const FwdPlan fp = fwd_plan(p, desc->aggr, g->N, desc->gno_in, g->E);
   BwdLayout L;
   if (int rc = bwd_layout(g, *desc, p, &L)) return rc;
+  if (p.layered) {  // 3: one tcgen05 GEMM per Dense layer (ngpde_layered.cuh)
+    paths[NGPDE_PROF_FWD_EDGE] = paths[NGPDE_PROF_BWD_EDGE] = 3;
+    paths[NGPDE_PROF_FWD_NODE] = paths[NGPDE_PROF_BWD_NODE] = p.has_node ? 3 : -1;
+    return NGPDE_OK;
+  }
   paths[NGPDE_PROF_FWD_EDGE] = fp.edge.on ? 1 : (p.contract == 2 ? 2 : 0);
   paths[NGPDE_PROF_FWD_NODE] = p.has_node ? (fp.node.on ? 1 : 0) : -1;
   paths[NGPDE_PROF_BWD_EDGE] = L.tce.on ? 1 : (p.contract == 2 ? 2 : 0);
@@ -1254,7 +1408,7 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
   if (g->N == 0) return NGPDE_OK;
   if (int rc = check_io(*desc, p, *io, false)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const FwdPlan fp = fwd_plan(p, desc->aggr, g->N, desc->gno_in);
+  const FwdPlan fp = fwd_plan(p, desc->aggr, g->N, desc->gno_in, g->E);
   if (fp.ws_bytes > 0 && (workspace == nullptr || workspace_bytes < fp.ws_bytes)) {
     set_error("forward workspace too small: %zu bytes given, %zu needed (ngpde_conv_workspace_bytes(g, desc, 0))",
               workspace_bytes, fp.ws_bytes);
@@ -1262,12 +1416,14 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
   }
   char* fws = static_cast<char*>(workspace);
   // the hoisted projections live in io->state when the caller provides it (the backward then reuses them), else in the workspace
-  const StatePlan sp = state_plan(p, g->N);
+  const StatePlan sp = state_plan(p, g->N, g->E);
   const bool keep = io->state != nullptr && sp.bytes > 0;
   NGPDE_REQUIRE(!keep || aligned16(io->state), "io.state must be 16-byte aligned");
   char* hbase = keep ? static_cast<char*>(io->state) : fws;
   const HoistWs& hw = keep ? sp.hoist : fp.hoist;
   const NodeHoistWs& nhw = keep ? sp.nhoist : fp.nhoist;
+
+  if (p.layered) return layered_forward(g, *desc, p, *io, fp, fws, st);
 
   // ---- edge phase ----
   int te = 0, smem = 0;
@@ -1397,8 +1553,9 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
   if (g->N == 0) return NGPDE_OK;
   char* ws = static_cast<char*>(workspace);
   NGPDE_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "workspace must be 16-byte aligned");
+  if (p.layered) return layered_backward(g, *desc, p, *io, L, ws, st);
   // hoisted projections: left in io->state by the forward, or recomputed here
-  const StatePlan sp = state_plan(p, g->N);
+  const StatePlan sp = state_plan(p, g->N, g->E);
   const bool kept = io->state != nullptr && sp.bytes > 0;
   NGPDE_REQUIRE(!kept || aligned16(io->state), "io.state must be 16-byte aligned");
   char* hbase = kept ? static_cast<char*>(io->state) : ws;

@@ -794,6 +794,51 @@ def test_chain_runner_matches_the_autograd_path():
     assert r.handle is not None and ngpde._lib.kernel_paths(r.handle, r.desc)["fwd_edge"] in (0, 1)
 
 
+@pytest.mark.parametrize("layered", [1, 0])
+@pytest.mark.parametrize("family", ["mppde", "vmh", "edgeconv"])
+def test_wide_layers_gemm_per_layer_and_fused_paths(family, layered):
+    """MLPs with an output wider than 64 columns (outside the fused tcgen05 kernels) and >= 8192 edges run one tcgen05 GEMM
+    per Dense layer (csrc/ngpde_layered.cuh, path code 3); NGPDE_OPT_LAYERED = 0 keeps them on the fused FFMA kernels.  Both
+    must meet the oracle bar.  Graph: duplicates, isolated nodes, one destination with 700 in-edges; phi input width not a
+    multiple of 4; swish / gelu (act' from the pre-activation) and tanh / identity layers."""
+    from ngpde import engine
+    rng = np.random.default_rng(41)
+    if family == "mppde":
+        w = workloads.c2_mppde(DEV, n_per=72, n_graphs=60, hidden=96)  # 8,520 edges, theta per graph, K = 2*96 + 2 + 2 = 196
+        layer, x, ps, st, g = w.layer, w.x, w.ps, w.st, w.graph
+    else:
+        n, e = 1500, 9000
+        s, t = rng.integers(0, n - 4, e), rng.integers(0, n - 4, e)
+        t[:700] = 11
+        g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"q": jl_rand(rng, 1, n), "x": jl_rand(rng, 2, n)}).to(DEV)
+        if family == "vmh":
+            layer = VMHConv(Chain(Dense(5 + 1 + 5 + 1 + 2, 100, "gelu"), Dense(100, 72, "tanh"), Dense(72, 12)),
+                            Chain(Dense(5 + 12, 68, "swish"), Dense(68, 8, "sigmoid")), initialgraph=g, aggr="+")
+        else:
+            layer = ExplicitEdgeConv(Chain(Dense(5 + 1 + 5 + 1 + 2, 80, "swish"), Dense(80, 16, bias=False)), initialgraph=g, aggr="mean")
+        ps, st = setup(rng, layer, DEV)
+        x = jl_rand(rng, 5, n, DEV)
+    ngpde._lib.set_option(ngpde._lib.OPT_LAYERED, layered)
+    try:
+        r = engine.RhsRunner(layer, x, ps, st)
+        paths = ngpde._lib.kernel_paths(r.handle, r.desc)
+        assert paths["fwd_edge"] == paths["bwd_edge"] == (3 if layered else 0)
+        check_layer(layer, x, ps, st, g)
+        if layered:
+            # io.state keeps the forward's activations for the backward; a binder that passes NULL gets a recomputation: same bits
+            assert r.state is not None
+            r.dy.copy_(torch.from_numpy(rng.standard_normal(tuple(r.dy.shape)).astype(np.float32)))
+            r.forward(); r.backward()
+            torch.cuda.synchronize()
+            kept = (r.y.clone(), r.dx.clone(), r.dparams.clone())
+            r.io.state = None
+            r.forward(); r.backward()
+            torch.cuda.synchronize()
+            assert torch.equal(kept[0], r.y) and torch.equal(kept[1], r.dx) and torch.equal(kept[2], r.dparams)
+    finally:
+        ngpde._lib.set_option(ngpde._lib.OPT_LAYERED, 1)
+
+
 def test_kernel_path_query_reports_the_engine_that_runs():
     """ngpde_conv_kernel_paths: C3 runs all four fused kernels on tcgen05; with the option off, or for GNOConv's bilinear
     contraction, the FP32-FFMA engine takes over (bench.py labels its roofline line with this)."""
