@@ -1306,6 +1306,7 @@ int layered_backward(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan&
                      char* ws, cudaStream_t st) {
   float* dmbar = p.has_node ? reinterpret_cast<float*>(ws + L.off_dmbar) : nullptr;
   float* dxdirect = p.has_node ? reinterpret_cast<float*>(ws + L.off_dxdirect) : nullptr;
+  NGPDE_REQUIRE(aligned16(io.dy), "layered evaluation: dy must be 16-byte aligned");
   // the forward's activations: left in io.state by the forward call, or recomputed here into the workspace
   const StatePlan sp = state_plan(p, g->N, g->E);
   const bool kept = io.state != nullptr && sp.bytes > 0;

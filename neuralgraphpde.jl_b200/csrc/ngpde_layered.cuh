@@ -132,32 +132,61 @@ struct Gather {
   int gdiv;
 };
 
-// Z0[row][f]: the segment list evaluated for one row (edge k in CSR order, or node), pad columns zero
-__global__ void assemble_kernel(Gather g, long long rows, int d0, int ld0, float* __restrict__ Z) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * ld0) return;
-  const long long r = idx / ld0;
-  const int f = (int)(idx - r * ld0);
-  float v = 0.f;
-  if (f < d0) {
-    const long long s = g.src ? g.src[r] : r, d = g.dst ? g.dst[r] : r, pe = g.perm ? g.perm[r] : r;
-    for (int si = 0; si < g.n_segs; ++si) {
-      const Seg sg = g.segs[si];
-      if (f < sg.row || f >= sg.row + sg.width) continue;
-      const float* __restrict__ A = g.arr[sg.arr] + sg.col + (f - sg.row);
-      const int ld = g.ld[sg.arr];
-      switch (sg.kind) {
-        case SEG_DST: v = A[(size_t)d * ld]; break;
-        case SEG_SRC: v = A[(size_t)s * ld]; break;
-        case SEG_SMD: v = A[(size_t)s * ld] - A[(size_t)d * ld]; break;
-        case SEG_DMS: v = A[(size_t)d * ld] - A[(size_t)s * ld]; break;
-        case SEG_EDGE: v = A[(size_t)pe * ld]; break;
-        default: v = A[(size_t)(pe / g.gdiv) * ld]; break;  // SEG_GRAPH
-      }
-      break;
+__device__ __forceinline__ float assemble_one(const Gather& g, int f, long long s, long long d, long long pe) {
+  for (int si = 0; si < g.n_segs; ++si) {
+    const Seg sg = g.segs[si];
+    if (f < sg.row || f >= sg.row + sg.width) continue;
+    const float* __restrict__ A = g.arr[sg.arr] + sg.col + (f - sg.row);
+    const int ld = g.ld[sg.arr];
+    switch (sg.kind) {
+      case SEG_DST: return A[(size_t)d * ld];
+      case SEG_SRC: return A[(size_t)s * ld];
+      case SEG_SMD: return A[(size_t)s * ld] - A[(size_t)d * ld];
+      case SEG_DMS: return A[(size_t)d * ld] - A[(size_t)s * ld];
+      case SEG_EDGE: return A[(size_t)pe * ld];
+      default: return A[(size_t)(pe / g.gdiv) * ld];  // SEG_GRAPH
     }
   }
-  Z[idx] = v;
+  return 0.f;
+}
+
+// Z0[row][f]: the segment list evaluated for one row (edge k in CSR order, or node), pad columns zero.  One thread per four
+// columns: a quad inside one segment whose source is 16-byte aligned (`vec` bit of its array) moves as float4.
+__global__ void assemble_kernel(Gather g, long long rows, int d0, int ld0, int vec, float* __restrict__ Z) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q4 = ld0 >> 2;
+  if (idx >= rows * q4) return;
+  const long long r = idx / q4;
+  const int f = (int)(idx - r * q4) * 4;
+  const long long s = g.src ? g.src[r] : r, d = g.dst ? g.dst[r] : r, pe = g.perm ? g.perm[r] : r;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool done = false;
+  for (int si = 0; si < g.n_segs; ++si) {
+    const Seg sg = g.segs[si];
+    if (f < sg.row || f + 3 >= sg.row + sg.width) continue;
+    const int c = sg.col + (f - sg.row);
+    if (!((vec >> sg.arr) & 1) || (c & 3)) break;
+    const float* __restrict__ A = g.arr[sg.arr] + c;
+    const int ld = g.ld[sg.arr];
+    auto ld4 = [&](long long row) { return __ldg(reinterpret_cast<const float4*>(A + (size_t)row * ld)); };
+    switch (sg.kind) {
+      case SEG_DST: v = ld4(d); break;
+      case SEG_SRC: v = ld4(s); break;
+      case SEG_SMD: { const float4 a = ld4(s), b = ld4(d); v = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); break; }
+      case SEG_DMS: { const float4 a = ld4(d), b = ld4(s); v = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); break; }
+      case SEG_EDGE: v = ld4(pe); break;
+      default: v = ld4(pe / g.gdiv); break;
+    }
+    done = true;
+    break;
+  }
+  if (!done) {
+    if (f < d0) v.x = assemble_one(g, f, s, d, pe);
+    if (f + 1 < d0) v.y = assemble_one(g, f + 1, s, d, pe);
+    if (f + 2 < d0) v.z = assemble_one(g, f + 2, s, d, pe);
+    if (f + 3 < d0) v.w = assemble_one(g, f + 3, s, d, pe);
+  }
+  *reinterpret_cast<float4*>(Z + (size_t)r * ld0 + f) = v;
 }
 
 // u = p + b (kept when `U` is given), z = act(u);  P, U, Zout are [rows][n]; U / Zout may alias P
@@ -192,28 +221,78 @@ __global__ void aggregate_rows_kernel(int N, int d, int mean, const int* __restr
 
 // Gp[r][c] = Gin[row(r)][c] (/ deg) * act'(U[r][c]);  block b owns rows [64 b, 64 b + 64): its column sums go to cpart[b][c].
 // row_of != null: the edge phase's last layer -- Gin = dmbar is indexed by the edge's destination, divided by the in-degree
-// for the mean (true division, like the fused kernels).
-__global__ void actgrad_kernel(const float* __restrict__ Gin, const float* __restrict__ U, int act, long long rows, int n,
-                               const int* __restrict__ row_of, const int* __restrict__ rowptr_mean, float* __restrict__ Gp,
-                               float* __restrict__ cpart) {
+// for the mean (true division, like the fused kernels).  256 threads = RG row groups x (n / 4) column quads (float4 accesses,
+// n / 4 <= 256; wider rows loop over the quads with RG = 1); a group takes every RG-th row of the chunk in ascending order, the
+// groups' sums are added in ascending group order: a fixed summation order for a given n.
+__global__ void __launch_bounds__(256) actgrad_kernel(const float* __restrict__ Gin, const float* __restrict__ U, int act,
+                                                      long long rows, int n, const int* __restrict__ row_of,
+                                                      const int* __restrict__ rowptr_mean, float* __restrict__ Gp,
+                                                      float* __restrict__ cpart) {
+  __shared__ float4 sm[256];
   const long long r0 = (long long)blockIdx.x * CHUNK_ROWS;
-  const long long r1 = r0 + CHUNK_ROWS < rows ? r0 + CHUNK_ROWS : rows;
-  for (int c = threadIdx.x; c < n; c += blockDim.x) {
-    float acc = 0.f;
-    for (long long r = r0; r < r1; ++r) {
-      float g;
-      if (row_of) {
-        const int dn = row_of[r];
-        g = Gin[(size_t)dn * n + c];
-        if (rowptr_mean) g = __fdiv_rn(g, (float)(rowptr_mean[dn + 1] - rowptr_mean[dn]));
-      } else {
-        g = Gin[(size_t)r * n + c];
+  const int nr = (int)((r0 + CHUNK_ROWS < rows ? r0 + CHUNK_ROWS : rows) - r0);
+  const int n4 = n >> 2;
+  const int Q = n4 < 256 ? n4 : 256, RG = 256 / Q;
+  const int q0 = threadIdx.x % Q, rg = threadIdx.x / Q;
+  for (int qb = 0; qb < n4; qb += Q) {
+    const int q = qb + q0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rg < RG && q < n4) {
+#pragma unroll 4
+      for (int i = rg; i < nr; i += RG) {
+        const long long r = r0 + i;
+        float4 g;
+        if (row_of) {
+          const int dn = row_of[r];
+          g = __ldg(reinterpret_cast<const float4*>(Gin + (size_t)dn * n) + q);
+          if (rowptr_mean) {
+            const float deg = (float)(rowptr_mean[dn + 1] - rowptr_mean[dn]);
+            g.x = __fdiv_rn(g.x, deg); g.y = __fdiv_rn(g.y, deg); g.z = __fdiv_rn(g.z, deg); g.w = __fdiv_rn(g.w, deg);
+          }
+        } else {
+          g = *(reinterpret_cast<const float4*>(Gin + (size_t)r * n) + q);
+        }
+        if (act != NGPDE_ACT_IDENTITY) {
+          const float4 u = *(reinterpret_cast<const float4*>(U + (size_t)r * n) + q);
+          g.x *= act_grad_pre(act, u.x); g.y *= act_grad_pre(act, u.y); g.z *= act_grad_pre(act, u.z); g.w *= act_grad_pre(act, u.w);
+        }
+        *(reinterpret_cast<float4*>(Gp + (size_t)r * n) + q) = g;
+        acc.x = __fadd_rn(acc.x, g.x); acc.y = __fadd_rn(acc.y, g.y); acc.z = __fadd_rn(acc.z, g.z); acc.w = __fadd_rn(acc.w, g.w);
       }
-      if (act != NGPDE_ACT_IDENTITY) g *= act_grad_pre(act, U[(size_t)r * n + c]);
-      Gp[(size_t)r * n + c] = g;
-      acc = __fadd_rn(acc, g);
     }
-    if (cpart) cpart[(size_t)blockIdx.x * n + c] = acc;
+    if (cpart) {
+      sm[threadIdx.x] = acc;
+      __syncthreads();
+      if (rg == 0 && q < n4) {
+        float4 t = sm[q0];
+        for (int j = 1; j < RG; ++j) {
+          const float4 o = sm[j * Q + q0];
+          t.x = __fadd_rn(t.x, o.x); t.y = __fadd_rn(t.y, o.y); t.z = __fadd_rn(t.z, o.z); t.w = __fadd_rn(t.w, o.w);
+        }
+        *(reinterpret_cast<float4*>(cpart + (size_t)blockIdx.x * n) + q) = t;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// db[c] = sum over the chunk sums part[k][c], k < slices: 32 columns x 8 slice lanes per block; lane j adds slices j, j + 8, ...
+// in ascending order (loads unrolled), the 8 lane sums are then added in ascending lane order
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ part, int slices, int n, float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int cl = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s = 0.f;
+  if (c < n) {
+#pragma unroll 8
+    for (int k = j; k < slices; k += 8) s = __fadd_rn(s, part[(size_t)k * n + c]);
+  }
+  sm[j][cl] = s;
+  __syncthreads();
+  if (j == 0 && c < n) {
+    float t = sm[0][cl];
+    for (int i = 1; i < 8; ++i) t = __fadd_rn(t, sm[i][cl]);
+    out[c] = t;
   }
 }
 
@@ -293,7 +372,10 @@ inline int run_forward(const Phase& ph, const Ws& w, char* kbase, char* sbase, c
   pack_weights_kernel<<<std::min(256u, blocks(ph.w_floats, 256)), 256, 0, st>>>(params, m, ph, wp);
   float* z = reinterpret_cast<float*>(keep ? kbase + w.z[0] : sbase + w.za);
   float* other = keep ? nullptr : reinterpret_cast<float*>(sbase + w.zb);
-  assemble_kernel<<<blocks(rows * ph.ld[0], 256), 256, 0, st>>>(g, rows, m.dims[0], ph.ld[0], z);
+  int vec = 0;
+  for (int a = 0; a < ARR_COUNT; ++a)
+    if (g.arr[a] != nullptr && (reinterpret_cast<uintptr_t>(g.arr[a]) & 15) == 0 && (g.ld[a] & 3) == 0) vec |= 1 << a;
+  assemble_kernel<<<blocks(rows * (ph.ld[0] / 4), 256), 256, 0, st>>>(g, rows, m.dims[0], ph.ld[0], vec, z);
   for (int l = 0; l < m.L; ++l) {
     const int n = m.dims[l + 1];
     float* u = keep ? reinterpret_cast<float*>(kbase + w.u[l]) : other;
@@ -339,9 +421,9 @@ inline int run_backward(const Phase& ph, const Ws& w, char* kbase, char* sbase, 
     const float* u = reinterpret_cast<const float*>(kbase + w.u[l]);
     const float* z = reinterpret_cast<const float*>(kbase + w.z[l]);
     const bool first = l == m.L - 1;
-    actgrad_kernel<<<nchunks, 128, 0, st>>>(g, u, m.act[l], rows, n, first ? row_of : nullptr, first ? rowptr_mean : nullptr, ga,
+    actgrad_kernel<<<nchunks, 256, 0, st>>>(g, u, m.act[l], rows, n, first ? row_of : nullptr, first ? rowptr_mean : nullptr, ga,
                                             m.b_off[l] >= 0 ? cpart : nullptr);
-    if (m.b_off[l] >= 0) reduce_slices_kernel<<<blocks(n, 128), 128, 0, st>>>(cpart, nchunks, (size_t)n, n, dparams + m.b_off[l]);
+    if (m.b_off[l] >= 0) colsum_reduce_kernel<<<blocks(n, 32), 256, 0, st>>>(cpart, nchunks, n, dparams + m.b_off[l]);
     const int sp = wgrad_splits(ph, l, rows, num_sms);
     if (int rc = gemm(z, ph.ld[l], true, ga, n, true, part, n, ph.ld[l], n, rows, sp, st)) return rc;
     reduce_slices_kernel<<<blocks(m.dims[l] * n, 256), 256, 0, st>>>(part, sp, (size_t)ph.ld[l] * n, m.dims[l] * n,
