@@ -1286,7 +1286,7 @@ int layered_forward(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& 
     const float* msg = nullptr;
     if (int rc = layered::run_forward(ph, w, kbase, ws, layered_gather(g, d, p, io, false), g->E, io.phi_params, keep, nullptr, &msg, st))
       return rc;
-    const long long tot = (long long)g->N * p.dm;
+    const long long tot = (long long)g->N * (p.dm / 4);
     layered::aggregate_rows_kernel<<<layered::blocks(tot, 256), 256, 0, st>>>((int)g->N, p.dm, d.aggr == NGPDE_AGGR_MEAN, g->rowptr,
                                                                               msg, io.mbar);
   }
@@ -1339,8 +1339,12 @@ int layered_backward(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan&
       return rc;
     const long long tot = (long long)g->N * d.dx;
     if (p.edge_need_dz0) {
-      layered::edge_dx_kernel<<<layered::blocks(tot, 256), 256, 0, st>>>(ga, (int)g->N, d.dx, ph.ld[0], g->rowptr, g->tptr, g->tpos, dz0,
-                                                                         dxdirect, io.dx);
+      if (layered::quads_ok(ga, d.dx) && aligned16(io.dx))
+        layered::edge_dx4_kernel<<<layered::blocks(tot / 4, 256), 256, 0, st>>>(ga, (int)g->N, d.dx, ph.ld[0], g->rowptr, g->tptr, g->tpos,
+                                                                                dz0, dxdirect, io.dx);
+      else
+        layered::edge_dx_kernel<<<layered::blocks(tot, 256), 256, 0, st>>>(ga, (int)g->N, d.dx, ph.ld[0], g->rowptr, g->tptr, g->tpos, dz0,
+                                                                           dxdirect, io.dx);
     } else if (dxdirect) {
       NGPDE_CUDA_TRY(cudaMemcpyAsync(io.dx, dxdirect, sizeof(float) * tot, cudaMemcpyDeviceToDevice, st));
     } else {

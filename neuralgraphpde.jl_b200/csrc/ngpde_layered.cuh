@@ -206,17 +206,27 @@ __global__ void bias_act_kernel(const float* P, const float* __restrict__ bias, 
   if (Zout) *reinterpret_cast<float4*>(Zout + i4) = v;
 }
 
-// mbar[n][c] = sum (mean) of M[k][c] over the CSR row of n, ascending k; 0 for an isolated node (NNlib.scatter, layers.jl:111)
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+}
+
+// mbar[n][c] = sum (mean) of M[k][c] over the CSR row of n, ascending k; 0 for an isolated node (NNlib.scatter, layers.jl:111).
+// One thread per (node, column quad); d is a multiple of 4.
 __global__ void aggregate_rows_kernel(int N, int d, int mean, const int* __restrict__ rowptr, const float* __restrict__ M,
                                       float* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * d) return;
-  const int n = (int)(idx / d), c = (int)(idx - (long long)n * d);
+  const int d4 = d >> 2;
+  if (idx >= (long long)N * d4) return;
+  const int n = (int)(idx / d4), q = (int)(idx - (long long)n * d4);
   const int r0 = rowptr[n], r1 = rowptr[n + 1];
-  float acc = 0.f;
-  for (int k = r0; k < r1; ++k) acc = __fadd_rn(acc, M[(size_t)k * d + c]);
-  if (mean && r1 > r0) acc = __fdiv_rn(acc, (float)(r1 - r0));
-  out[idx] = acc;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int k = r0; k < r1; ++k) acc = add4(acc, *(reinterpret_cast<const float4*>(M + (size_t)k * d) + q));
+  if (mean && r1 > r0) {
+    const float deg = (float)(r1 - r0);
+    acc = make_float4(__fdiv_rn(acc.x, deg), __fdiv_rn(acc.y, deg), __fdiv_rn(acc.z, deg), __fdiv_rn(acc.w, deg));
+  }
+  *(reinterpret_cast<float4*>(out + (size_t)n * d) + q) = acc;
 }
 
 // Gp[r][c] = Gin[row(r)][c] (/ deg) * act'(U[r][c]);  block b owns rows [64 b, 64 b + 64): its column sums go to cpart[b][c].
@@ -306,7 +316,8 @@ __global__ void reduce_slices_kernel(const float* __restrict__ part, int slices,
 }
 
 // edge phase: dx[n][c] = dx_direct[n][c] + sum over the in-edges k of n (ascending) of the destination-side uses of x column c
-// in dZ0[k] + sum over the out-edges (transposed row, ascending) of the source-side uses
+// in dZ0[k] + sum over the out-edges (transposed row, ascending) of the source-side uses.  One thread per (node, column);
+// `edge_dx4_kernel` is the same per column quad for segments that start on multiples of 4 (both in x and in Z0).
 __global__ void edge_dx_kernel(Gather g, int N, int dx, int ld0, const int* __restrict__ rowptr, const int* __restrict__ tptr,
                                const int* __restrict__ tpos, const float* __restrict__ dZ0, const float* __restrict__ dx_direct,
                                float* __restrict__ out) {
@@ -331,6 +342,45 @@ __global__ void edge_dx_kernel(Gather g, int N, int dx, int ld0, const int* __re
     }
   }
   out[idx] = acc;
+}
+
+__global__ void edge_dx4_kernel(Gather g, int N, int dx, int ld0, const int* __restrict__ rowptr, const int* __restrict__ tptr,
+                                const int* __restrict__ tpos, const float* __restrict__ dZ0, const float* __restrict__ dx_direct,
+                                float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d4 = dx >> 2;
+  if (idx >= (long long)N * d4) return;
+  const int n = (int)(idx / d4), c = (int)(idx - (long long)n * d4) * 4;
+  float4 acc = dx_direct ? *reinterpret_cast<const float4*>(dx_direct + (size_t)n * dx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int si = 0; si < g.n_segs; ++si) {
+    const Seg sg = g.segs[si];
+    if (sg.arr != ARR_X || c < sg.col || c >= sg.col + sg.width) continue;
+    const int f = sg.row + (c - sg.col);
+    const float cd = coef_dst(sg.kind), cs = coef_src(sg.kind);
+    if (cd != 0.f) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int k = rowptr[n]; k < rowptr[n + 1]; ++k) s = add4(s, *reinterpret_cast<const float4*>(dZ0 + (size_t)k * ld0 + f));
+      acc = add4(acc, make_float4(cd * s.x, cd * s.y, cd * s.z, cd * s.w));
+    }
+    if (cs != 0.f) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int q = tptr[n]; q < tptr[n + 1]; ++q) s = add4(s, *reinterpret_cast<const float4*>(dZ0 + (size_t)tpos[q] * ld0 + f));
+      acc = add4(acc, make_float4(cs * s.x, cs * s.y, cs * s.z, cs * s.w));
+    }
+  }
+  *reinterpret_cast<float4*>(out + (size_t)n * dx + c) = acc;
+}
+
+// true when every x segment starts on a multiple of 4 columns of x and of Z0 and is a multiple of 4 wide
+inline bool quads_ok(const Gather& g, int dx) {
+  if (dx & 3) return false;
+  for (int si = 0; si < g.n_segs; ++si) {
+    const Seg& sg = g.segs[si];
+    if (sg.arr == ARR_X && ((sg.col | sg.row | sg.width) & 3)) return false;
+  }
+  return true;
 }
 
 // node phase: dZ0 [N][ld0] -> dx_direct [N][dx] (the x segments) and dmbar [N][dm] (the aggregated-message segment)
