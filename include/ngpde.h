@@ -142,7 +142,10 @@ const char* ngpde_last_error(void);
 /* Process-wide switches (benchmarks and tests only).  NGPDE_OPT_TENSOR_CORES: 1 (default) runs MLPs whose layers are at
  * most 64 wide on the tcgen05 tensor-core kernels (3xTF32, fp32-accurate); 0 forces the FP32-FFMA kernels everywhere. */
 enum { NGPDE_OPT_TENSOR_CORES = 0, NGPDE_OPT_GNO_FACTORED = 1, NGPDE_OPT_DEBUG_SKIP = 2 /* developer aid: phase timing */,
-       NGPDE_OPT_HOIST = 3, NGPDE_OPT_LAYERED = 4 };
+       NGPDE_OPT_HOIST = 3, NGPDE_OPT_LAYERED = 4, NGPDE_OPT_GNO_LAYERED = 5 };
+/* NGPDE_OPT_GNO_LAYERED: 1 (default) runs the factored GNOConv (hidden width == in_chs in {32, 64}, >= 2048 edges) with
+ * phi's hidden layers on the tcgen05 GEMM and the per-destination products in a warp-per-node kernel
+ * (csrc/ngpde_gno_node.cuh); 0 keeps the fused FFMA edge kernels. */
 /* NGPDE_OPT_LAYERED: 1 (default) evaluates layers whose MLPs are wider than the fused tensor-core kernels take (an output
  * wider than 64 columns; + / mean aggregation; at least 8192 edges) one Dense layer at a time on the tcgen05 GEMM
  * (csrc/ngpde_layered.cuh); 0 keeps them on the fused FP32-FFMA kernels. */

@@ -153,6 +153,7 @@ OPT_TENSOR_CORES = 0
 OPT_GNO_FACTORED = 1
 OPT_HOIST = 3
 OPT_LAYERED = 4
+OPT_GNO_LAYERED = 5
 
 
 def set_option(option: int, value: int) -> None:

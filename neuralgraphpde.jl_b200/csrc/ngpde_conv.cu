@@ -8,6 +8,7 @@
 #include "ngpde_conv_launch.cuh"
 #include "ngpde_gno_tile.cuh"
 #include "ngpde_layered.cuh"
+#include "ngpde_gno_node.cuh"
 #include "ngpde_tc_layout.cuh"
 #include "ngpde_gno.cuh"
 
@@ -391,9 +392,14 @@ struct Plan {
   // Layer-by-layer evaluation on the tcgen05 GEMM (ngpde_layered.cuh): MLPs with a layer wider than the fused tensor-core
   // kernels take (outputs > 64), + / mean aggregation, enough edges to fill the GEMM grid
   bool layered = false;
+  // Factored GNOConv with phi's hidden layers on the tcgen05 GEMMs (ngpde_layered.cuh) and the per-destination products in a
+  // warp-per-node kernel (ngpde_gno_node.cuh) instead of the fused FFMA edge kernel
+  bool gno_layered = false;
+  MlpDev phi_hidden{};
 };
 bool g_hoist = true;    // NGPDE_OPT_HOIST
 bool g_layered = true;  // NGPDE_OPT_LAYERED
+bool g_gno_layered = true;  // NGPDE_OPT_GNO_LAYERED
 
 void push_seg(Seg* segs, int* n, int* row, int kind, int arr, int col, int width) {
   if (width <= 0) return;
@@ -618,6 +624,11 @@ int make_plan(const ngpde_graph* g, const ngpde_conv_desc& d, Plan* p) {
     p->layered = g_layered && tc_get_enabled() && !p->contract && !p->hoist && !p->nhoist && widest > 64 && g->E >= 8192 &&
                  (d.aggr == NGPDE_AGGR_SUM || d.aggr == NGPDE_AGGR_MEAN) && layered::eligible(p->phi) &&
                  (!p->has_node || layered::eligible(p->node));
+  }
+  if (p->contract == 2 && g_gno_layered && p->phi.L >= 2 && gnonode::supported(p->gno_K, d.gno_in) && g->E >= 2048) {
+    p->phi_hidden = p->phi;
+    p->phi_hidden.L = p->phi.L - 1;
+    p->gno_layered = layered::eligible(p->phi_hidden);
   }
   return NGPDE_OK;
 }
@@ -874,6 +885,8 @@ struct BwdLayout {
   int te_f = 0, smem_f = 0;
   layered::Ws lye, lyn;  // Plan::layered
   size_t off_layered = 0;
+  layered::Ws lyg;  // Plan::gno_layered: phi's hidden layers (kept + scratch) and dz [E][K]
+  size_t off_dzg = 0;
   // factored GNO
   size_t off_S = 0, off_T = 0, off_DM = 0, off_dBpart = 0, off_B = 0;
   int part_stride = 0, gno_splits = 1;
@@ -1008,6 +1021,13 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
     L->off_DM = off;     off = align256(off + sizeof(float) * (size_t)g->N * d.gno_out);
     L->off_dBpart = off; off = align256(off + sizeof(float) * (size_t)L->gno_splits * R * d.gno_out);
     L->off_B = off;      off = align256(off + sizeof(float) * R * d.gno_out);
+    if (p.gno_layered) {
+      const layered::Phase hp = layered::make_phase(p.phi_hidden);
+      layered::plan_kept(hp, g->E, off, &L->lyg);
+      layered::plan_scratch(hp, g->E, true, true, g->num_sms, L->lyg.kept_end, &L->lyg);
+      off = L->lyg.end;
+      L->off_dzg = off;  off = align256(off + sizeof(float) * (size_t)g->E * p.gno_K);
+    }
   }
   if (p.hoist || p.nhoist) {
     L->hgemm = p.hoist && (d.dx & 3) == 0 && p.ds <= 7;
@@ -1188,6 +1208,7 @@ struct FwdPlan {
   size_t off_S = 0, off_B = 0;
   HoistWs hoist;
   layered::Ws lye, lyn;  // Plan::layered
+  layered::Ws lyg;       // Plan::gno_layered
 };
 
 // layout of the optional ngpde_conv_io.state buffer: the hoisted projections and folded parameters, kept for the backward
@@ -1250,6 +1271,10 @@ FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin, int64_t E = 0) {
     off = align256(off + sizeof(float) * (size_t)N * p.gno_Ka * gin);
     f.off_B = off;  // 16-byte aligned copy of B = [W3; b3] for when the flat parameter segment is not
     off = align256(off + sizeof(float) * (size_t)p.gno_Ka * gin * p.dm);
+    if (p.gno_layered) {
+      layered::plan_scratch(layered::make_phase(p.phi_hidden), E, false, false, 1, off, &f.lyg);
+      off = f.lyg.end;
+    }
   }
   f.ws_bytes = off;
   return f;
@@ -1364,6 +1389,7 @@ extern "C" int ngpde_set_option(int32_t option, int32_t value) {
     case NGPDE_OPT_DEBUG_SKIP: g_debug_skip = value; return NGPDE_OK;
     case NGPDE_OPT_HOIST: g_hoist = value != 0; return NGPDE_OK;
     case NGPDE_OPT_LAYERED: g_layered = value != 0; return NGPDE_OK;
+    case NGPDE_OPT_GNO_LAYERED: g_gno_layered = value != 0; return NGPDE_OK;
     default: set_error("unknown option %d", option); return NGPDE_ERR_INVALID;
   }
 }
@@ -1478,6 +1504,17 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
       a.tg.n_units = g->n_units[2];
       if (int rc = launch_fwd_tc(false, g->num_sms, fp.edge, p.phi, io->phi_params, a, reinterpret_cast<float*>(fws + fp.edge.ws_off), st))
         return rc;
+    } else if (p.gno_layered) {
+      // z_e = phi's hidden layers as GEMMs over all edges, then S_n = sum_e [z_e; 1] h_e' with one warp per destination
+      const layered::Phase hp = layered::make_phase(p.phi_hidden);
+      const float* z = nullptr;
+      if (int rc = layered::run_forward(hp, fp.lyg, fws, fws, layered_gather(g, *desc, p, *io, false), g->E, io->phi_params, false,
+                                        nullptr, &z, st))
+        return rc;
+      gnonode::Args na{};
+      na.z = z; na.x = io->x; na.ldx = desc->dx; na.src = g->src; na.rowptr = g->rowptr; na.N = (int)g->N; na.Ka = p.gno_Ka;
+      na.S = a.gno_S;
+      if (int rc = gnonode::launch(na, p.gno_K, false, g->num_sms, st)) return rc;
     } else {
       if (int rc = launch_fwd_edge(te, a, smem, g->num_sms, st)) return rc;
     }
@@ -1796,6 +1833,27 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
         a.tg.unit_ptr = g->units[2];
         a.tg.n_units = g->n_units[2];
         if (int rc = launch_bwd_tc(false, L.tce, a.mlp, a, reinterpret_cast<float*>(ws + L.tce.ws_off), st)) return rc;
+      } else if (p.gno_layered) {
+        // phi's hidden layers once more as GEMMs (activations kept), the per-destination products (dz, dh, S) with one warp per
+        // node, then the hidden layers' backward as GEMMs: their parameter gradients go straight to dphi_params
+        const layered::Phase hp = layered::make_phase(p.phi_hidden);
+        if (int rc = layered::run_forward(hp, L.lyg, ws, ws, layered_gather(g, *desc, p, *io, false), g->E, io->phi_params, true,
+                                          nullptr, nullptr, st))
+          return rc;
+        // z = act(U_{L-2}): the keep-mode forward leaves the last layer's pre-activation; activate it into the dz buffer's
+        // neighbour (ga is free until run_backward)
+        float* zbuf = reinterpret_cast<float*>(ws + L.lyg.gb);
+        const int Lh = hp.mlp.L, K = p.gno_K;
+        const long long tot = (long long)g->E * K;
+        layered::bias_act_kernel<<<layered::blocks(tot / 4, 256), 256, 0, st>>>(reinterpret_cast<const float*>(ws + L.lyg.u[Lh - 1]), nullptr,
+                                                                                hp.mlp.act[Lh - 1], tot, K, nullptr, zbuf);
+        float* dzg = reinterpret_cast<float*>(ws + L.off_dzg);
+        gnonode::Args na{};
+        na.z = zbuf; na.x = io->x; na.ldx = desc->dx; na.src = g->src; na.rowptr = g->rowptr; na.N = (int)g->N; na.Ka = p.gno_Ka;
+        na.T = gT; na.S = gS; na.dz = dzg; na.desrc = desrc;
+        if (int rc = gnonode::launch(na, K, true, g->num_sms, st)) return rc;
+        if (int rc = layered::run_backward(hp, L.lyg, ws, ws, g->E, dzg, nullptr, nullptr, false, g->num_sms, io->dphi_params, nullptr, st))
+          return rc;
       } else {
         if (int rc = launch_bwd_edge(te, a, L.smem_e, L.grid_e, st)) return rc;
       }
@@ -1811,7 +1869,8 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     }
     const int P = L.part_stride;
     float* dphi_target = p.hoist ? reinterpret_cast<float*>(ws + L.off_dfin) : io->dphi_params;
-    if (P > 0) reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_phi, L.grid_e, P, dphi_target);
+    if (P > 0 && !(p.gno_layered && g->E > 0))
+      reduce_partials_kernel<<<(P + 255) / 256, 256, 0, st>>>(part_phi, L.grid_e, P, dphi_target);
     if (p.hoist) {
       // dQ = dxdst + transpose-gather(desrc) -> (dPt, dPs) -> the two projections' backward -> dx, d(Wt, b1, Ws) -> dphi
       ProfScope prof(NGPDE_PROF_BWD_EDGE, st);

@@ -57,13 +57,18 @@ inline Phase make_phase(const MlpDev& m) {
   return p;
 }
 
-constexpr int CHUNK_ROWS = 64;  // rows per block of the fused act' / bias-gradient pass (fixed: the summation order)
+constexpr int CHUNK_ROWS = 64;  // rows per block of the fused act' / bias-gradient pass (fixed: the summation order) ...
+// ... up to 2048 chunks; beyond, a chunk grows in multiples of 64 rows so the second reduction stage stays short
+inline int chunk_rows(int64_t rows) {
+  const int64_t per = (rows + 2047) / 2048;
+  return (int)std::max<int64_t>(CHUNK_ROWS, (per + CHUNK_ROWS - 1) / CHUNK_ROWS * CHUNK_ROWS);
+}
 
 inline int wgrad_splits(const Phase& p, int l, int64_t rows, int num_sms) {
   const int tiles = ((p.ld[l] + 127) / 128) * ((p.mlp.dims[l + 1] + 63) / 64);
   int best = 1;
   double best_cost = 1e30;
-  for (int sp = 1; sp <= 64; ++sp) {
+  for (int sp = 1; sp <= 1024; ++sp) {  // a 64 x 64 gradient over millions of rows wants hundreds of slices to fill the GPU
     if ((int64_t)sp * 512 > rows && sp > 1) break;
     const int waves = (tiles * sp + 2 * num_sms - 1) / (2 * num_sms);
     const double cost = (double)waves / sp;
@@ -103,7 +108,7 @@ inline void plan_scratch(const Phase& p, int64_t rows, bool backward, bool kept,
     int maxsp = 1;
     for (int l = 0; l < p.mlp.L; ++l) maxsp = std::max(maxsp, wgrad_splits(p, l, rows, num_sms));
     w->part = off; off = a256(off + 4 * (size_t)maxsp * p.maxwn);
-    w->cpart = off; off = a256(off + 4 * (size_t)((rows + CHUNK_ROWS - 1) / CHUNK_ROWS) * p.maxld);
+    w->cpart = off; off = a256(off + 4 * (size_t)((rows + chunk_rows(rows) - 1) / chunk_rows(rows)) * p.maxld);
   }
   w->end = off;
 }
@@ -229,7 +234,7 @@ __global__ void aggregate_rows_kernel(int N, int d, int mean, const int* __restr
   *(reinterpret_cast<float4*>(out + (size_t)n * d) + q) = acc;
 }
 
-// Gp[r][c] = Gin[row(r)][c] (/ deg) * act'(U[r][c]);  block b owns rows [64 b, 64 b + 64): its column sums go to cpart[b][c].
+// Gp[r][c] = Gin[row(r)][c] (/ deg) * act'(U[r][c]);  block b owns rows [crows b, crows (b + 1)) (crows = chunk_rows(rows)): its column sums go to cpart[b][c].
 // row_of != null: the edge phase's last layer -- Gin = dmbar is indexed by the edge's destination, divided by the in-degree
 // for the mean (true division, like the fused kernels).  256 threads = RG row groups x (n / 4) column quads (float4 accesses,
 // n / 4 <= 256; wider rows loop over the quads with RG = 1); a group takes every RG-th row of the chunk in ascending order, the
@@ -237,10 +242,10 @@ __global__ void aggregate_rows_kernel(int N, int d, int mean, const int* __restr
 __global__ void __launch_bounds__(256) actgrad_kernel(const float* __restrict__ Gin, const float* __restrict__ U, int act,
                                                       long long rows, int n, const int* __restrict__ row_of,
                                                       const int* __restrict__ rowptr_mean, float* __restrict__ Gp,
-                                                      float* __restrict__ cpart) {
+                                                      float* __restrict__ cpart, int crows) {
   __shared__ float4 sm[256];
-  const long long r0 = (long long)blockIdx.x * CHUNK_ROWS;
-  const int nr = (int)((r0 + CHUNK_ROWS < rows ? r0 + CHUNK_ROWS : rows) - r0);
+  const long long r0 = (long long)blockIdx.x * crows;
+  const int nr = (int)((r0 + crows < rows ? r0 + crows : rows) - r0);
   const int n4 = n >> 2;
   const int Q = n4 < 256 ? n4 : 256, RG = 256 / Q;
   const int q0 = threadIdx.x % Q, rg = threadIdx.x / Q;
@@ -464,7 +469,8 @@ inline int run_backward(const Phase& ph, const Ws& w, char* kbase, char* sbase, 
   float* gb = reinterpret_cast<float*>(sbase + w.gb);
   float* part = reinterpret_cast<float*>(sbase + w.part);
   float* cpart = reinterpret_cast<float*>(sbase + w.cpart);
-  const int nchunks = (int)((rows + CHUNK_ROWS - 1) / CHUNK_ROWS);
+  const int crows = chunk_rows(rows);
+  const int nchunks = (int)((rows + crows - 1) / crows);
   const float* g = Gin;
   for (int l = m.L - 1; l >= 0; --l) {
     const int n = m.dims[l + 1];
@@ -472,7 +478,7 @@ inline int run_backward(const Phase& ph, const Ws& w, char* kbase, char* sbase, 
     const float* z = reinterpret_cast<const float*>(kbase + w.z[l]);
     const bool first = l == m.L - 1;
     actgrad_kernel<<<nchunks, 256, 0, st>>>(g, u, m.act[l], rows, n, first ? row_of : nullptr, first ? rowptr_mean : nullptr, ga,
-                                            m.b_off[l] >= 0 ? cpart : nullptr);
+                                            m.b_off[l] >= 0 ? cpart : nullptr, crows);
     if (m.b_off[l] >= 0) colsum_reduce_kernel<<<blocks(n, 32), 256, 0, st>>>(cpart, nchunks, n, dparams + m.b_off[l]);
     const int sp = wgrad_splits(ph, l, rows, num_sms);
     if (int rc = gemm(z, ph.ld[l], true, ga, n, true, part, n, ph.ld[l], n, rows, sp, st)) return rc;

@@ -839,6 +839,33 @@ def test_wide_layers_gemm_per_layer_and_fused_paths(family, layered):
         ngpde._lib.set_option(ngpde._lib.OPT_LAYERED, 1)
 
 
+@pytest.mark.parametrize("gno_layered", [1, 0])
+@pytest.mark.parametrize("chs,bias", [(64, True), (32, False)])
+def test_gno_conv_warp_per_node_and_fused_paths(chs, bias, gno_layered):
+    """Factored GNOConv with hidden width == in_chs in {32, 64} and >= 2048 edges: phi's hidden layers as tcgen05 GEMMs + the
+    per-destination products in the warp-per-node kernel (csrc/ngpde_gno_node.cuh); NGPDE_OPT_GNO_LAYERED = 0 keeps the fused
+    FFMA edge kernels.  Both against the oracle.  Graph: isolated nodes, edge features, duplicates, one destination with 200
+    in-edges (13 batches of 16 added into its own S_n), in-degrees 1..40 otherwise."""
+    from ngpde import engine
+    rng = np.random.default_rng(51 + chs)
+    n, e = 260, 3000
+    s, t = rng.integers(0, n - 5, e), rng.integers(0, n - 5, e)
+    t[:200] = 7
+    g = GNNGraph(torch.from_numpy(s), torch.from_numpy(t), num_nodes=n, ndata={"a": jl_rand(rng, 1, n), "x": jl_rand(rng, 2, n)},
+                 edata={"e": jl_rand(rng, 2, e)}).to(DEV)
+    phi = Chain(Dense(3 + 3 + 2, chs, "relu"), Dense(chs, chs, "tanh"), Dense(chs, chs * 8, bias=bias))
+    layer = GNOConv((chs, 8), phi, "relu", initialgraph=g, aggr="mean")
+    ps, st = setup(rng, layer, DEV)
+    x = jl_rand(rng, chs, n, DEV)
+    ngpde._lib.set_option(ngpde._lib.OPT_GNO_LAYERED, gno_layered)
+    try:
+        r = engine.RhsRunner(layer, x, ps, st)
+        assert ngpde._lib.kernel_paths(r.handle, r.desc)["bwd_edge"] == 2
+        check_layer(layer, x, ps, st, g)
+    finally:
+        ngpde._lib.set_option(ngpde._lib.OPT_GNO_LAYERED, 1)
+
+
 def test_kernel_path_query_reports_the_engine_that_runs():
     """ngpde_conv_kernel_paths: C3 runs all four fused kernels on tcgen05; with the option off, or for GNOConv's bilinear
     contraction, the FP32-FFMA engine takes over (bench.py labels its roofline line with this)."""
