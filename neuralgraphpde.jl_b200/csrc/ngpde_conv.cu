@@ -1216,6 +1216,8 @@ struct StatePlan {
   HoistWs hoist;
   NodeHoistWs nhoist;
   layered::Ws lye, lyn;  // Plan::layered: the kept activations of both phases (up to 8 GiB; beyond that the backward recomputes)
+  layered::Ws lyg;       // Plan::gno_layered: phi's hidden activations and z = the activated last hidden layer [E][K] (up to 24 GiB)
+  size_t off_zg = 0;
   size_t bytes = 0;
 };
 StatePlan state_plan(const Plan& p, int64_t N, int64_t E = 0) {
@@ -1229,6 +1231,13 @@ StatePlan state_plan(const Plan& p, int64_t N, int64_t E = 0) {
       off = sp.lyn.kept_end;
     }
     sp.bytes = off <= (size_t(8) << 30) ? off : 0;
+    return sp;
+  }
+  if (p.gno_layered) {
+    layered::plan_kept(layered::make_phase(p.phi_hidden), E, 0, &sp.lyg);
+    sp.off_zg = sp.lyg.kept_end;
+    off = align256(sp.off_zg + sizeof(float) * (size_t)E * p.gno_K);
+    sp.bytes = off <= (size_t(24) << 30) ? off : 0;
     return sp;
   }
   if (p.hoist) off = hoist_ws(p, N, off, &sp.hoist);
@@ -1508,9 +1517,14 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
       // z_e = phi's hidden layers as GEMMs over all edges, then S_n = sum_e [z_e; 1] h_e' with one warp per destination
       const layered::Phase hp = layered::make_phase(p.phi_hidden);
       const float* z = nullptr;
-      if (int rc = layered::run_forward(hp, fp.lyg, fws, fws, layered_gather(g, *desc, p, *io, false), g->E, io->phi_params, false,
-                                        nullptr, &z, st))
+      if (keep) {  // hidden activations and z stay in io->state for the backward
+        if (int rc = layered::run_forward(hp, sp.lyg, static_cast<char*>(io->state), fws, layered_gather(g, *desc, p, *io, false), g->E,
+                                          io->phi_params, true, reinterpret_cast<float*>(static_cast<char*>(io->state) + sp.off_zg), &z, st))
+          return rc;
+      } else if (int rc = layered::run_forward(hp, fp.lyg, fws, fws, layered_gather(g, *desc, p, *io, false), g->E, io->phi_params,
+                                               false, nullptr, &z, st)) {
         return rc;
+      }
       gnonode::Args na{};
       na.z = z; na.x = io->x; na.ldx = desc->dx; na.src = g->src; na.rowptr = g->rowptr; na.N = (int)g->N; na.Ka = p.gno_Ka;
       na.S = a.gno_S;
@@ -1837,22 +1851,26 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
         // phi's hidden layers once more as GEMMs (activations kept), the per-destination products (dz, dh, S) with one warp per
         // node, then the hidden layers' backward as GEMMs: their parameter gradients go straight to dphi_params
         const layered::Phase hp = layered::make_phase(p.phi_hidden);
-        if (int rc = layered::run_forward(hp, L.lyg, ws, ws, layered_gather(g, *desc, p, *io, false), g->E, io->phi_params, true,
-                                          nullptr, nullptr, st))
-          return rc;
-        // z = act(U_{L-2}): the keep-mode forward leaves the last layer's pre-activation; activate it into the dz buffer's
-        // neighbour (ga is free until run_backward)
-        float* zbuf = reinterpret_cast<float*>(ws + L.lyg.gb);
-        const int Lh = hp.mlp.L, K = p.gno_K;
-        const long long tot = (long long)g->E * K;
-        layered::bias_act_kernel<<<layered::blocks(tot / 4, 256), 256, 0, st>>>(reinterpret_cast<const float*>(ws + L.lyg.u[Lh - 1]), nullptr,
-                                                                                hp.mlp.act[Lh - 1], tot, K, nullptr, zbuf);
+        const int K = p.gno_K;
+        layered::Ws w = L.lyg;
+        char* kb = ws;
+        const float* zbuf = nullptr;
+        if (kept) {  // left in io->state by the forward call
+          kb = static_cast<char*>(io->state);
+          w = sp.lyg;
+          w.ga = L.lyg.ga; w.gb = L.lyg.gb; w.part = L.lyg.part; w.cpart = L.lyg.cpart; w.end = L.lyg.end;
+          zbuf = reinterpret_cast<const float*>(kb + sp.off_zg);
+        } else {     // recomputed: z goes to the cotangent ping-pong buffer run_backward writes last
+          if (int rc = layered::run_forward(hp, w, kb, ws, layered_gather(g, *desc, p, *io, false), g->E, io->phi_params, true,
+                                            reinterpret_cast<float*>(ws + L.lyg.gb), &zbuf, st))
+            return rc;
+        }
         float* dzg = reinterpret_cast<float*>(ws + L.off_dzg);
         gnonode::Args na{};
         na.z = zbuf; na.x = io->x; na.ldx = desc->dx; na.src = g->src; na.rowptr = g->rowptr; na.N = (int)g->N; na.Ka = p.gno_Ka;
         na.T = gT; na.S = gS; na.dz = dzg; na.desrc = desrc;
         if (int rc = gnonode::launch(na, K, true, g->num_sms, st)) return rc;
-        if (int rc = layered::run_backward(hp, L.lyg, ws, ws, g->E, dzg, nullptr, nullptr, false, g->num_sms, io->dphi_params, nullptr, st))
+        if (int rc = layered::run_backward(hp, w, kb, ws, g->E, dzg, nullptr, nullptr, false, g->num_sms, io->dphi_params, nullptr, st))
           return rc;
       } else {
         if (int rc = launch_bwd_edge(te, a, L.smem_e, L.grid_e, st)) return rc;

@@ -862,6 +862,16 @@ def test_gno_conv_warp_per_node_and_fused_paths(chs, bias, gno_layered):
         r = engine.RhsRunner(layer, x, ps, st)
         assert ngpde._lib.kernel_paths(r.handle, r.desc)["bwd_edge"] == 2
         check_layer(layer, x, ps, st, g)
+        if gno_layered:  # io.state keeps phi's hidden activations for the backward; without it they are recomputed: same bits
+            assert r.state is not None
+            r.dy.copy_(torch.from_numpy(rng.standard_normal(tuple(r.dy.shape)).astype(np.float32)))
+            r.forward(); r.backward()
+            torch.cuda.synchronize()
+            kept = (r.y.clone(), r.dx.clone(), r.dparams.clone())
+            r.io.state = None
+            r.forward(); r.backward()
+            torch.cuda.synchronize()
+            assert torch.equal(kept[0], r.y) and torch.equal(kept[1], r.dx) and torch.equal(kept[2], r.dparams)
     finally:
         ngpde._lib.set_option(ngpde._lib.OPT_GNO_LAYERED, 1)
 
