@@ -243,13 +243,18 @@ def roofline_block(workload, w, prof, K, paths, step_ms, peaks, edges_launch, no
     alg_flops = f_phase * (1.0 if dom.startswith("fwd") else 2.0)
     ach_tflops = alg_flops / (dom_ms * 1e-3) / 1e12
     step_kernel_ms = sum(v[0] for v in prof.values()) / K
-    on_tc = paths.get(dom, 0) == 1
+    on_tc = paths.get(dom, 0) in (1, 3)
     factored = paths.get(dom, 0) == 2
     kname = {"fwd_edge": "mp_fwd{}_kernel<edge>", "fwd_node": "mp_fwd{}_kernel<node>", "bwd_node": "mp_bwd{}_kernel<node>",
              "bwd_edge": "mp_bwd{}_kernel<edge>"}[dom].format("_tc" if on_tc else "")
+    if paths.get(dom, 0) == 3:
+        kname = ("%s phase, one gno_gemm_tc_kernel (tcgen05 3xTF32) per Dense layer + elementwise kernels "
+                 "(csrc/ngpde_layered.cuh)" % dom)
     if factored:
-        kname = {"fwd_edge": "gno factored edge phase: mp_fwd_kernel<edge> (S builder) + gno_gemm (mbar = S B)",
-                 "bwd_edge": "gno factored edge phase: gno_gemm (T = DM B') + mp_bwd_kernel<edge> + gno_gemm (dB = S' DM)"}[dom]
+        kname = {"fwd_edge": "gno factored edge phase: phi hidden layers (gno_gemm_tc GEMMs, or mp_fwd_kernel<edge> with "
+                             "NGPDE_OPT_GNO_LAYERED=0) + gno_node_kernel (S builder) + gno_gemm (mbar = S B)",
+                 "bwd_edge": "gno factored edge phase: gno_gemm (T = DM B') + gno_node_kernel (dz, dh per destination) + phi hidden "
+                             "layers' backward GEMMs + gno_gemm (dB = S' DM)"}[dom]
     # the pipe that can hold the 1e-5 tolerance: 3xTF32 on tcgen05 = a third of the TF32 rate = a sixth of the dense BF16
     # peak; the FP32-FFMA engine: 148 SMs x 128 lanes x 2 flop x 1.965 GHz = 74.4 TFLOP/s
     pipe_peak = peaks["bf16_tflops"] / 6.0 if on_tc else 74.4

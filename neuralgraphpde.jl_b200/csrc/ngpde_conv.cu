@@ -1216,8 +1216,9 @@ struct StatePlan {
   HoistWs hoist;
   NodeHoistWs nhoist;
   layered::Ws lye, lyn;  // Plan::layered: the kept activations of both phases (up to 8 GiB; beyond that the backward recomputes)
-  layered::Ws lyg;       // Plan::gno_layered: phi's hidden activations and z = the activated last hidden layer [E][K] (up to 24 GiB)
-  size_t off_zg = 0;
+  layered::Ws lyg;       // Plan::gno_layered: phi's hidden activations, z = the activated last hidden layer [E][K] and the
+  size_t off_zg = 0;     // per-destination sums S [N][Ka * gin] (up to 40 GiB; beyond that the backward recomputes)
+  size_t off_Sg = 0;
   size_t bytes = 0;
 };
 StatePlan state_plan(const Plan& p, int64_t N, int64_t E = 0) {
@@ -1237,7 +1238,10 @@ StatePlan state_plan(const Plan& p, int64_t N, int64_t E = 0) {
     layered::plan_kept(layered::make_phase(p.phi_hidden), E, 0, &sp.lyg);
     sp.off_zg = sp.lyg.kept_end;
     off = align256(sp.off_zg + sizeof(float) * (size_t)E * p.gno_K);
-    sp.bytes = off <= (size_t(24) << 30) ? off : 0;
+    sp.off_Sg = off;
+    const int gin = p.phi.dims[p.phi.L] / std::max(1, p.dm);  // phi's last layer is gin * gout wide
+    off = align256(off + sizeof(float) * (size_t)N * p.gno_Ka * gin);
+    sp.bytes = off <= (size_t(40) << 30) ? off : 0;
     return sp;
   }
   if (p.hoist) off = hoist_ws(p, N, off, &sp.hoist);
@@ -1490,6 +1494,7 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
   a.offA = fs.offA; a.offB = fs.offB; a.offW = fs.offW; a.offH = fs.offH; a.offZt = fs.offZt;
   a.gno_Ka = p.gno_Ka;
   a.gno_S = p.contract == 2 ? reinterpret_cast<float*>(fws + fp.off_S) : nullptr;
+  if (p.gno_layered && keep) a.gno_S = reinterpret_cast<float*>(static_cast<char*>(io->state) + sp.off_Sg);  // kept for dB = S' DM
   {
     ProfScope prof(NGPDE_PROF_FWD_EDGE, st);
     if (p.hoist) {
@@ -1860,6 +1865,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
           w = sp.lyg;
           w.ga = L.lyg.ga; w.gb = L.lyg.gb; w.part = L.lyg.part; w.cpart = L.lyg.cpart; w.end = L.lyg.end;
           zbuf = reinterpret_cast<const float*>(kb + sp.off_zg);
+          gS = reinterpret_cast<float*>(kb + sp.off_Sg);
         } else {     // recomputed: z goes to the cotangent ping-pong buffer run_backward writes last
           if (int rc = layered::run_forward(hp, w, kb, ws, layered_gather(g, *desc, p, *io, false), g->E, io->phi_params, true,
                                             reinterpret_cast<float*>(ws + L.lyg.gb), &zbuf, st))
@@ -1868,7 +1874,7 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
         float* dzg = reinterpret_cast<float*>(ws + L.off_dzg);
         gnonode::Args na{};
         na.z = zbuf; na.x = io->x; na.ldx = desc->dx; na.src = g->src; na.rowptr = g->rowptr; na.N = (int)g->N; na.Ka = p.gno_Ka;
-        na.T = gT; na.S = gS; na.dz = dzg; na.desrc = desrc;
+        na.T = gT; na.S = kept ? nullptr : gS; na.dz = dzg; na.desrc = desrc;  // S kept from the forward: not rebuilt
         if (int rc = gnonode::launch(na, K, true, g->num_sms, st)) return rc;
         if (int rc = layered::run_backward(hp, w, kb, ws, g->E, dzg, nullptr, nullptr, false, g->num_sms, io->dphi_params, nullptr, st))
           return rc;

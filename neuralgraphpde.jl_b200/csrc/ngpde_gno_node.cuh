@@ -33,7 +33,7 @@ struct Args {
   const int* rowptr;  // [N + 1]
   int N, Ka;          // Ka = K + 1 when phi's last layer has a bias, else K
   const float* T;     // [N][Ka * GIN]   (backward)
-  float* S;           // [N][Ka * GIN]
+  float* S;           // [N][Ka * GIN]; null in the backward when the forward's S was kept (io.state)
   float* dz;          // [E][K]          (backward)
   float* desrc;       // [E][GIN]        (backward)
 };
@@ -113,7 +113,7 @@ __device__ __forceinline__ void batch(const Args& a, const float* __restrict__ T
         for (int gc = 0; gc < GC; ++gc) a.desrc[(size_t)(b0 + e) * GIN + lane + 32 * gc] = acc[e][gc];
       }
   }
-  {  // S_n[j][i] (+)= sum_e za_e[j] h_e[i], ascending e; columns i = lane + 32 gc; this warp's half of the rows j
+  if (a.S != nullptr) {  // S_n[j][i] (+)= sum_e za_e[j] h_e[i], ascending e; columns i = lane + 32 gc; this warp's half of the rows j
     float h[NE][GC];
 #pragma unroll
     for (int e = 0; e < NE; ++e)
@@ -161,8 +161,10 @@ __global__ void __launch_bounds__(64 * PAIRS, 1) gno_node_kernel(const Args a) {
   for (int n = blockIdx.x * PAIRS + pair; n < a.N; n += gridDim.x * PAIRS) {
     const int r0 = a.rowptr[n], r1 = a.rowptr[n + 1];
     if (r0 == r1) {  // isolated destination: S_n = 0 (mbar = 0, nothing for dB)
-      float4* Sn = reinterpret_cast<float4*>(a.S + (size_t)n * R);
-      for (int i = half * 32 + lane; i < R / 4; i += 64) Sn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.S != nullptr) {
+        float4* Sn = reinterpret_cast<float4*>(a.S + (size_t)n * R);
+        for (int i = half * 32 + lane; i < R / 4; i += 64) Sn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       continue;
     }
     if (BWD) {
