@@ -145,9 +145,10 @@ __device__ __forceinline__ void batch(const Args& a, const float* __restrict__ T
 }
 
 __device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int KC, int GC, bool BWD>
-__global__ void __launch_bounds__(64 * PAIRS, 1) gno_node_kernel(const Args a) {
+__global__ void __launch_bounds__(64 * PAIRS, BWD ? 1 : 2) gno_node_kernel(const Args a) {
   using SM = Smem<KC, GC, BWD>;
   constexpr int K = SM::K, GIN = SM::GIN, LT = SM::LT, LH = SM::LH;
   extern __shared__ __align__(16) float smem[];
@@ -160,6 +161,14 @@ __global__ void __launch_bounds__(64 * PAIRS, 1) gno_node_kernel(const Args a) {
   const int R = Ka * GIN;
   for (int n = blockIdx.x * PAIRS + pair; n < a.N; n += gridDim.x * PAIRS) {
     const int r0 = a.rowptr[n], r1 = a.rowptr[n + 1];
+    if (!BWD && half == 0) {  // the pair's NEXT node: the z rows of its first batch are pulled into L2 while this node computes
+      const int nn = n + gridDim.x * PAIRS;
+      if (nn < a.N) {
+        const int q0 = a.rowptr[nn], q1 = a.rowptr[nn + 1];
+        const int lines = (min(q1 - q0, EB) * K * 4 + 127) / 128;
+        if (lane < lines) prefetch_l2(reinterpret_cast<const char*>(a.z + (size_t)q0 * K) + (size_t)lane * 128);
+      }
+    }
     if (r0 == r1) {  // isolated destination: S_n = 0 (mbar = 0, nothing for dB)
       if (a.S != nullptr) {
         float4* Sn = reinterpret_cast<float4*>(a.S + (size_t)n * R);
@@ -220,7 +229,7 @@ int launch_one(const Args& a, int num_sms, cudaStream_t st) {
     NGPDE_CUDA_TRY(cudaFuncSetAttribute(gno_node_kernel<KC, GC, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::bytes));
     configured = true;
   }
-  const int per_sm = std::max(1, std::min(2, (220 * 1024) / SM::bytes));
+  const int per_sm = BWD ? 1 : std::max(1, std::min(2, (220 * 1024) / SM::bytes));
   const int grid = std::max(1, std::min(num_sms * per_sm, (a.N + PAIRS - 1) / PAIRS));
   gno_node_kernel<KC, GC, BWD><<<grid, 64 * PAIRS, SM::bytes, st>>>(a);
   NGPDE_CUDA_TRY(cudaGetLastError());
