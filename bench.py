@@ -599,6 +599,13 @@ def main():
     dp_host = torch.empty(ca.data.numel(), dtype=torch.float32).pin_memory()
     h2d = x_host.numel() * 4 + dy_host.numel() * 4
     d2h = y_host.numel() * 4 + dx_host.numel() * 4 + dp_host.numel() * 4
+    # the resident-step runner's workspaces and forward->backward state are not needed any more; the public-API leg allocates
+    # its own (C4 at 1M nodes: 63 GB + 33 GB each -- both sets do not fit 180 GB at once)
+    graph_kernels = getattr(runner, "graph_kernels", None)
+    for name in ("graph", "ws", "ws_fwd", "state"):
+        if hasattr(runner, name):
+            setattr(runner, name, None)
+    torch.cuda.empty_cache()
 
     def e2e_step():
         x_dev.copy_(x_host, non_blocking=True)
@@ -637,7 +644,7 @@ def main():
         "algorithmic_tflops": 3.0 * w.flops_fwd * world / (total_ms / K * 1e-3) / 1e12,
         "gpu_launches": launches,
         "gpu_launches_how": ("kernel nodes of the captured CUDA graph x replays (ngpde_cuda_graph_kernel_nodes)"
-                             if getattr(runner, "graph_kernels", None) is not None and args.cuda_graph and not chain
+                             if graph_kernels is not None and args.cuda_graph and not chain
                              else "per-call table in ops.py"),
         "lib_sha256": lib_sha256(),
         "clocks": clocks,

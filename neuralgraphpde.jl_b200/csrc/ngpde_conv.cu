@@ -395,6 +395,7 @@ struct Plan {
   // Factored GNOConv with phi's hidden layers on the tcgen05 GEMMs (ngpde_layered.cuh) and the per-destination products in a
   // warp-per-node kernel (ngpde_gno_node.cuh) instead of the fused FFMA edge kernel
   bool gno_layered = false;
+  bool gno_node_gemm = false;  // ... and its node update act(W x + mbar + b) as one GEMM + an elementwise pass
   MlpDev phi_hidden{};
 };
 bool g_hoist = true;    // NGPDE_OPT_HOIST
@@ -629,6 +630,7 @@ int make_plan(const ngpde_graph* g, const ngpde_conv_desc& d, Plan* p) {
     p->phi_hidden = p->phi;
     p->phi_hidden.L = p->phi.L - 1;
     p->gno_layered = layered::eligible(p->phi_hidden);
+    p->gno_node_gemm = p->gno_layered && p->node_addend && p->node.L == 1 && layered::eligible(p->node) && (d.dx & 3) == 0;
   }
   return NGPDE_OK;
 }
@@ -886,6 +888,7 @@ struct BwdLayout {
   layered::Ws lye, lyn;  // Plan::layered
   size_t off_layered = 0;
   layered::Ws lyg;  // Plan::gno_layered: phi's hidden layers (kept + scratch) and dz [E][K]
+  layered::Ws lygn; // Plan::gno_node_gemm: the node update (its cotangent buffers double as dmbar / dx_direct: a region of its own)
   size_t off_dzg = 0;
   // factored GNO
   size_t off_S = 0, off_T = 0, off_DM = 0, off_dBpart = 0, off_B = 0;
@@ -1027,6 +1030,12 @@ int bwd_layout(const ngpde_graph* g, const ngpde_conv_desc& d, const Plan& p, Bw
       layered::plan_scratch(hp, g->E, true, true, g->num_sms, L->lyg.kept_end, &L->lyg);
       off = L->lyg.end;
       L->off_dzg = off;  off = align256(off + sizeof(float) * (size_t)g->E * p.gno_K);
+      if (p.gno_node_gemm) {
+        const layered::Phase np = layered::make_phase(p.node);
+        layered::plan_kept(np, g->N, off, &L->lygn);
+        layered::plan_scratch(np, g->N, true, true, g->num_sms, L->lygn.kept_end, &L->lygn);
+        off = L->lygn.end;
+      }
     }
   }
   if (p.hoist || p.nhoist) {
@@ -1208,7 +1217,7 @@ struct FwdPlan {
   size_t off_S = 0, off_B = 0;
   HoistWs hoist;
   layered::Ws lye, lyn;  // Plan::layered
-  layered::Ws lyg;       // Plan::gno_layered
+  layered::Ws lyg, lygn;  // Plan::gno_layered (edge phase: phi's hidden layers; node update)
 };
 
 // layout of the optional ngpde_conv_io.state buffer: the hoisted projections and folded parameters, kept for the backward
@@ -1287,6 +1296,10 @@ FwdPlan fwd_plan(const Plan& p, int aggr, int64_t N, int gin, int64_t E = 0) {
     if (p.gno_layered) {
       layered::plan_scratch(layered::make_phase(p.phi_hidden), E, false, false, 1, off, &f.lyg);
       off = f.lyg.end;
+      if (p.gno_node_gemm) {
+        layered::plan_scratch(layered::make_phase(p.node), N, false, false, 1, off, &f.lygn);
+        off = f.lygn.end;
+      }
     }
   }
   f.ws_bytes = off;
@@ -1441,6 +1454,7 @@ extern "C" int ngpde_conv_kernel_paths(ngpde_graph_t g, const ngpde_conv_desc* d
   paths[NGPDE_PROF_FWD_NODE] = p.has_node ? (fp.node.on ? 1 : 0) : -1;
   paths[NGPDE_PROF_BWD_EDGE] = L.tce.on ? 1 : (p.contract == 2 ? 2 : 0);
   paths[NGPDE_PROF_BWD_NODE] = p.has_node ? (L.tcn.on ? 1 : 0) : -1;
+  if (p.gno_node_gemm) paths[NGPDE_PROF_FWD_NODE] = paths[NGPDE_PROF_BWD_NODE] = 3;
   return NGPDE_OK;
 }
 
@@ -1573,7 +1587,12 @@ extern "C" int ngpde_conv_forward(ngpde_graph_t g, const ngpde_conv_desc* desc, 
     n.addend = p.node_addend ? io->mbar : nullptr;
     n.offA = fs.offA; n.offB = fs.offB; n.offW = fs.offW; n.offH = fs.offH;
     ProfScope prof(NGPDE_PROF_FWD_NODE, st);
-    if (p.nhoist) {
+    if (p.gno_node_gemm) {  // y = act((W x + mbar) + b): one GEMM over the nodes + one elementwise pass
+      NGPDE_REQUIRE(aligned16(io->mbar) && aligned16(io->y), "GNOConv node update: mbar and y must be 16-byte aligned");
+      if (int rc = layered::run_forward(layered::make_phase(p.node), fp.lygn, fws, fws, layered_gather(g, *desc, p, *io, true), g->N,
+                                        io->node_params, false, io->y, nullptr, st, io->mbar))
+        return rc;
+    } else if (p.nhoist) {
       NGPDE_REQUIRE(fp.node.on, "internal: hoisted node plan without a tensor-core node phase");
       if (int rc = nhoist_forward(g, *desc, p, *io, hbase, nhw, st)) return rc;
       nhoist_args(p, reinterpret_cast<const float*>(hbase + nhw.off_q), &n);
@@ -1676,7 +1695,21 @@ extern "C" int ngpde_conv_backward(ngpde_graph_t g, const ngpde_conv_desc* desc,
     n.store_last = L.sn.store_last;
     std::memcpy(n.zoff, L.sn.zoff, sizeof(n.zoff));
     n.offG0 = L.sn.offG0; n.offG1 = L.sn.offG1; n.offW = L.sn.offW;
-    if (p.nhoist) {
+    if (p.gno_node_gemm) {
+      // u = W x + mbar + b recomputed as one GEMM; G = dy * act'(u) is at once the cotangent of mbar; dx_direct = G W', dW = x' G
+      ProfScope prof(NGPDE_PROF_BWD_NODE, st);
+      NGPDE_REQUIRE(aligned16(io->mbar) && aligned16(io->dy), "GNOConv node update: mbar and dy must be 16-byte aligned");
+      const layered::Phase np = layered::make_phase(p.node);
+      if (int rc = layered::run_forward(np, L.lygn, ws, ws, layered_gather(g, *desc, p, *io, true), g->N, io->node_params, true, nullptr,
+                                        nullptr, st, io->mbar))
+        return rc;
+      const float *dz0 = nullptr, *gp0 = nullptr;
+      if (int rc = layered::run_backward(np, L.lygn, ws, ws, g->N, io->dy, nullptr, nullptr, true, g->num_sms, io->dnode_params, &dz0, st,
+                                         &gp0))
+        return rc;
+      dmbar = const_cast<float*>(gp0);      // [N][dm]
+      dxdirect = const_cast<float*>(dz0);   // [N][dx] (dx % 4 == 0: no pad columns)
+    } else if (p.nhoist) {
       // first layer of gamma hoisted (Plan::nhoist): inner backward on Q' gives g = d(U + V); the two projections' backward
       // then produce exactly what this phase owes: dx_direct (from U = x Wx + b1) and dmbar (from V = mbar Wm)
       ProfScope prof(NGPDE_PROF_BWD_NODE, st);

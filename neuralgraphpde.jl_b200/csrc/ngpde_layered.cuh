@@ -194,13 +194,18 @@ __global__ void assemble_kernel(Gather g, long long rows, int d0, int ld0, int v
   *reinterpret_cast<float4*>(Z + (size_t)r * ld0 + f) = v;
 }
 
-// u = p + b (kept when `U` is given), z = act(u);  P, U, Zout are [rows][n]; U / Zout may alias P
+// u = p (+ add) + b (kept when `U` is given), z = act(u);  P, add, U, Zout are [rows][n]; U / Zout may alias P.  `add` is
+// GNOConv's aggregated message entering the node update before the activation (layers.jl:536-547): (W x + mbar) + b.
 __global__ void bias_act_kernel(const float* P, const float* __restrict__ bias, int act, long long total, int n,
-                                float* U, float* Zout) {
+                                float* U, float* Zout, const float* __restrict__ add = nullptr) {
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= total) return;
   const int c = (int)(i4 % n);
   float4 v = *reinterpret_cast<const float4*>(P + i4);
+  if (add) {
+    const float4 a = *reinterpret_cast<const float4*>(add + i4);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
   if (bias) {
     v.x += bias[c]; v.y += bias[c + 1]; v.z += bias[c + 2]; v.w += bias[c + 3];
   }
@@ -421,7 +426,7 @@ inline unsigned blocks(long long total, int per) { return (unsigned)((total + pe
 // the last layer is written to `out` ([rows][dims[L]]) when given, else to a scratch buffer when `last` is asked for; *last
 // then points at it.  keep == false: ping-pong buffers in sbase only.
 inline int run_forward(const Phase& ph, const Ws& w, char* kbase, char* sbase, const Gather& g, int64_t rows, const float* params,
-                       bool keep, float* out, const float** last, cudaStream_t st) {
+                       bool keep, float* out, const float** last, cudaStream_t st, const float* addend = nullptr) {
   const MlpDev& m = ph.mlp;
   float* wp = reinterpret_cast<float*>((keep ? kbase : sbase) + w.wp);
   pack_weights_kernel<<<std::min(256u, blocks(ph.w_floats, 256)), 256, 0, st>>>(params, m, ph, wp);
@@ -438,17 +443,18 @@ inline int run_forward(const Phase& ph, const Ws& w, char* kbase, char* sbase, c
     const float* bias = m.b_off[l] >= 0 ? params + m.b_off[l] : nullptr;
     const long long total = (long long)rows * n;
     const bool lastl = l + 1 == m.L;
+    const float* add = lastl ? addend : nullptr;  // enters the last layer before its activation
     if (keep) {
       float* zn = nullptr;
       if (!lastl) zn = reinterpret_cast<float*>(kbase + w.z[l + 1]);
       else if (out) zn = out;
       else if (last && m.act[l] != NGPDE_ACT_IDENTITY) zn = reinterpret_cast<float*>(sbase + w.za);
-      if (bias || zn) bias_act_kernel<<<blocks(total / 4, 256), 256, 0, st>>>(u, bias, m.act[l], total, n, u, zn);
+      if (bias || zn || add) bias_act_kernel<<<blocks(total / 4, 256), 256, 0, st>>>(u, bias, m.act[l], total, n, u, zn, add);
       z = zn ? zn : u;
     } else {
       float* zo = (lastl && out) ? out : u;
-      if (bias || m.act[l] != NGPDE_ACT_IDENTITY || zo != u)
-        bias_act_kernel<<<blocks(total / 4, 256), 256, 0, st>>>(u, bias, m.act[l], total, n, nullptr, zo);
+      if (bias || add || m.act[l] != NGPDE_ACT_IDENTITY || zo != u)
+        bias_act_kernel<<<blocks(total / 4, 256), 256, 0, st>>>(u, bias, m.act[l], total, n, nullptr, zo, add);
       other = z;
       z = zo;
     }
@@ -462,7 +468,8 @@ inline int run_forward(const Phase& ph, const Ws& w, char* kbase, char* sbase, c
 // row_of, dmbar [N][dims[L]] indexed through the edge's destination (mean: divided by the in-degree).  Leaves dZ0 in *dz0
 // ([rows][ld[0]]) when need_dz0, and the parameter gradients in dparams (the flat layout of `params`).
 inline int run_backward(const Phase& ph, const Ws& w, char* kbase, char* sbase, int64_t rows, const float* Gin, const int* row_of,
-                        const int* rowptr_mean, bool need_dz0, int num_sms, float* dparams, const float** dz0, cudaStream_t st) {
+                        const int* rowptr_mean, bool need_dz0, int num_sms, float* dparams, const float** dz0, cudaStream_t st,
+                        const float** gp0 = nullptr) {
   const MlpDev& m = ph.mlp;
   const float* wp = reinterpret_cast<const float*>(kbase + w.wp);
   float* ga = reinterpret_cast<float*>(sbase + w.ga);
@@ -490,6 +497,7 @@ inline int run_backward(const Phase& ph, const Ws& w, char* kbase, char* sbase, 
     }
   }
   if (dz0) *dz0 = g;
+  if (gp0) *gp0 = ga;  // G * act'(U) of layer 0 (a one-layer phase: the cotangent of an addend to its pre-activation)
   NGPDE_CUDA_TRY(cudaGetLastError());
   return NGPDE_OK;
 }
