@@ -385,9 +385,13 @@ def strong_c4(args, rank, world, dev, peaks):
         step()
         y_p, dx_p = pr.y_owned.clone(), pr.dx_owned.clone()
         dp_p = runner.dparams.clone()
-        del pr, runner
+        del pr, runner, step   # (`step` is the partitioned runner's bound method: it keeps its workspaces alive)
+        import gc
+        gc.collect()
         torch.cuda.empty_cache()
-        full = engine.RhsRunner(w.layer, w.x, w.ps, w.st)   # the same call on the whole graph, on this rank's GPU
+        # the same call on the whole graph, on this rank's GPU; without the forward->backward state buffer (31 GB at 1M nodes):
+        # the backward recomputes instead, bit-identical results (tests/test_gpu_parity.py)
+        full = engine.RhsRunner(w.layer, w.x, w.ps, w.st, use_state=False)
         full.dy.copy_(dy_full.T)
         full.step()
         own = pl.owned_global.to(dev)

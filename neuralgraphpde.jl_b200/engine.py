@@ -18,7 +18,7 @@ Tensor = torch.Tensor
 
 class RhsRunner:
     def __init__(self, layer, x: Tensor, ps, st, use_cuda_graph: bool = False, share: Optional["RhsRunner"] = None,
-                 dparams: Optional[Tensor] = None):
+                 dparams: Optional[Tensor] = None, use_state: bool = True):
         """`share`: another runner of the same layer / graph whose parameter buffers and workspaces this one uses too
         (the stages of one Runge-Kutta step: same parameters, calls strictly one after the other)."""
         if not hasattr(layer, "prepare"):
@@ -68,7 +68,8 @@ class RhsRunner:
         with torch.cuda.device(dev):
             nstate = self.lib.ngpde_conv_state_bytes(self.handle, C.byref(self.desc))
         # forward -> backward state (hoisted first-layer projections): private to this runner, like mbar
-        self.state = torch.empty(int(nstate), dtype=torch.uint8, device=dev) if nstate else None
+        # (use_state=False: io.state stays NULL and the backward recomputes what it needs -- same results, less memory)
+        self.state = torch.empty(int(nstate), dtype=torch.uint8, device=dev) if (nstate and use_state) else None
         p = ops._ptr
         self.io = _lib.ConvIO(x=p(self.x), snode=p(self.snode), edata=p(self.edata), theta=p(self.theta),
                               phi_params=p(self.phi), node_params=p(self.node), mbar=p(self.mbar), y=p(self.y),
