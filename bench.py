@@ -267,7 +267,9 @@ def roofline_block(workload, w, prof, K, paths, step_ms, peaks, edges_launch, no
         "frac": ach_tflops / peaks["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peaks["source"] + " bf16 cuBLAS burst (MEASURED_PEAKS.json)",
         "pipe": ("tcgen05 3xTF32 (fp32-accurate split: 3 TF32 MMAs per product; peak = bf16 peak / 6)" if on_tc else
-                 "fp32 FFMA (fp32-accurate; tolerance 1e-5 excludes plain TF32/BF16)"),
+                 ("mixed: tcgen05 3xTF32 GEMMs (phi hidden layers, T, mbar, dB) + fp32 FFMA per-destination kernel; fractions "
+                  "quoted against the fp32 FFMA peak" if factored else
+                  "fp32 FFMA (fp32-accurate; tolerance 1e-5 excludes plain TF32/BF16)")),
         "pipe_peak_tflops": pipe_peak, "pipe_frac": ach_tflops / pipe_peak,
         "kernel_paths": {k: {1: "tcgen05", 0: "ffma", 2: "factored (ffma + fp32 gemm)", 3: "tcgen05 GEMM per Dense layer", -1: "none"}[v] for k, v in paths.items()},
         "avg_launch_ms": dom_ms, "algorithmic_flops_per_launch": alg_flops,

@@ -104,6 +104,9 @@ outdim(model) = Int(dense_layers(model)[end].out_dims)
 
 # ---- library ----
 ngpde_version() = ccall((:ngpde_version, libngpde), Cint, ())
+# process-wide switches (include/ngpde.h): all default to 1 except OPT_DEBUG_SKIP; OPT_LAYERED / OPT_GNO_LAYERED choose the
+# GEMM-per-Dense-layer evaluation of wide MLPs / of the factored GNOConv (more workspace, see INTEGRATION.md)
+const OPT_TENSOR_CORES, OPT_GNO_FACTORED, OPT_DEBUG_SKIP, OPT_HOIST, OPT_LAYERED, OPT_GNO_LAYERED = Int32.(0:5)
 set_option(option::Integer, value::Integer) = check(ccall((:ngpde_set_option, libngpde), Cint, (Int32, Int32), option, value))
 
 # ---- graph handle ----

@@ -36,6 +36,25 @@ def test_library_exports_every_declared_symbol():
     assert lib.ngpde_version() == 200
 
 
+def test_enum_values_agree_between_header_python_and_julia_bindings():
+    """The aggregation / option codes are part of the C ABI: include/ngpde.h is the source, the ctypes mirror (_lib.py) and the
+    Julia binding (julia/NeuralGraphPDEB200/src/capi.jl) must carry the same numbers."""
+    header = open(os.path.join(ROOT, "include", "ngpde.h")).read()
+    vals = {k: int(v) for k, v in re.findall(r"\b(NGPDE_(?:AGGR|OPT)_[A-Z_]+)\s*=\s*(\d+)", header)}
+    assert vals["NGPDE_AGGR_SUM"] == 0 and vals["NGPDE_AGGR_PROD"] == 4
+    L = ngpde._lib
+    assert L.AGGR == {"+": vals["NGPDE_AGGR_SUM"], "sum": vals["NGPDE_AGGR_SUM"], "mean": vals["NGPDE_AGGR_MEAN"],
+                      "max": vals["NGPDE_AGGR_MAX"], "min": vals["NGPDE_AGGR_MIN"], "*": vals["NGPDE_AGGR_PROD"],
+                      "prod": vals["NGPDE_AGGR_PROD"]}
+    assert (L.OPT_TENSOR_CORES, L.OPT_GNO_FACTORED, L.OPT_HOIST, L.OPT_LAYERED, L.OPT_GNO_LAYERED) == tuple(
+        vals[k] for k in ("NGPDE_OPT_TENSOR_CORES", "NGPDE_OPT_GNO_FACTORED", "NGPDE_OPT_HOIST", "NGPDE_OPT_LAYERED",
+                          "NGPDE_OPT_GNO_LAYERED"))
+    jl = open(os.path.join(ROOT, "julia", "NeuralGraphPDEB200", "src", "capi.jl")).read()
+    assert "AGGR_SUM, AGGR_MEAN, AGGR_MAX, AGGR_MIN, AGGR_PROD = Int32.(0:4)" in jl
+    m = re.search(r"const OPT_TENSOR_CORES, OPT_GNO_FACTORED, OPT_DEBUG_SKIP, OPT_HOIST, OPT_LAYERED, OPT_GNO_LAYERED = Int32\.\((\d):(\d)\)", jl)
+    assert m and (int(m.group(1)), int(m.group(2))) == (0, 5)
+
+
 def test_gcn_state_and_params():  # runtests.jl:16-25
     g = toy()
     l = GCNConv((3, 5), initialgraph=g)
